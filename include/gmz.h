@@ -1,0 +1,151 @@
+/*
+ * gmz.h -- C ABI of the B200-native batched Gumbel-MCTS self-play engine.
+ *
+ * This is the drop-in boundary for the reference's search hot path
+ * (Datou/Datou-gomoku-muzero).  The reference has no FFI: its seam is the Python
+ * class pair AlphaZeroMCTS / MuZeroMCTS (mcts.py:191-362) plus the inference
+ * queue protocol (mcts.py:73-85, workers.py:314-373).  Each entry point below
+ * names the reference code it replaces; datou_gomoku_muzero_b200/{mcts,engine}.py
+ * rebuild the reference classes on top through ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *    the parameter name ends in _host.  The caller (PyTorch) owns every buffer,
+ *    including the engine workspace; the library never allocates device memory.
+ *  - every call that launches work takes the cudaStream_t to launch on
+ *    (gmz_stream, passed as void*) and is asynchronous with respect to the host.
+ *  - return value: 0 = OK, non-zero = error; gmz_last_error() gives the text
+ *    (thread-local).  There is no CPU fallback behind any entry point.
+ *  - G = num_games, A = board_size^2, S = num_simulations, K = num_top_actions.
+ *    Actions are r*board_size + c.  "None" last move = -1.
+ */
+#ifndef GMZ_H
+#define GMZ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMZ_VERSION 100
+#define GMZ_MODE_ALPHAZERO 0 /* AlphaZeroMCTS, mcts.py:191-280 */
+#define GMZ_MODE_MUZERO 1    /* MuZeroMCTS,   mcts.py:283-362 */
+#define GMZ_MAX_BOARD 19
+#define GMZ_MAX_TOP_ACTIONS 32
+#define GMZ_WINNER_NONE 2 /* get_game_ended() returned None (game.py:60-63) */
+
+#define GMZ_F32 0
+#define GMZ_F64 1
+#define GMZ_BF16 2
+
+typedef struct gmz_engine gmz_engine;
+typedef void *gmz_stream;
+
+/* The subset of config.py the search reads (config.py:18-34). */
+typedef struct gmz_config {
+    int32_t board_size;      /* BOARD_SIZE  <= GMZ_MAX_BOARD */
+    int32_t n_in_row;        /* N_IN_ROW */
+    int32_t num_simulations; /* NUM_SIMULATIONS, 1..32767 */
+    int32_t num_top_actions; /* NUM_TOP_ACTIONS, 1..GMZ_MAX_TOP_ACTIONS */
+    int32_t mode;            /* GMZ_MODE_* (MCTS_IMPLEMENTATION) */
+    int32_t num_games;       /* G: concurrent game trees held by this engine */
+    int32_t max_moves;       /* trajectory capacity per game (0 = board_size^2) */
+    int32_t reserved;
+    double c_visit;          /* C_VISIT */
+    double c_scale;          /* C_SCALE */
+    double minmax_delta;     /* VALUE_MINMAX_DELTA */
+    double discount;         /* DISCOUNT */
+} gmz_config;
+
+int gmz_version(void);
+const char *gmz_last_error(void);
+
+/* Bytes of device workspace gmz_create needs (node pools + per-game state). */
+size_t gmz_workspace_bytes(const gmz_config *cfg);
+
+/* Replaces AlphaZeroMCTS(...) / MuZeroMCTS(...) construction (mcts.py:51-56,
+ * workers.py:134-142).  `workspace` must stay alive until gmz_destroy and be
+ * 256-byte aligned; it is zero-initialised by gmz_create on `stream`. */
+int gmz_create(const gmz_config *cfg, void *workspace, size_t workspace_bytes, gmz_stream stream, gmz_engine **out);
+int gmz_destroy(gmz_engine *e);
+
+/* ---- root positions ------------------------------------------------------ */
+/* Load G root positions: what search() reads off `game` (mcts.py:203,213):
+ * boards int8 [G,A] in {-1,0,+1}, players int8 [G] (+-1), last_moves int32 [G]
+ * (-1 = None), move_counts int32 [G].  A full board makes that game inactive
+ * (search() sentinel, mcts.py:214-215). */
+int gmz_set_roots(gmz_engine *e, const int8_t *boards, const int8_t *players, const int32_t *last_moves,
+                  const int32_t *move_counts, gmz_stream stream);
+/* GomokuGame.reset() (game.py:8-11) for every game with mask[g] != 0 (NULL = all). */
+int gmz_games_reset(gmz_engine *e, const uint8_t *mask, gmz_stream stream);
+/* GomokuGame.get_board_state at the roots (game.py:12-17): obs [G,3,N,N]. */
+int gmz_root_obs(gmz_engine *e, void *obs, int obs_dtype, gmz_stream stream);
+/* Read the root positions back (boards int8 [G,A], players, last_moves, move_counts; any may be NULL). */
+int gmz_get_roots(gmz_engine *e, int8_t *boards, int8_t *players, int32_t *last_moves, int32_t *move_counts,
+                  gmz_stream stream);
+
+/* ---- one search, step by step (external evaluator) ------------------------ */
+/* Root expansion + first backup + Gumbel top-k + halving schedule
+ * (mcts.py:217-226): logits f32 [G,A], values [G] (value_dtype GMZ_F32/F64),
+ * gumbel f64 [G,A] = the np.random.gumbel(0,1,A) draw of each search. */
+int gmz_root_expand(gmz_engine *e, const float *logits, const void *values, int value_dtype,
+                    const double *gumbel, gmz_stream stream);
+/* AlphaZero mode: _select_leaf + path replay on the real board + leaf
+ * observation (mcts.py:232-251).  leaf_obs [G,3,N,N]; optional int32 [G]
+ * out_leaf_action / out_leaf_depth for tracing.  Games whose search is
+ * complete (sim_count >= S) or inactive write a zero observation. */
+int gmz_select(gmz_engine *e, void *leaf_obs, int obs_dtype, int32_t *out_leaf_action, int32_t *out_leaf_depth,
+               gmz_stream stream);
+/* MuZero mode: the len(selected_children_actions) identical selections of
+ * mcts.py:326-332, deduplicated.  Outputs int32 [G]: parent_slot (index of the
+ * parent's hidden state, g*S + node), action, child_slot (where the evaluator's
+ * next hidden state belongs), or -1 for games with nothing to evaluate. */
+int gmz_select_mz(gmz_engine *e, int32_t *out_parent_slot, int32_t *out_action, int32_t *out_child_slot,
+                  int32_t *out_leaf_depth, gmz_stream stream);
+/* leaf.expand + _backpropagate + sim_count update + sequential halving
+ * (mcts.py:260-268 / 340-350): logits f32 [G,A], values [G], rewards [G]
+ * (same dtype as values; NULL = 0.0, AlphaZero mode). */
+int gmz_expand_backup(gmz_engine *e, const float *logits, const void *values, const void *rewards,
+                      int value_dtype, gmz_stream stream);
+/* Decision phase (mcts.py:271-280): policy f64 [G,A], value f64 [G], action
+ * int32 [G] (-1 for inactive games), optional visits int32 [G,A] (root child
+ * visit counts).  Any output may be NULL. */
+int gmz_finalize(gmz_engine *e, double *policy, double *value, int32_t *action, int32_t *visits, gmz_stream stream);
+
+/* ---- E0, the fixed deterministic evaluator --------------------- */
+/* Stand-alone evaluator kernel over observations obs f32 [B,3,N,N] ->
+ * logits f32 [B,A], values f64 [B] (the device twin of tests/golden/e0_py.py). */
+int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint64_t seed, int logit_div,
+                    float *logits, double *values, gmz_stream stream);
+/* Whole search (root evaluation + S-1 simulations) in ONE persistent kernel
+ * with E0 inlined: the tree-only fast path.  gumbel f64 [G,A]; optional int32
+ * [G,S] traces (leaf action / depth per evaluation).  Follow with gmz_finalize. */
+int gmz_search_e0(gmz_engine *e, const double *gumbel, uint64_t seed, int logit_div,
+                  int32_t *trace_leaf_action, int32_t *trace_leaf_depth, gmz_stream stream);
+/* Gumbel(0,1) noise on device from a counter-based generator: out f64 [n],
+ * element i uses counter (offset + i).  (Parity runs pass NumPy's draw instead.) */
+int gmz_fill_gumbel(double *out, size_t n, uint64_t seed, uint64_t offset, gmz_stream stream);
+
+/* ---- self-play game step --------------------------------------------------- */
+/* game.do_move(action) + game.get_game_ended() on the roots (workers.py:178-181,
+ * game.py:20-63): actions int32 [G] (<0 = skip that game); out_winner int32 [G]
+ * = +-1, 0 (draw) or GMZ_WINNER_NONE. */
+int gmz_game_step(gmz_engine *e, const int32_t *actions, int32_t *out_winner, gmz_stream stream);
+
+/* ---- prioritized replay: SumTree (replay_buffer.py:4-106) ------------------- */
+/* tree f64 [2*capacity-1] lives in caller memory.  Sequential reference
+ * semantics are preserved bit for bit (each node receives its += in batch order). */
+/* update_priorities / add: tree_idx int64 [n], priorities f64 [n], applied in order. */
+int gmz_per_update(double *tree, int64_t capacity, const int64_t *tree_idx, const double *priorities, int n,
+                   gmz_stream stream);
+/* sample(): u01 f64 [B] uniform draws; outputs tree_idx int64 [B], priority f64 [B],
+ * is_weights f32 [B] (already divided by the batch max). */
+int gmz_per_sample(const double *tree, int64_t capacity, int64_t count, const double *u01, int batch, double beta,
+                   int64_t *out_tree_idx, double *out_priority, float *out_weights, gmz_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMZ_H */

@@ -1,0 +1,359 @@
+"""Generate golden vectors by importing the UNMODIFIED reference from /root/reference.
+
+Runs only in the build container (the reference does not travel to the GPU box); the .npz
+files it writes next to itself are committed and are what tests/ read.  Usage:
+
+    python tests/golden/make_golden.py all          # every group (a few minutes)
+    python tests/golden/make_golden.py search_az | search_mz | selfplay | game | per | tactics
+
+Nothing here is copied from the reference: the reference is imported and driven through its
+public interface with (a) the E0 evaluator behind its queue protocol and (b) np.random.seed
+so the Gumbel noise it draws is reproducible (RandomState(seed).gumbel(0, 1, A)).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("GMZ_REFERENCE", "/root/reference")
+sys.path.insert(0, HERE)
+sys.dont_write_bytecode = True
+
+
+def _import_reference(board_size, n_in_row=5):
+    """config must be mutated before `game` is imported (game.py:5 binds defaults)."""
+    sys.path.insert(0, os.path.join(HERE, "_stubs"))
+    sys.path.insert(0, REF)
+    from config import config
+    config.BOARD_SIZE = board_size
+    config.N_IN_ROW = n_in_row
+    config.ACTION_SPACE_SIZE = board_size * board_size
+    import game, mcts  # noqa
+    return config, game, mcts
+
+
+def _apply(config, p):
+    config.NUM_SIMULATIONS = p["S"]
+    config.NUM_TOP_ACTIONS = p["K"]
+    config.C_VISIT = p.get("c_visit", 30)
+    config.C_SCALE = p.get("c_scale", 1.0)
+    config.DISCOUNT = p.get("discount", 0.997)
+    config.VALUE_MINMAX_DELTA = p.get("delta", 1e-3)
+
+
+def _random_position(N, n_moves, rs, game_mod, n_in_row):
+    g = game_mod.GomokuGame(board_size=N, n_in_row=n_in_row)
+    cells = rs.permutation(N * N)[:n_moves]
+    for a in cells:
+        g.do_move(int(a))
+    return g
+
+
+def _search_cases(N):
+    A = N * N
+    base = dict(S={6: 50, 9: 100, 15: 400}[N], K=16)
+    cases = []
+    for n_moves in [0, 1, 2, 7, A // 3, A // 2, A - 20, A - 9, A - 3, A - 1]:
+        cases.append(dict(base, n_moves=n_moves))
+    for K in [1, 2, 4, 5, 8, 32]:
+        cases.append(dict(base, K=K, n_moves=4))
+    for S in [2, 15, 17, 33]:
+        cases.append(dict(base, S=S, n_moves=3))
+        cases.append(dict(base, S=S, n_moves=A - 6))
+    cases.append(dict(base, n_moves=6, logit_div=4))
+    cases.append(dict(base, n_moves=6, logit_div=2))
+    cases.append(dict(base, n_moves=5, c_visit=50, c_scale=0.1))
+    cases.append(dict(base, n_moves=5, discount=1.0, delta=0.01))
+    cases.append(dict(base, n_moves=5, kind=1, const_value=0.5))       # MockModel
+    cases.append(dict(base, n_moves=5, kind=1, const_value=1.5, const_reward=0.25))  # exercises the clip
+    if N == 15:
+        cases = cases[:10] + cases[10:16:2] + cases[-6:]
+    return cases
+
+
+def gen_search(mode_name, N):
+    from e0_py import E0Queue
+    config, game_mod, mcts = _import_reference(N)
+    Engine = mcts.AlphaZeroMCTS if mode_name == "az" else mcts.MuZeroMCTS
+    A = N * N
+    rows = []
+    for ci, p in enumerate(_search_cases(N)):
+        _apply(config, p)
+        seed = 1000 * N + ci
+        rs = np.random.RandomState(seed)
+        g = _random_position(N, p["n_moves"], rs, game_mod, 5)
+        q = E0Queue(seed=seed, logit_div=p.get("logit_div", 16), kind=p.get("kind", 0),
+                    const_value=p.get("const_value", 0.5), const_reward=p.get("const_reward", 0.0))
+        q.set_action_space(A)
+        eng = Engine(0, q, q)
+        # capture the root Node and the per-evaluation leaf (action, depth)
+        made = []
+        OrigNode = mcts.Node
+
+        class RecNode(OrigNode):
+            def __init__(self, action=None, parent=None):
+                super().__init__(action, parent)
+                if parent is None:
+                    made.append(self)
+        mcts.Node = RecNode
+        trace_a, trace_d = [], []
+        orig_select = eng._select_leaf
+
+        def traced(root, valid, mm, _o=orig_select):
+            leaf, act = _o(root, valid, mm)
+            d, n = 0, leaf
+            while n.parent is not None:
+                d += 1
+                n = n.parent
+            trace_a.append(int(act)); trace_d.append(d)
+            return leaf, act
+        eng._select_leaf = traced
+        batch_sizes = []
+        orig_rec = eng._remote_recurrent_inference_batch
+
+        def rec_batch(h, acts, _o=orig_rec):
+            batch_sizes.append(len(acts))
+            return _o(h, acts)
+        eng._remote_recurrent_inference_batch = rec_batch
+        board0 = g.board.copy()
+        np.random.seed(seed)
+        policy, value, action = eng.search(g)
+        mcts.Node = OrigNode
+        assert np.array_equal(board0, g.board), "search mutated the game"
+        gumbel = np.random.RandomState(seed).gumbel(0, 1, A)
+        root = made[0]
+        visits = np.zeros(A, np.int32)
+        for a, ch in root.children.items():
+            visits[int(a)] = ch.visit_count
+        if mode_name == "mz":  # K selections per evaluation reach the same leaf: keep the first of each batch
+            starts = np.concatenate([[0], np.cumsum(batch_sizes)[:-1]]).astype(int) if batch_sizes else []
+            for s0, bs in zip(starts, batch_sizes):
+                assert len(set(zip(trace_a[s0:s0 + bs], trace_d[s0:s0 + bs]))) == 1, "batch reached >1 leaf"
+            ta, td = [trace_a[i] for i in starts], [trace_d[i] for i in starts]
+        else:
+            ta, td = trace_a, trace_d
+        lm = -1 if g.last_move is None else int(g.last_move[0]) * N + int(g.last_move[1])
+        rows.append(dict(
+            params=np.array([N, 5, p["S"], p["K"], p.get("kind", 0), p.get("logit_div", 16), seed], np.int64),
+            fparams=np.array([p.get("c_visit", 30), p.get("c_scale", 1.0), p.get("delta", 1e-3),
+                              p.get("discount", 0.997), p.get("const_value", 0.5), p.get("const_reward", 0.0)], np.float64),
+            board=board0.astype(np.int8), player=int(g.current_player), last_move=lm, move_count=int(g.move_count),
+            gumbel=gumbel, policy=np.asarray(policy, np.float64), value=float(value), action=int(action),
+            visits=visits, root_n=int(root.visit_count), root_w=float(root.value_sum),
+            n_initial=q.n_initial, n_recurrent=q.n_recurrent,
+            leaf_actions=np.array(ta, np.int32), leaf_depths=np.array(td, np.int32),
+            batch_sizes=np.array(batch_sizes, np.int32)))
+        print(f"[{mode_name} N={N}] case {ci}: S={p['S']} K={p['K']} moves={p['n_moves']} -> action {action} "
+              f"value {float(value):+.6f} maxvisit {visits.max()} evals {q.n_initial}+{q.n_recurrent}", flush=True)
+    out = {}
+    for i, r in enumerate(rows):
+        for k, v in r.items():
+            out[f"c{i}_{k}"] = v
+    out["n_cases"] = len(rows)
+    np.savez_compressed(os.path.join(HERE, f"search_{mode_name}_{N}.npz"), **out)
+
+
+def gen_selfplay(N, S, seed, mode_name="az"):
+    """One whole game through the reference's own universal_worker (workers.py:129-241)."""
+    from e0_py import E0Queue
+    import queue
+    config, game_mod, mcts = _import_reference(N)
+    config.NUM_SIMULATIONS = S
+    config.NUM_TOP_ACTIONS = 16
+    config.MCTS_IMPLEMENTATION = "AlphaZero" if mode_name == "az" else "MuZero"
+    import workers
+
+    class Flag:
+        def __init__(self): self.v = False
+        def is_set(self): return self.v
+        def set(self): self.v = True
+
+    class Val:
+        def __init__(self, v): self.value = v
+
+    class Sink:
+        def __init__(self, on_put=None): self.items, self.on_put = [], on_put
+        def put(self, x):
+            self.items.append(x)
+            if self.on_put: self.on_put()
+        def full(self): return False
+
+    shutdown = Flag()
+    data_q = Sink(on_put=shutdown.set)
+    q = E0Queue(seed=seed, logit_div=16)
+    q.set_action_space(N * N)
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp()
+    os.chdir(tmp)
+    try:
+        np.random.seed(seed)
+        workers.universal_worker(0, Val(0), data_q, Sink(), Sink(), shutdown, q, q, Sink(), Sink(), Val(7),
+                                 queue.Queue(), Flag())
+    finally:
+        os.chdir(cwd)
+    rec, slices, version = data_q.items[0]
+    T = len(rec.actions)
+    U = config.NUM_UNROLL_STEPS
+    out = dict(
+        params=np.array([N, 5, S, 16, seed, U, config.N_STEPS, version], np.int64),
+        discount=float(config.DISCOUNT),
+        actions=np.array(rec.actions, np.int32),
+        rewards=np.array(rec.rewards, np.float64),
+        values_targets=np.array(rec.values, np.float64),
+        policies=np.stack(rec.policies).astype(np.float64),
+        boards=np.stack(rec.board_states).astype(np.int8),
+        observations=np.stack(rec.observations).astype(np.float32),
+        n_slices=len(slices),
+        slice_obs=np.stack([s.observation for s in slices]),
+        slice_act=np.stack([s.action_history for s in slices]),
+        slice_rew=np.stack([s.reward_history for s in slices]),
+        slice_pi=np.stack([s.policy_history for s in slices]),
+        slice_val=np.stack([s.value_history for s in slices]),
+    )
+    out["slice_dtypes"] = np.array([str(slices[0].observation.dtype), str(slices[0].action_history.dtype),
+                                    str(slices[0].reward_history.dtype), str(slices[0].policy_history.dtype),
+                                    str(slices[0].value_history.dtype)])
+    # the search values (bootstrap inputs) are not in the record: re-derive them by re-running
+    # the reference search on every stored position with the same noise stream
+    np.random.seed(seed)
+    eng = (mcts.AlphaZeroMCTS if mode_name == "az" else mcts.MuZeroMCTS)(0, q, q)
+    g = game_mod.GomokuGame(board_size=N, n_in_row=5)
+    sv = []
+    for t in range(T):
+        pol, val, act = eng.search(g)
+        assert act == rec.actions[t]
+        sv.append(float(val))
+        g.do_move(act)
+    out["search_values"] = np.array(sv, np.float64)
+    out["winner"] = int(g.get_game_ended())
+    print(f"[selfplay {mode_name} N={N} S={S}] T={T} winner={out['winner']} slices={len(slices)}", flush=True)
+    np.savez_compressed(os.path.join(HERE, f"selfplay_{mode_name}_{N}_{S}.npz"), **out)
+
+
+def gen_game():
+    """check_win / get_game_ended KATs (game.py:25-63): no upstream tests exist for these."""
+    rows = []
+    config, game_mod, _ = _import_reference(15)   # sizes are passed explicitly to GomokuGame below
+    for N, nir in [(6, 5), (9, 5), (15, 5), (15, 6), (9, 4)]:
+        rs = np.random.RandomState(7 * N + nir)
+        for k in range(400):
+            g = game_mod.GomokuGame(board_size=N, n_in_row=nir)
+            fill = rs.uniform(0.2, 1.0)
+            dens = rs.uniform(0.5, 0.9)   # biased colours make long runs likely
+            b = np.where(rs.rand(N, N) < fill, np.where(rs.rand(N, N) < dens, 1, -1), 0).astype(np.int8)
+            if k % 7 == 0:  # plant an exact run incl. overlines
+                L = int(rs.randint(nir - 1, nir + 3)); r0 = int(rs.randint(0, N)); c0 = int(rs.randint(0, max(1, N - L)))
+                b[r0, c0:c0 + L] = 1
+            g.board = b
+            occ = np.argwhere(b != 0)
+            if len(occ) == 0:
+                continue
+            r, c = occ[rs.randint(len(occ))]
+            g.last_move = (int(r), int(c))
+            g.move_count = int((b != 0).sum())
+            w = g.get_game_ended()
+            rows.append((N, nir, b.reshape(-1).copy(), int(r) * N + int(c), g.move_count, 2 if w is None else int(w),
+                         int(bool(g.check_win()))))
+    out = dict(n=len(rows))
+    out["N"] = np.array([r[0] for r in rows], np.int32)
+    out["nir"] = np.array([r[1] for r in rows], np.int32)
+    out["boards"] = np.array([np.pad(r[2], (0, 225 - len(r[2]))) for r in rows], np.int8)
+    out["last"] = np.array([r[3] for r in rows], np.int32)
+    out["move_count"] = np.array([r[4] for r in rows], np.int32)
+    out["ended"] = np.array([r[5] for r in rows], np.int32)
+    out["win"] = np.array([r[6] for r in rows], np.int32)
+    print(f"[game] {len(rows)} positions, {int(out['win'].sum())} wins, {(out['ended'] == 0).sum()} draws", flush=True)
+    np.savez_compressed(os.path.join(HERE, "game_kat.npz"), **out)
+
+
+def gen_per():
+    """SumTree / InMemoryReplayBuffer KATs (replay_buffer.py:4-106): no upstream tests exist."""
+    sys.path.insert(0, REF)
+    from config import config
+    import replay_buffer as rb
+    config.ENABLE_PER = True
+    out = {}
+    for ci, (cap, n_add, B, rounds) in enumerate([(8, 8, 4, 6), (37, 50, 8, 8), (1024, 700, 64, 6), (4096, 6000, 360, 5)]):
+        np.random.seed(100 + ci)
+        buf = rb.InMemoryReplayBuffer(cap)
+        log_idx, log_w, log_td, log_tree, log_u = [], [], [], [], []
+        rs = np.random.RandomState(55 + ci)
+        for i in range(n_add):
+            buf.add(i)
+            if i % 5 == 0 and len(buf) >= 1:   # interleave priority updates so max_priority moves
+                k = int(rs.randint(0, len(buf)))
+                buf.update_priorities([k + cap - 1], rs.randn(1).astype(np.float32) * 3)
+        out[f"p{ci}_tree_after_add"] = buf.sum_tree.tree.copy()
+        out[f"p{ci}_state_after_add"] = np.array([buf.sum_tree.write_ptr, buf.sum_tree.count], np.int64)
+        out[f"p{ci}_maxp_after_add"] = float(buf.max_priority)
+        for r in range(rounds):
+            st = np.random.get_state()
+            u = np.random.random_sample(B)      # the B doubles np.random.uniform will consume
+            np.random.set_state(st)
+            batch, idx, w = buf.sample(B)
+            td = rs.randn(B).astype(np.float32) * (2.0 if r % 2 else 0.05)
+            buf.update_priorities(idx, td)
+            log_u.append(u); log_idx.append(np.array(idx, np.int64)); log_w.append(w); log_td.append(td)
+            log_tree.append(buf.sum_tree.tree.copy())
+        out[f"p{ci}_params"] = np.array([cap, n_add, B, rounds], np.int64)
+        out[f"p{ci}_u"] = np.stack(log_u); out[f"p{ci}_idx"] = np.stack(log_idx)
+        out[f"p{ci}_w"] = np.stack(log_w); out[f"p{ci}_td"] = np.stack(log_td)
+        out[f"p{ci}_tree"] = np.stack(log_tree)
+        out[f"p{ci}_maxp"] = float(buf.max_priority)
+        out[f"p{ci}_data"] = np.array([-1 if d is None else d for d in buf.data], np.int64)
+        print(f"[per] case {ci}: cap={cap} adds={n_add} B={B} total={buf.sum_tree.total_priority():.6f}", flush=True)
+    out["beta"] = float(config.PER_BETA); out["eps"] = float(config.PER_EPSILON); out["n_cases"] = 4
+    np.savez_compressed(os.path.join(HERE, "per_kat.npz"), **out)
+
+
+def gen_tactics():
+    """find_winning_moves_rebuilt KATs (workers.py:49-123) incl. the boards of tests/test_winning_moves.py."""
+    config, game_mod, _ = _import_reference(15)
+    import workers
+    rows = []
+    rs = np.random.RandomState(3)
+    for k in range(120):
+        N = [9, 15][k % 2]
+        fill = rs.uniform(0.05, 0.5)
+        b = np.where(rs.rand(N, N) < fill, np.where(rs.rand(N, N) < 0.6, 1, -1), 0).astype(np.int8)
+        for player in (1, -1):
+            w = workers.find_winning_moves_rebuilt(b.copy(), player)
+            cls = np.zeros(N * N, np.int8)
+            for (r, c) in w["five"]: cls[r * N + c] = 1
+            for (r, c) in w["open_four"]: cls[r * N + c] = 2
+            for (r, c) in w["combo"]: cls[r * N + c] = 3
+            rows.append((N, player, np.pad(b.reshape(-1), (0, 225 - N * N)), np.pad(cls, (0, 225 - N * N))))
+    np.savez_compressed(os.path.join(HERE, "tactics_kat.npz"), n=len(rows),
+                        N=np.array([r[0] for r in rows], np.int32), player=np.array([r[1] for r in rows], np.int32),
+                        boards=np.array([r[2] for r in rows], np.int8), cls=np.array([r[3] for r in rows], np.int8))
+    print(f"[tactics] {len(rows)} boards", flush=True)
+
+
+def _sub(*args):
+    subprocess.check_call([sys.executable, os.path.abspath(__file__), *map(str, args)])
+
+
+if __name__ == "__main__":
+    cmd = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if cmd == "all":
+        for N in (6, 9, 15):
+            _sub("search_az", N); _sub("search_mz", N)
+        _sub("selfplay", 6, 36, 11, "az"); _sub("selfplay", 9, 100, 12, "az"); _sub("selfplay", 6, 50, 13, "mz")
+        _sub("game"); _sub("per"); _sub("tactics")
+    elif cmd in ("search_az", "search_mz"):
+        gen_search(cmd[-2:], int(sys.argv[2]))
+    elif cmd == "selfplay":
+        gen_selfplay(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5] if len(sys.argv) > 5 else "az")
+    elif cmd == "game":
+        gen_game()
+    elif cmd == "per":
+        gen_per()
+    elif cmd == "tactics":
+        gen_tactics()
+    else:
+        raise SystemExit(f"unknown group {cmd}")
