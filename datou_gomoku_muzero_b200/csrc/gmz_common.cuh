@@ -1,0 +1,142 @@
+// gmz_common.cuh -- shared types and warp-level helpers of the batched Gumbel-MCTS engine.
+//
+// Execution model: ONE WARP OWNS ONE GAME TREE.  Simulations inside a game are sequential
+// (the reference has exactly one simulation in flight per search, mcts.py:229-268, and visit
+// counts must be bit-exact), so the parallelism is across the G concurrent games.  Within a
+// warp the A actions of a node are spread over the 32 lanes: lane l owns actions
+// 128*j + 4*l + t (j < NC chunks, t < 4), i.e. one float4 of logits and one short4 of child
+// indices per chunk -- every row access is a fully coalesced 512-byte / 256-byte transaction.
+//
+// All parity-critical arithmetic is IEEE double with one rounding per operation
+// (__dadd_rn/__dmul_rn/__ddiv_rn; the file is also compiled with -fmad=false), mirroring the
+// reference's Python-float / NumPy-float64 arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+
+#define GMZ_FULL 0xffffffffu
+#define GMZ_MAX_PHASES 16
+#define GMZ_WORDS 8  // 64-bit words per bitboard held in GState (A <= 384 uses <= 6)
+
+// Per-game search + game state, one 1 KiB record per game (lane-indexed arrays so a warp
+// loads/stores it with coalesced accesses).
+struct __align__(128) GState {
+    u64 p1[GMZ_WORDS];        // stones of player +1 at the root        game.py:9 board
+    u64 m1[GMZ_WORDS];        // stones of player -1 at the root
+    u64 valid[GMZ_WORDS];     // empty cells at the root = valid_moves   mcts.py:213
+    double surv_g[32];        // gumbel noise of the initial top-k actions  mcts.py:221
+    int surv_n[32];           // visit count of the root child of each survivor
+    float surv_logit[32];     // root logit of each survivor
+    short surv_act[32];       // selected_children_actions (first n_surv) + eliminated ones (up to n_init)
+    short surv_child[32];     // node index of that root child, -1 if not created yet
+    double mm_min, mm_max;    // utils.MinMaxStats                          utils.py:6-25
+    int sim_count;            // mcts.py:228
+    int num_nodes;            // nodes allocated in this game's pool (root = node 0)
+    int phase;                // current_phase                              mcts.py:159
+    int next_thr;             // visit_num_for_next_phase
+    int n_surv;               // len(selected_children_actions)
+    int n_init;               // length of the initial top-k list
+    int to_move;              // game.current_player (+1 / -1)
+    int last_move;            // game.last_move as an action index, -1 = None
+    int move_count;           // game.move_count
+    int active;               // 0: no valid moves -> search() sentinel (mcts.py:214-215)
+    int leaf_parent;          // pending leaf (between select and expand_backup)
+    int leaf_action;
+    int leaf_depth;           // edges root -> leaf, 0 = nothing pending
+    int leaf_reps;            // number of backups the pending leaf receives (MuZero: n_surv)
+    int winner;               // get_game_ended(): +-1, 0 draw, 2 = None
+    int pad0;
+    char pad1[112];
+};
+static_assert(sizeof(GState) == 1024, "GState must be 1 KiB");
+
+// Kernel parameters (passed by value).
+struct Params {
+    int G, N, A, S, K, NW, AP, mode;   // NW = ceil(A/64) words in use, AP = padded row length (128*NC)
+    int n_in_row, max_moves, first_thr, n_phases;
+    int m_of_phase[GMZ_MAX_PHASES];      // current_num_top_actions after p halvings (mcts.py:168-169)
+    int extra_of_phase[GMZ_MAX_PHASES];  // int(extra_visit) of phase p            (mcts.py:173-180)
+    double c_visit, c_scale, delta, discount;
+    GState *gs;
+    float *logits;   // [G*S][AP]  node.policy_logits
+    short *child;    // [G*S][AP]  node.children -> node index, -1 = absent
+    int *nN;         // [G*S]      node.visit_count
+    double *nW;      // [G*S]      node.value_sum
+    double *nR;      // [G*S]      node.reward (MuZero mode only)
+    short *path;     // [G][S+2]   node ids root..leaf-parent of the pending simulation
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dclip1(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }  // np.clip(v,-1,1)
+
+__device__ __forceinline__ double warp_max_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(GMZ_FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(GMZ_FULL, v, o));
+    return v;
+}
+// xor-butterfly sum: a+b == b+a exactly, so every lane ends with the same bits
+__device__ __forceinline__ double warp_sum_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(GMZ_FULL, v, o));
+    return v;
+}
+// argmax with lowest-index tie-break (np.argmax, mcts.py:117)
+__device__ __forceinline__ void warp_argmax_lowidx(double &s, int &a)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double s2 = __shfl_xor_sync(GMZ_FULL, s, o);
+        int a2 = __shfl_xor_sync(GMZ_FULL, a, o);
+        if (s2 > s || (s2 == s && a2 < a)) { s = s2; a = a2; }
+    }
+}
+// argmax with highest-index tie-break (sorted(zip(scores, actions), reverse=True), mcts.py:225)
+__device__ __forceinline__ void warp_argmax_highidx(double &s, int &a)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double s2 = __shfl_xor_sync(GMZ_FULL, s, o);
+        int a2 = __shfl_xor_sync(GMZ_FULL, a, o);
+        if (s2 > s || (s2 == s && a2 > a)) { s = s2; a = a2; }
+    }
+}
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src) { return __shfl_sync(GMZ_FULL, v, src); }
+
+// ---------------------------------------------------------------------------------------------
+// E0, the fixed deterministic evaluator: splitmix64-style hashing of the observation.
+#define E0_GOLD 0x9E3779B97F4A7C15ULL
+#define E0_CV 0xD1B54A32D192ED03ULL
+#define E0_CA 0x8CB92BA72F3D8DD7ULL
+#define E0_CR 0xA24BAED4963EE407ULL
+
+__host__ __device__ __forceinline__ u64 mix64(u64 z)
+{
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+    z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return z;
+}
+// own_w / opp_w: lane w holds word w of the plane.  All lanes return the same hash.
+__device__ __forceinline__ u64 e0_hash_planes(u64 seed, u64 own_w, u64 opp_w, int nw, int last)
+{
+    u64 h = mix64(seed ^ E0_GOLD);
+    for (int w = 0; w < nw; ++w) h = mix64(h ^ shfl_u64(own_w, w));
+    for (int w = 0; w < nw; ++w) h = mix64(h ^ shfl_u64(opp_w, w));
+    return mix64(h ^ (u64)(long long)(last + 1));
+}
+__device__ __forceinline__ float e0_logit(u64 h, int a, float logit_div)
+{
+    int k = (int)(mix64(h + (u64)(a + 1) * E0_GOLD) >> 58);
+    return __fdiv_rn((float)(k - 32), logit_div);
+}
+__device__ __forceinline__ double e0_value(u64 h) { return (double)((int)((mix64(h ^ E0_CV) >> 40) % 33) - 16) / 16.0; }

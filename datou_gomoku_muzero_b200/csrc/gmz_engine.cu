@@ -1,0 +1,676 @@
+// gmz_engine.cu -- kernels and C ABI (include/gmz.h) of the batched Gumbel-MCTS engine.
+// sm_100a only; build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo ...
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/gmz.h"
+#include "gmz_tree.cuh"
+
+#define WARPS_PER_CTA 4
+#define CTA_THREADS (32 * WARPS_PER_CTA)
+
+static thread_local char g_err[512] = "";
+static int fail(const char *fmt, const char *a = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, a);
+    return 1;
+}
+extern "C" void gmz_set_error_(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+static int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
+struct gmz_engine {
+    gmz_config cfg;
+    Params p;
+    int NC;
+    size_t bytes;
+    void *workspace;
+};
+
+// ---------------------------------------------------------------------------------------------
+// root positions
+// ---------------------------------------------------------------------------------------------
+// boards int8 [G,A] -> bitboards; one warp per game, ballots pack 32 cells at a time.
+__global__ void __launch_bounds__(CTA_THREADS)
+k_set_roots(Params p, const int8_t *boards, const int8_t *players, const int32_t *last_moves, const int32_t *move_counts)
+{
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= p.G) return;
+    const int8_t *b = boards + (size_t)g * p.A;
+    u64 P = 0, M = 0, V = 0;
+    int nvalid = 0;
+    for (int w = 0; w < GMZ_WORDS; ++w) {
+        u64 pw = 0, mw = 0, vw = 0;
+        for (int h = 0; h < 2; ++h) {
+            const int a = 64 * w + 32 * h + lane;
+            const int c = a < p.A ? (int)b[a] : 2;
+            pw |= (u64)__ballot_sync(GMZ_FULL, c == 1) << (32 * h);
+            mw |= (u64)__ballot_sync(GMZ_FULL, c == -1) << (32 * h);
+            vw |= (u64)__ballot_sync(GMZ_FULL, c == 0) << (32 * h);
+        }
+        nvalid += __popcll(vw);
+        if (lane == w) { P = pw; M = mw; V = vw; }
+    }
+    GState *s = p.gs + g;
+    if (lane < GMZ_WORDS) { s->p1[lane] = P; s->m1[lane] = M; s->valid[lane] = V; }
+    if (lane == 0) {
+        s->to_move = players[g] >= 0 ? 1 : -1;
+        s->last_move = last_moves[g];
+        s->move_count = move_counts[g];
+        s->active = nvalid > 0;
+        s->sim_count = 0; s->num_nodes = 0; s->leaf_depth = 0; s->n_surv = 0; s->n_init = 0;
+        s->winner = GMZ_WINNER_NONE;
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS) k_games_reset(Params p, const uint8_t *mask)
+{
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= p.G) return;
+    if (mask && !mask[g]) return;
+    GState *s = p.gs + g;
+    if (lane < GMZ_WORDS) {
+        u64 v = 0;
+        const int lo = 64 * lane;
+        if (lo < p.A) v = (p.A - lo >= 64) ? ~0ull : ((1ull << (p.A - lo)) - 1ull);
+        s->p1[lane] = 0; s->m1[lane] = 0; s->valid[lane] = v;
+    }
+    if (lane == 0) {
+        s->to_move = 1; s->last_move = -1; s->move_count = 0; s->active = 1;
+        s->sim_count = 0; s->num_nodes = 0; s->leaf_depth = 0; s->n_surv = 0; s->n_init = 0;
+        s->winner = GMZ_WINNER_NONE;
+    }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS)
+k_get_roots(Params p, int8_t *boards, int8_t *players, int32_t *last_moves, int32_t *move_counts)
+{
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= p.G) return;
+    const GState *s = p.gs + g;
+    if (boards) {
+        for (int a = lane; a < p.A; a += 32) {
+            const u64 b = 1ull << (a & 63);
+            boards[(size_t)g * p.A + a] = (s->p1[a >> 6] & b) ? 1 : ((s->m1[a >> 6] & b) ? -1 : 0);
+        }
+    }
+    if (lane == 0) {
+        if (players) players[g] = (int8_t)s->to_move;
+        if (last_moves) last_moves[g] = s->last_move;
+        if (move_counts) move_counts[g] = s->move_count;
+    }
+}
+
+template <int NC, typename T>
+__global__ void __launch_bounds__(CTA_THREADS) k_root_obs(Params p, T *obs)
+{
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= p.G) return;
+    const GState *s = p.gs + g;
+    const u64 P = lane < GMZ_WORDS ? s->p1[lane] : 0ull, M = lane < GMZ_WORDS ? s->m1[lane] : 0ull;
+    const int tm = s->to_move;
+    obs_write<NC, T>(obs + (size_t)g * 3 * p.A, p.A, tm > 0 ? P : M, tm > 0 ? M : P, s->last_move, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stepwise search kernels (external evaluator)
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ void load_lane_logits(const float *src, int A, int lane, float *lg)
+{
+#pragma unroll
+    for (int i = 0; i < 4 * NC; ++i) {
+        const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
+        lg[i] = a < A ? src[a] : 0.0f;
+    }
+}
+__device__ __forceinline__ double load_value(const void *v, int dtype, int g)
+{
+    return dtype == GMZ_F64 ? ((const double *)v)[g] : (double)((const float *)v)[g];
+}
+
+template <int NC>
+__global__ void __launch_bounds__(CTA_THREADS)
+k_root_expand(Params p, const float *logits, const void *values, int vdtype, const double *gumbel)
+{
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= p.G) return;
+    WG w; wg_load(p, g, lane, w);
+    if (!w.active) return;
+    wg_valid_bits<NC>(w, lane);
+    float lg[4 * NC]; double gum[4 * NC];
+    load_lane_logits<NC>(logits + (size_t)g * p.A, p.A, lane, lg);
+#pragma unroll
+    for (int i = 0; i < 4 * NC; ++i) {
+        const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
+        gum[i] = a < p.A ? gumbel[(size_t)g * p.A + a] : 0.0;
+    }
+    root_init<NC>(p, w, lg, gum, load_value(values, vdtype, g), lane);
+    wg_store_search(p, lane, w);
+    if (lane == 0) p.gs[g].leaf_depth = 0;
+}
+
+template <int NC, bool MZ, typename T>
+__global__ void __launch_bounds__(CTA_THREADS)
+k_select(Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, int32_t *out_depth)
+{
+    // AZ: out_a = leaf action (trace).  MZ: out_a = parent slot, out_b = action, out_c = child slot.
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= p.G) return;
+    WG w; wg_load(p, g, lane, w);
+    const bool run = w.active && w.sim_count >= 1 && w.sim_count < p.S;
+    if (!run) {
+        if (!MZ && leaf_obs) {
+            T *o = leaf_obs + (size_t)g * 3 * p.A;
+            for (int a = lane; a < 3 * p.A; a += 32) o[a] = (T)0.0f;
+        }
+        if (lane == 0) {
+            if (out_a) out_a[g] = -1;
+            if (out_b) out_b[g] = -1;
+            if (out_c) out_c[g] = -1;
+            if (out_depth) out_depth[g] = 0;
+            p.gs[g].leaf_depth = 0;
+        }
+        return;
+    }
+    wg_valid_bits<NC>(w, lane);
+    short *path = p.path + (size_t)g * (p.S + 2);
+    u64 P = w.P, M = w.M; int colour = w.to_move;
+    int lp, la;
+    const int depth = descend<NC, MZ>(p, w, path, lane, lp, la, P, M, colour);
+    if (!MZ && leaf_obs)   // colour is now the player to move at the leaf; last move = la
+        obs_write<NC, T>(leaf_obs + (size_t)g * 3 * p.A, p.A, colour > 0 ? P : M, colour > 0 ? M : P, la, lane);
+    if (lane == 0) {
+        GState *s = p.gs + g;
+        s->leaf_parent = lp; s->leaf_action = la; s->leaf_depth = depth; s->leaf_reps = MZ ? w.n_surv : 1;
+        if (MZ) {
+            if (out_a) out_a[g] = (int32_t)(w.nbase + (size_t)lp);
+            if (out_b) out_b[g] = la;
+            if (out_c) out_c[g] = (int32_t)(w.nbase + (size_t)w.num_nodes);
+        } else if (out_a) out_a[g] = la;
+        if (out_depth) out_depth[g] = depth;
+    }
+}
+
+template <int NC, bool MZ>
+__global__ void __launch_bounds__(CTA_THREADS)
+k_expand_backup(Params p, const float *logits, const void *values, const void *rewards, int vdtype)
+{
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= p.G) return;
+    const GState *s = p.gs + g;
+    const int depth = s->leaf_depth;
+    if (!s->active || depth <= 0) return;
+    WG w; wg_load(p, g, lane, w);
+    const int lp = s->leaf_parent, la = s->leaf_action, reps = s->leaf_reps;
+    const short *path = p.path + (size_t)g * (p.S + 2);
+    float lg[4 * NC];
+    load_lane_logits<NC>(logits + (size_t)g * p.A, p.A, lane, lg);
+    const double value = load_value(values, vdtype, g);
+    const double reward = (MZ && rewards) ? load_value(rewards, vdtype, g) : 0.0;
+    const int nn = w.num_nodes;
+    node_write_row<NC>(p, w, nn, lg, lane);
+    if (lane == 0) p.child[(w.nbase + (size_t)lp) * (size_t)p.AP + la] = (short)nn;
+    w.num_nodes = nn + 1;
+    backup<MZ>(p, w, path, depth, nn, value, reward, reps, lane);
+    survivor_visit(w, depth, path, nn, la, reps, lane);
+    w.sim_count += reps;
+    __syncwarp();
+    if (halving_ready(p, w)) sequential_halving<MZ>(p, w, lane);
+    wg_store_search(p, lane, w);
+    if (lane == 0) p.gs[g].leaf_depth = 0;
+}
+
+// CPython set iteration order over the valid actions, to break ties of the final
+// max(visit_counts, key=visit_counts.get) the way the reference does (mcts.py:274-275).
+// Runs on one lane, only when the maximum visit count is not unique.  Restates
+// Objects/setobject.c (set_add_entry / set_table_resize / set_insert_clean).
+__device__ int pyset_first_max(const u64 *vw, int A, const short *nvis, int maxn, short *table /*2048*/)
+{
+    int mask = 7, fill = 0;
+    for (int i = 0; i < 8; ++i) table[i] = -1;
+    short *cur = table, *alt = table + 2048;   // two halves of a 4096-entry scratch
+    for (int a = 0; a < A; ++a) {
+        if (!((vw[a >> 6] >> (a & 63)) & 1ull)) continue;
+        unsigned i = (unsigned)a & mask, perturb = (unsigned)a, e;
+        for (;;) {
+            e = i;
+            int probes = (i + 9 <= (unsigned)mask) ? 9 : 0; bool found = false;
+            do { if (cur[e] < 0) { found = true; break; } ++e; } while (probes--);
+            if (found) break;
+            perturb >>= 5; i = (i * 5 + 1 + perturb) & mask;
+        }
+        cur[e] = (short)a; ++fill;
+        if (fill * 5 >= mask * 3) {
+            int newsize = 8; const int minused = fill * 4;
+            while (newsize <= minused) newsize <<= 1;
+            const int nmask = newsize - 1;
+            for (int j = 0; j < newsize; ++j) alt[j] = -1;
+            for (int j = 0; j <= mask; ++j) {
+                if (cur[j] < 0) continue;
+                const unsigned h2 = (unsigned)cur[j];
+                unsigned ii = h2 & nmask, pp = h2, ee;
+                for (;;) {
+                    ee = ii;
+                    if (alt[ee] < 0) break;
+                    bool ok = false;
+                    if (ii + 9 <= (unsigned)nmask) { for (int q = 0; q < 9; ++q) { ++ee; if (alt[ee] < 0) { ok = true; break; } } }
+                    if (ok) break;
+                    pp >>= 5; ii = (ii * 5 + 1 + pp) & nmask;
+                }
+                alt[ee] = cur[j];
+            }
+            short *t = cur; cur = alt; alt = t; mask = nmask;
+        }
+    }
+    for (int j = 0; j <= mask; ++j) if (cur[j] >= 0 && nvis[cur[j]] == maxn) return cur[j];
+    return -1;
+}
+
+template <int NC, bool MZ>
+__global__ void __launch_bounds__(CTA_THREADS)
+k_finalize(Params p, double *policy, double *value, int32_t *action, int32_t *visits)
+{
+    __shared__ short s_table[WARPS_PER_CTA][4096];
+    __shared__ short s_nvis[WARPS_PER_CTA][128 * NC];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_CTA + wi;
+    if (g >= p.G) return;
+    WG w; wg_load(p, g, lane, w);
+    if (!w.active || w.sim_count < 1) {   // sentinel (np.zeros(A), 0.0, -1), mcts.py:214-215
+        for (int a = lane; a < p.A; a += 32) {
+            if (policy) policy[(size_t)g * p.A + a] = 0.0;
+            if (visits) visits[(size_t)g * p.A + a] = 0;
+        }
+        if (lane == 0) { if (value) value[g] = 0.0; if (action) action[g] = -1; }
+        return;
+    }
+    wg_valid_bits<NC>(w, lane);
+    Row<NC> r;
+    row_load<NC, MZ>(p, w, 0, lane, r);
+    double x[4 * NC];
+    const double inv = row_softmax<NC>(p, w, r, x);
+    int bn = -1, ba = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 4 * NC; ++i) {
+        const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
+        s_nvis[wi][128 * (i >> 2) + 4 * lane + (i & 3)] = (short)r.n[i];
+        if (a < p.A) {
+            if (policy) policy[(size_t)g * p.A + a] = __dmul_rn(x[i], inv);
+            if (visits) visits[(size_t)g * p.A + a] = r.n[i];
+            if (((w.vb >> i) & 1u) && r.n[i] > bn) { bn = r.n[i]; ba = a; }
+        }
+    }
+    const int maxn = __reduce_max_sync(GMZ_FULL, bn);
+    int ties = 0;
+#pragma unroll
+    for (int i = 0; i < 4 * NC; ++i) ties += (((w.vb >> i) & 1u) && r.n[i] == maxn) ? 1 : 0;
+    ties = __reduce_add_sync(GMZ_FULL, ties);
+    int best = __reduce_min_sync(GMZ_FULL, bn == maxn ? ba : 0x7fffffff);
+    u64 vw[GMZ_WORDS];
+#pragma unroll
+    for (int k = 0; k < GMZ_WORDS; ++k) vw[k] = shfl_u64(w.V, k);
+    __syncwarp();
+    if (ties > 1) {
+        if (lane == 0) best = pyset_first_max(vw, p.A, s_nvis[wi], maxn, s_table[wi]);
+        best = __shfl_sync(GMZ_FULL, best, 0);
+    }
+    if (lane == 0) {
+        if (value) value[g] = __ddiv_rn(p.nW[w.nbase], (double)p.nN[w.nbase]);
+        if (action) action[g] = best;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// E0 evaluator kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS)
+k_e0_eval_obs(const float *obs, int B, int N, u64 seed, float logit_div, float *logits, double *values)
+{
+    const int lane = threadIdx.x & 31, b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int A = N * N, nw = (A + 63) / 64;
+    const float *o = obs + (size_t)b * 3 * A;
+    u64 own = 0, opp = 0; int last = -1;
+    for (int w = 0; w < nw; ++w) {
+        u64 ow = 0, pw = 0;
+        for (int h = 0; h < 2; ++h) {
+            const int a = 64 * w + 32 * h + lane;
+            const bool in = a < A;
+            ow |= (u64)__ballot_sync(GMZ_FULL, in && o[a] > 0.5f) << (32 * h);
+            pw |= (u64)__ballot_sync(GMZ_FULL, in && o[A + a] > 0.5f) << (32 * h);
+            const unsigned lb = __ballot_sync(GMZ_FULL, in && o[2 * A + a] > 0.5f);
+            if (lb && last < 0) last = 64 * w + 32 * h + (__ffs(lb) - 1);
+        }
+        if (lane == w) { own = ow; opp = pw; }
+    }
+    const u64 h = e0_hash_planes(seed, own, opp, nw, last);
+    for (int a = lane; a < A; a += 32) logits[(size_t)b * A + a] = e0_logit(h, a, logit_div);
+    if (lane == 0) values[b] = e0_value(h);
+}
+
+// The whole search of mcts.py:197-280 for one game per warp, E0 inlined: root evaluation,
+// Gumbel top-k, then S-1 x { select, replay, evaluate, expand, backup, halving }.
+template <int NC>
+__global__ void __launch_bounds__(CTA_THREADS)
+k_search_e0(Params p, const double *gumbel, u64 seed, float logit_div, int32_t *trace_a, int32_t *trace_d)
+{
+    extern __shared__ short s_path[];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_CTA + wi;
+    if (g >= p.G) return;
+    WG w; wg_load(p, g, lane, w);
+    if (!w.active) return;
+    wg_valid_bits<NC>(w, lane);
+    short *path = s_path + (size_t)wi * (p.S + 2);
+    float lg[4 * NC];
+    {   // root: obs = get_board_state(current_player, last_move)  (mcts.py:203)
+        const u64 h = e0_hash_planes(seed, w.to_move > 0 ? w.P : w.M, w.to_move > 0 ? w.M : w.P, p.NW, w.last_move);
+        double gum[4 * NC];
+#pragma unroll
+        for (int i = 0; i < 4 * NC; ++i) {
+            const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
+            lg[i] = a < p.A ? e0_logit(h, a, logit_div) : 0.0f;
+            gum[i] = a < p.A ? gumbel[(size_t)g * p.A + a] : 0.0;
+        }
+        root_init<NC>(p, w, lg, gum, e0_value(h), lane);
+    }
+    __syncwarp();
+    int ev = 0;
+    while (w.sim_count < p.S) {
+        u64 P = w.P, M = w.M; int colour = w.to_move;
+        int lp, la;
+        const int depth = descend<NC, false>(p, w, path, lane, lp, la, P, M, colour);
+        const u64 h = e0_hash_planes(seed, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la);
+#pragma unroll
+        for (int i = 0; i < 4 * NC; ++i) {
+            const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
+            lg[i] = a < p.A ? e0_logit(h, a, logit_div) : 0.0f;
+        }
+        const int nn = w.num_nodes;
+        node_write_row<NC>(p, w, nn, lg, lane);
+        if (lane == 0) {
+            p.child[(w.nbase + (size_t)lp) * (size_t)p.AP + la] = (short)nn;
+            if (trace_a) trace_a[(size_t)g * p.S + ev] = la;
+            if (trace_d) trace_d[(size_t)g * p.S + ev] = depth;
+        }
+        w.num_nodes = nn + 1; ++ev;
+        __syncwarp();
+        backup<false>(p, w, path, depth, nn, e0_value(h), 0.0, 1, lane);
+        survivor_visit(w, depth, path, nn, la, 1, lane);
+        w.sim_count += 1;
+        __syncwarp();
+        if (halving_ready(p, w)) sequential_halving<false>(p, w, lane);
+    }
+    wg_store_search(p, lane, w);
+    if (lane == 0) p.gs[g].leaf_depth = 0;
+}
+
+// Gumbel(0,1) = -log(-log(u)), u from a counter-based splitmix64 stream, 53-bit mantissa in (0,1).
+__global__ void k_fill_gumbel(double *out, size_t n, u64 seed, u64 offset)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 z = mix64(mix64(seed ^ E0_GOLD) + (offset + i) * E0_GOLD);
+    const double u = ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+    out[i] = -log(-log(u));
+}
+
+// ---------------------------------------------------------------------------------------------
+// self-play game step: do_move + get_game_ended on the roots (game.py:20-63)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS) k_game_step(Params p, const int32_t *actions, int32_t *out_winner)
+{
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= p.G) return;
+    GState *s = p.gs + g;
+    const int a = actions[g];
+    if (a < 0 || a >= p.A) { if (lane == 0 && out_winner) out_winner[g] = s->winner; return; }
+    const int colour = s->to_move;
+    u64 P = lane < GMZ_WORDS ? s->p1[lane] : 0ull, M = lane < GMZ_WORDS ? s->m1[lane] : 0ull;
+    bb_do_move(P, M, colour, a, lane);
+    const int mc = s->move_count + 1;
+    // check_win(last_move): 4 directions, up to n_in_row+1 stones each way (game.py:25-58).
+    // Lane l tests the cell at offset (l - span) along the direction; the ballot is the line.
+    const int r = a / p.N, c = a % p.N, span = p.n_in_row + 1;
+    const int off = lane - span;
+    bool win = false;
+    const int DR[4] = {0, 1, 1, 1}, DC[4] = {1, 0, 1, -1};
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const int rr = r + off * DR[d], cc = c + off * DC[d];
+        const bool in = lane <= 2 * span && rr >= 0 && rr < p.N && cc >= 0 && cc < p.N;
+        const int cell = in ? rr * p.N + cc : 0;
+        const u64 mine = shfl_u64(colour > 0 ? P : M, cell >> 6);
+        const unsigned line = __ballot_sync(GMZ_FULL, in && ((mine >> (cell & 63)) & 1ull));
+        // contiguous run through bit `span`
+        const unsigned up = line >> (span + 1);               // cells after the stone
+        const int fwd = __ffs(~up) - 1;
+        const unsigned dn = __brev(line << (32 - span));      // cells before the stone, nearest first
+        const int bwd = span > 0 ? (__ffs(~dn) - 1) : 0;
+        const int cnt = 1 + min(fwd, span) + min(bwd, span);
+        win = win || cnt >= p.n_in_row;
+    }
+    const int wv = win ? colour : (mc >= p.A ? 0 : GMZ_WINNER_NONE);
+    if (lane < GMZ_WORDS) {
+        s->p1[lane] = P; s->m1[lane] = M;
+        u64 fullm = 0; const int lo = 64 * lane;
+        if (lo < p.A) fullm = (p.A - lo >= 64) ? ~0ull : ((1ull << (p.A - lo)) - 1ull);
+        s->valid[lane] = ~(P | M) & fullm;
+    }
+    if (lane == 0) {
+        s->to_move = -colour; s->last_move = a; s->move_count = mc; s->winner = wv;
+        s->active = (wv == GMZ_WINNER_NONE);
+        s->sim_count = 0; s->leaf_depth = 0;
+        if (out_winner) out_winner[g] = wv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Layout { size_t gs, logits, child, nN, nW, nR, path, total; };
+
+static int validate(const gmz_config *c)
+{
+    if (!c) return fail("null config");
+    if (c->board_size < 1 || c->board_size > GMZ_MAX_BOARD) return fail("board_size out of range (1..19)");
+    if (c->num_simulations < 1 || c->num_simulations > 32767) return fail("num_simulations out of range (1..32767)");
+    if (c->num_top_actions < 1 || c->num_top_actions > GMZ_MAX_TOP_ACTIONS) return fail("num_top_actions out of range (1..32)");
+    if (c->mode != GMZ_MODE_ALPHAZERO && c->mode != GMZ_MODE_MUZERO) return fail("unknown mode");
+    if (c->num_games < 1) return fail("num_games must be >= 1");
+    if (c->n_in_row < 1 || c->n_in_row > 14) return fail("n_in_row out of range (1..14)");
+    return 0;
+}
+static Layout make_layout(const gmz_config *c)
+{
+    const size_t A = (size_t)c->board_size * c->board_size, NC = (A + 127) / 128, AP = 128 * NC;
+    const size_t G = c->num_games, S = c->num_simulations;
+    Layout L; size_t o = 0;
+    L.gs = o; o = align_up(o + G * sizeof(GState), 256);
+    L.logits = o; o = align_up(o + G * S * AP * sizeof(float), 256);
+    L.child = o; o = align_up(o + G * S * AP * sizeof(short), 256);
+    L.nN = o; o = align_up(o + G * S * sizeof(int), 256);
+    L.nW = o; o = align_up(o + G * S * sizeof(double), 256);
+    L.nR = o; if (c->mode == GMZ_MODE_MUZERO) o = align_up(o + G * S * sizeof(double), 256);
+    L.path = o; o = align_up(o + G * (S + 2) * sizeof(short), 256);
+    L.total = o;
+    return L;
+}
+
+extern "C" int gmz_version(void) { return GMZ_VERSION; }
+extern "C" const char *gmz_last_error(void) { return g_err; }
+
+extern "C" size_t gmz_workspace_bytes(const gmz_config *cfg)
+{
+    if (validate(cfg)) return 0;
+    return make_layout(cfg).total;
+}
+
+extern "C" int gmz_create(const gmz_config *cfg, void *workspace, size_t workspace_bytes, gmz_stream stream, gmz_engine **out)
+{
+    if (validate(cfg)) return 1;
+    if (!out) return fail("null out pointer");
+    const Layout L = make_layout(cfg);
+    if (!workspace || workspace_bytes < L.total) return fail("workspace too small");
+    if ((uintptr_t)workspace % 256) return fail("workspace must be 256-byte aligned");
+    gmz_engine *e = (gmz_engine *)calloc(1, sizeof(gmz_engine));
+    e->cfg = *cfg; e->workspace = workspace; e->bytes = L.total;
+    Params &p = e->p;
+    p.G = cfg->num_games; p.N = cfg->board_size; p.A = p.N * p.N; p.S = cfg->num_simulations; p.K = cfg->num_top_actions;
+    p.NW = (p.A + 63) / 64; e->NC = (p.A + 127) / 128; p.AP = 128 * e->NC; p.mode = cfg->mode;
+    p.n_in_row = cfg->n_in_row; p.max_moves = cfg->max_moves > 0 ? cfg->max_moves : p.A;
+    p.c_visit = cfg->c_visit; p.c_scale = cfg->c_scale; p.delta = cfg->minmax_delta; p.discount = cfg->discount;
+    // sequential-halving schedule (mcts.py:158-181), same double arithmetic as the reference
+    {
+        const int n = p.S, m = p.K;
+        const double lg2 = log2((double)m);
+        if (m <= 1 || lg2 <= 0) p.first_thr = n;
+        else { double v = floor((double)n / (lg2 * (double)m)) * (double)m; if ((double)n < v) v = (double)n; p.first_thr = (int)v; }
+        double used = 0.0; int cm = m; p.n_phases = 0;
+        for (int ph = 1; ph < GMZ_MAX_PHASES; ++ph) {
+            cm /= 2;
+            if (cm < 1) break;
+            double extra = (cm <= 1 || lg2 <= 0) ? (double)n - used : floor((double)n / (lg2 * (double)cm)) * (double)cm;
+            used += extra;
+            p.m_of_phase[ph] = cm; p.extra_of_phase[ph] = (int)extra; p.n_phases = ph;
+        }
+    }
+    char *base = (char *)workspace;
+    p.gs = (GState *)(base + L.gs); p.logits = (float *)(base + L.logits); p.child = (short *)(base + L.child);
+    p.nN = (int *)(base + L.nN); p.nW = (double *)(base + L.nW);
+    p.nR = cfg->mode == GMZ_MODE_MUZERO ? (double *)(base + L.nR) : nullptr;
+    p.path = (short *)(base + L.path);
+    cudaError_t err = cudaMemsetAsync(base + L.gs, 0, (size_t)p.G * sizeof(GState), (cudaStream_t)stream);
+    if (err != cudaSuccess) { free(e); return fail("cudaMemsetAsync: %s", cudaGetErrorString(err)); }
+    *out = e;
+    return 0;
+}
+
+extern "C" int gmz_destroy(gmz_engine *e) { free(e); return 0; }
+
+#define GRID(e) dim3(((e)->p.G + WARPS_PER_CTA - 1) / WARPS_PER_CTA), dim3(CTA_THREADS)
+#define DISPATCH_NC(e, ...)                                      \
+    switch ((e)->NC) {                                           \
+        case 1: { constexpr int NC = 1; __VA_ARGS__; } break;    \
+        case 2: { constexpr int NC = 2; __VA_ARGS__; } break;    \
+        default: { constexpr int NC = 3; __VA_ARGS__; } break;   \
+    }
+
+extern "C" int gmz_set_roots(gmz_engine *e, const int8_t *boards, const int8_t *players, const int32_t *last_moves,
+                             const int32_t *move_counts, gmz_stream stream)
+{
+    if (!e || !boards || !players || !last_moves || !move_counts) return fail("gmz_set_roots: null argument");
+    k_set_roots<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, boards, players, last_moves, move_counts);
+    return check_launch("k_set_roots");
+}
+extern "C" int gmz_games_reset(gmz_engine *e, const uint8_t *mask, gmz_stream stream)
+{
+    if (!e) return fail("gmz_games_reset: null engine");
+    k_games_reset<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, mask);
+    return check_launch("k_games_reset");
+}
+extern "C" int gmz_get_roots(gmz_engine *e, int8_t *boards, int8_t *players, int32_t *last_moves, int32_t *move_counts,
+                             gmz_stream stream)
+{
+    if (!e) return fail("gmz_get_roots: null engine");
+    k_get_roots<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, boards, players, last_moves, move_counts);
+    return check_launch("k_get_roots");
+}
+extern "C" int gmz_root_obs(gmz_engine *e, void *obs, int obs_dtype, gmz_stream stream)
+{
+    if (!e || !obs) return fail("gmz_root_obs: null argument");
+    if (obs_dtype != GMZ_F32) return fail("gmz_root_obs: only GMZ_F32 observations are supported");
+    DISPATCH_NC(e, k_root_obs<NC, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)obs));
+    return check_launch("k_root_obs");
+}
+extern "C" int gmz_root_expand(gmz_engine *e, const float *logits, const void *values, int value_dtype,
+                               const double *gumbel, gmz_stream stream)
+{
+    if (!e || !logits || !values || !gumbel) return fail("gmz_root_expand: null argument");
+    if (value_dtype != GMZ_F32 && value_dtype != GMZ_F64) return fail("gmz_root_expand: bad value dtype");
+    DISPATCH_NC(e, k_root_expand<NC><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, logits, values, value_dtype, gumbel));
+    return check_launch("k_root_expand");
+}
+extern "C" int gmz_select(gmz_engine *e, void *leaf_obs, int obs_dtype, int32_t *out_leaf_action, int32_t *out_leaf_depth,
+                          gmz_stream stream)
+{
+    if (!e) return fail("gmz_select: null engine");
+    if (e->p.mode != GMZ_MODE_ALPHAZERO) return fail("gmz_select: engine is in MuZero mode, use gmz_select_mz");
+    if (obs_dtype != GMZ_F32) return fail("gmz_select: only GMZ_F32 observations are supported");
+    DISPATCH_NC(e, k_select<NC, false, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)leaf_obs, out_leaf_action,
+                                                                                     nullptr, nullptr, out_leaf_depth));
+    return check_launch("k_select");
+}
+extern "C" int gmz_select_mz(gmz_engine *e, int32_t *out_parent_slot, int32_t *out_action, int32_t *out_child_slot,
+                             int32_t *out_leaf_depth, gmz_stream stream)
+{
+    if (!e) return fail("gmz_select_mz: null engine");
+    if (e->p.mode != GMZ_MODE_MUZERO) return fail("gmz_select_mz: engine is in AlphaZero mode, use gmz_select");
+    DISPATCH_NC(e, k_select<NC, true, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, nullptr, out_parent_slot, out_action,
+                                                                                    out_child_slot, out_leaf_depth));
+    return check_launch("k_select_mz");
+}
+extern "C" int gmz_expand_backup(gmz_engine *e, const float *logits, const void *values, const void *rewards,
+                                 int value_dtype, gmz_stream stream)
+{
+    if (!e || !logits || !values) return fail("gmz_expand_backup: null argument");
+    if (value_dtype != GMZ_F32 && value_dtype != GMZ_F64) return fail("gmz_expand_backup: bad value dtype");
+    if (e->p.mode == GMZ_MODE_MUZERO) {
+        DISPATCH_NC(e, k_expand_backup<NC, true><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, logits, values, rewards, value_dtype));
+    } else {
+        DISPATCH_NC(e, k_expand_backup<NC, false><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, logits, values, rewards, value_dtype));
+    }
+    return check_launch("k_expand_backup");
+}
+extern "C" int gmz_finalize(gmz_engine *e, double *policy, double *value, int32_t *action, int32_t *visits, gmz_stream stream)
+{
+    if (!e) return fail("gmz_finalize: null engine");
+    if (e->p.mode == GMZ_MODE_MUZERO) {
+        DISPATCH_NC(e, k_finalize<NC, true><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, policy, value, action, visits));
+    } else {
+        DISPATCH_NC(e, k_finalize<NC, false><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, policy, value, action, visits));
+    }
+    return check_launch("k_finalize");
+}
+extern "C" int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint64_t seed, int logit_div,
+                               float *logits, double *values, gmz_stream stream)
+{
+    if (!obs || !logits || !values) return fail("gmz_e0_eval_obs: null argument");
+    if (batch <= 0) return 0;
+    if (board_size < 1 || board_size > GMZ_MAX_BOARD) return fail("gmz_e0_eval_obs: board_size out of range");
+    k_e0_eval_obs<<<(batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA, CTA_THREADS, 0, (cudaStream_t)stream>>>(
+        obs, batch, board_size, (u64)seed, (float)logit_div, logits, values);
+    return check_launch("k_e0_eval_obs");
+}
+extern "C" int gmz_search_e0(gmz_engine *e, const double *gumbel, uint64_t seed, int logit_div,
+                             int32_t *trace_leaf_action, int32_t *trace_leaf_depth, gmz_stream stream)
+{
+    if (!e || !gumbel) return fail("gmz_search_e0: null argument");
+    if (e->p.mode != GMZ_MODE_ALPHAZERO) return fail("gmz_search_e0: AlphaZero mode only");
+    const size_t smem = (size_t)WARPS_PER_CTA * (e->p.S + 2) * sizeof(short);
+    DISPATCH_NC(e, {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_search_e0<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_search_e0<NC><<<GRID(e), smem, (cudaStream_t)stream>>>(e->p, gumbel, (u64)seed, (float)logit_div, trace_leaf_action, trace_leaf_depth);
+    });
+    return check_launch("k_search_e0");
+}
+extern "C" int gmz_fill_gumbel(double *out, size_t n, uint64_t seed, uint64_t offset, gmz_stream stream)
+{
+    if (!out) return fail("gmz_fill_gumbel: null argument");
+    if (n == 0) return 0;
+    k_fill_gumbel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, (u64)seed, (u64)offset);
+    return check_launch("k_fill_gumbel");
+}
+extern "C" int gmz_game_step(gmz_engine *e, const int32_t *actions, int32_t *out_winner, gmz_stream stream)
+{
+    if (!e || !actions) return fail("gmz_game_step: null argument");
+    k_game_step<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, actions, out_winner);
+    return check_launch("k_game_step");
+}

@@ -1,0 +1,155 @@
+// gmz_per.cu -- prioritized-replay SumTree kernels (reference replay_buffer.py:4-106).
+//
+// The reference applies priority updates one after another in Python; each update adds
+// `change` to every ancestor (replay_buffer.py:11-19), so a tree node's float64 value depends
+// on the ORDER its += arrive in.  To stay bit-exact the update kernel keeps that order while
+// running every tree depth in parallel: warp d owns all nodes of depth d, walks the batch in
+// order 32 updates at a time, groups lanes that hit the same node (__match_any_sync) and lets
+// the group leader accumulate the group's changes in lane (= batch) order.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gmz.h"
+#include "gmz_common.cuh"
+
+#define PER_MAX_CHUNK 2048
+
+extern "C" void gmz_set_error_(const char *msg);   // defined in gmz_engine.cu (feeds gmz_last_error)
+
+__device__ __forceinline__ int node_depth(long long k) { return 63 - __clzll((unsigned long long)(k + 1)); }
+
+// One CTA of 1024 threads (32 warps).  Stage 1 (warp 0): leaf writes and `change` per update,
+// in batch order (a repeated leaf sees the previous write).  Stage 2 (warp d): depth-d ancestors.
+__global__ void __launch_bounds__(1024)
+k_per_update(double *tree, const long long *tree_idx, const double *prio, int n)
+{
+    extern __shared__ double s_change[];           // [n]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const bool act = i < n;
+            const long long key = act ? tree_idx[i] : -1 - lane;
+            const double p = act ? prio[i] : 0.0;
+            const unsigned grp = __match_any_sync(GMZ_FULL, key);
+            const int leader = __ffs(grp) - 1;
+            double cur = 0.0;
+            if (act && lane == leader) cur = __ldcg(tree + key);
+            cur = __shfl_sync(GMZ_FULL, cur, leader);
+            // walk the group in lane order: change_b = p_b - cur; cur = p_b
+            double my_change = 0.0, last = cur;
+            for (int b = 0; b < 32; ++b) {
+                const long long kb = __shfl_sync(GMZ_FULL, key, b);
+                const double pb = __shfl_sync(GMZ_FULL, p, b);
+                if (kb == key) {
+                    if (b == lane) my_change = __dsub_rn(pb, last);
+                    last = pb;
+                }
+            }
+            if (act) {
+                s_change[i] = my_change;
+                if (lane == leader) __stcg(tree + key, last);   // value after the group's last write
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const int d = warp;                              // this warp's tree depth (0 = root)
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        long long key = -1 - lane;
+        double ch = 0.0;
+        if (i < n) {
+            const long long leaf = tree_idx[i];
+            const int D = node_depth(leaf);
+            if (D > d) { key = ((leaf + 1) >> (D - d)) - 1; ch = s_change[i]; }
+        }
+        const bool act = key >= 0;
+        const unsigned grp = __match_any_sync(GMZ_FULL, key);
+        if (__ballot_sync(GMZ_FULL, act) == 0) continue;
+        const int leader = __ffs(grp) - 1;
+        double acc = 0.0;
+        if (act && lane == leader) acc = __ldcg(tree + key);
+        for (int b = 0; b < 32; ++b) {
+            const long long kb = __shfl_sync(GMZ_FULL, key, b);
+            const double cb = __shfl_sync(GMZ_FULL, ch, b);
+            if (act && lane == leader && kb == key) acc = __dadd_rn(acc, cb);   // self.tree[parent] += change
+        }
+        if (act && lane == leader) __stcg(tree + key, acc);
+        __syncwarp();
+    }
+}
+
+// InMemoryReplayBuffer.sample, PER branch (replay_buffer.py:60-86).  Single CTA: stratified
+// draw + get_leaf descent per sample, then the batch-max normalisation of the IS weights.
+__global__ void __launch_bounds__(1024)
+k_per_sample(const double *tree, long long capacity, long long count, const double *u01, int B, double beta,
+             long long *out_idx, double *out_prio, float *out_w)
+{
+    __shared__ float s_max[32];
+    const long long len = 2 * capacity - 1;
+    const double total = tree[0];
+    const double segment = __ddiv_rn(total, (double)B);
+    float lmax = -INFINITY;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const double lo = __dmul_rn(segment, (double)i), hi = __dmul_rn(segment, (double)(i + 1));
+        double v = __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u01[i]));   // np.random.uniform(lo, hi)
+        long long parent = 0;
+        for (;;) {                                                        // SumTree.get_leaf
+            const long long left = 2 * parent + 1;
+            if (left >= len) break;
+            const double lv = tree[left];
+            if (v <= lv) parent = left; else { v = __dsub_rn(v, lv); parent = left + 1; }
+        }
+        const double p = tree[parent];
+        const double prob = __ddiv_rn(p, total);
+        const float wgt = (float)pow(__dmul_rn((double)count, prob), -beta);
+        out_idx[i] = parent; out_prio[i] = p; out_w[i] = wgt;
+        lmax = fmaxf(lmax, wgt);
+    }
+    for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(GMZ_FULL, lmax, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = lmax;
+    __syncthreads();
+    float m = (threadIdx.x & 31) < (blockDim.x >> 5) ? s_max[threadIdx.x & 31] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(GMZ_FULL, m, o));
+    if (m > 0.0f)
+        for (int i = threadIdx.x; i < B; i += blockDim.x) out_w[i] = __fdiv_rn(out_w[i], m);
+}
+
+static int per_fail(const char *msg)
+{
+    gmz_set_error_(msg);
+    return 1;
+}
+
+extern "C" int gmz_per_update(double *tree, int64_t capacity, const int64_t *tree_idx, const double *priorities, int n,
+                              gmz_stream stream)
+{
+    if (!tree || !tree_idx || !priorities) return per_fail("gmz_per_update: null argument");
+    if (capacity < 1) return per_fail("gmz_per_update: capacity out of range");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_per_update, cudaFuncAttributeMaxDynamicSharedMemorySize, PER_MAX_CHUNK * (int)sizeof(double));
+        attr_set = true;
+    }
+    for (int off = 0; off < n; off += PER_MAX_CHUNK) {     // chunks run in stream order = batch order
+        const int m = n - off < PER_MAX_CHUNK ? n - off : PER_MAX_CHUNK;
+        k_per_update<<<1, 1024, m * sizeof(double), (cudaStream_t)stream>>>(tree, (const long long *)tree_idx + off, priorities + off, m);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return per_fail(cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int gmz_per_sample(const double *tree, int64_t capacity, int64_t count, const double *u01, int batch, double beta,
+                              int64_t *out_tree_idx, double *out_priority, float *out_weights, gmz_stream stream)
+{
+    if (!tree || !u01 || !out_tree_idx || !out_priority || !out_weights) return per_fail("gmz_per_sample: null argument");
+    if (batch <= 0) return 0;
+    k_per_sample<<<1, 1024, 0, (cudaStream_t)stream>>>(tree, capacity, count, u01, batch, beta,
+                                                        (long long *)out_tree_idx, out_priority, out_weights);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return per_fail(cudaGetErrorString(e));
+    return 0;
+}

@@ -1,0 +1,376 @@
+// gmz_tree.cuh -- warp-cooperative device functions of the Gumbel-MCTS simulation step.
+// Each function restates one piece of the reference search (file:line cited) for a warp that
+// owns one game; see gmz_common.cuh for the lane <-> action mapping.
+#pragma once
+#include "gmz_common.cuh"
+
+// Register-resident view of one game ("U" = warp-uniform, "L" = one element per lane).
+struct WG {
+    int g;                 // U
+    size_t nbase;          // U  g * S : index of this game's node 0 in the per-node arrays
+    double mm_min, mm_max; // U  MinMaxStats
+    int sim_count, num_nodes, phase, next_thr, n_surv, n_init, to_move, last_move, active;  // U
+    u64 P, M, V;           // L  lane w < NW holds word w of p1 / m1 / valid
+    unsigned vb;           // L  valid bits of this lane's actions (bit 4*j + t)
+    int s_act, s_child, s_n;  // L  lane i < n_init: survivor i
+    double s_g;            // L
+    float s_logit;         // L
+};
+
+__device__ __forceinline__ void wg_load(const Params &p, int g, int lane, WG &w)
+{
+    const GState *s = p.gs + g;
+    w.g = g; w.nbase = (size_t)g * (size_t)p.S;
+    w.mm_min = s->mm_min; w.mm_max = s->mm_max;
+    w.sim_count = s->sim_count; w.num_nodes = s->num_nodes; w.phase = s->phase; w.next_thr = s->next_thr;
+    w.n_surv = s->n_surv; w.n_init = s->n_init; w.to_move = s->to_move; w.last_move = s->last_move;
+    w.active = s->active;
+    w.P = lane < GMZ_WORDS ? s->p1[lane] : 0ull;
+    w.M = lane < GMZ_WORDS ? s->m1[lane] : 0ull;
+    w.V = lane < GMZ_WORDS ? s->valid[lane] : 0ull;
+    w.s_act = s->surv_act[lane]; w.s_child = s->surv_child[lane]; w.s_n = s->surv_n[lane];
+    w.s_g = s->surv_g[lane]; w.s_logit = s->surv_logit[lane];
+}
+template <int NC>
+__device__ __forceinline__ void wg_valid_bits(WG &w, int lane)
+{
+    unsigned vb = 0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        u64 word = shfl_u64(w.V, 2 * j + (lane >> 4));
+        vb |= (unsigned)((word >> ((lane & 15) * 4)) & 0xFull) << (4 * j);
+    }
+    w.vb = vb;
+}
+__device__ __forceinline__ void wg_store_search(const Params &p, int lane, const WG &w)
+{
+    GState *s = p.gs + w.g;
+    if (lane == 0) {
+        s->mm_min = w.mm_min; s->mm_max = w.mm_max;
+        s->sim_count = w.sim_count; s->num_nodes = w.num_nodes; s->phase = w.phase; s->next_thr = w.next_thr;
+        s->n_surv = w.n_surv; s->n_init = w.n_init;
+    }
+    s->surv_act[lane] = (short)w.s_act; s->surv_child[lane] = (short)w.s_child; s->surv_n[lane] = w.s_n;
+    s->surv_g[lane] = w.s_g; s->surv_logit[lane] = w.s_logit;
+}
+
+// GomokuGame.do_move on the lane-distributed bitboards (game.py:20-23): the stone OVERWRITES
+// whatever is on the cell (the reference's in-tree replay has no legality check).
+__device__ __forceinline__ void bb_do_move(u64 &P, u64 &M, int colour, int a, int lane)
+{
+    if (lane == (a >> 6)) {
+        const u64 b = 1ull << (a & 63);
+        if (colour > 0) { P |= b; M &= ~b; } else { M |= b; P &= ~b; }
+    }
+}
+
+// utils.MinMaxStats.normalize (utils.py:16-25) with the range test hoisted.
+__device__ __forceinline__ double mm_norm(double q, bool rng, double mn, double denom)
+{
+    if (!rng) return 0.0;
+    double n = __ddiv_rn(__dsub_rn(q, mn), denom);
+    n = n < 1.0 ? n : 1.0;
+    return n > 0.0 ? n : 0.0;
+}
+
+// Loaded view of one expanded node's row: logits, child ids, child visit counts and q values.
+template <int NC>
+struct Row {
+    float lg[4 * NC];
+    short ch[4 * NC];
+    int n[4 * NC];
+    double q[4 * NC];
+    int maxN, sumN;
+};
+
+// Node.get_qsa for every action of `node` (mcts.py:35-38) + max / sum of child visits
+// (mcts.py:144-147, 110).  Only visited children (child id >= 0) touch memory beyond the row.
+template <int NC, bool MZ>
+__device__ __forceinline__ void row_load(const Params &p, const WG &w, int node, int lane, Row<NC> &r)
+{
+    const size_t ni = w.nbase + (size_t)node;
+    const float *lrow = p.logits + ni * (size_t)p.AP;
+    const short *crow = p.child + ni * (size_t)p.AP;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const float4 t = *reinterpret_cast<const float4 *>(lrow + 128 * j + 4 * lane);
+        const short4 c = *reinterpret_cast<const short4 *>(crow + 128 * j + 4 * lane);
+        r.lg[4 * j + 0] = t.x; r.lg[4 * j + 1] = t.y; r.lg[4 * j + 2] = t.z; r.lg[4 * j + 3] = t.w;
+        r.ch[4 * j + 0] = c.x; r.ch[4 * j + 1] = c.y; r.ch[4 * j + 2] = c.z; r.ch[4 * j + 3] = c.w;
+    }
+    int lmax = 0, lsum = 0;
+#pragma unroll
+    for (int i = 0; i < 4 * NC; ++i) {
+        r.n[i] = 0; r.q[i] = 0.0;
+        if (r.ch[i] >= 0) {
+            const size_t ci = w.nbase + (size_t)r.ch[i];
+            const int nn = p.nN[ci];
+            const double val = __ddiv_rn(p.nW[ci], (double)nn);          // child.get_value()
+            const double rew = MZ ? p.nR[ci] : 0.0;                        // child.reward
+            r.q[i] = __dadd_rn(rew, __dmul_rn(p.discount, val));
+            r.n[i] = nn; lmax = max(lmax, nn); lsum += nn;
+        }
+    }
+    r.maxN = __reduce_max_sync(GMZ_FULL, lmax);
+    r.sumN = __reduce_add_sync(GMZ_FULL, lsum);
+}
+
+// softmax over the root-valid actions of logits + sigma(q) (mcts.py:141-156): on return
+// x[i] = exp(logit + sigma - max) (0 for invalid actions) and the return value is 1/sum.
+template <int NC>
+__device__ __forceinline__ double row_softmax(const Params &p, const WG &w, const Row<NC> &r, double *x)
+{
+    const double scale = __dmul_rn(__dadd_rn(p.c_visit, (double)r.maxN), p.c_scale);
+    const bool rng = w.mm_max > w.mm_min;
+    const double denom = __dadd_rn(__dsub_rn(w.mm_max, w.mm_min), p.delta);
+    const double sig0 = __dmul_rn(scale, mm_norm(0.0, rng, w.mm_min, denom));   // unvisited: q = 0.0
+    double lmx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4 * NC; ++i) {
+        if ((w.vb >> i) & 1u) {
+            const double sig = r.ch[i] >= 0 ? __dmul_rn(scale, mm_norm(r.q[i], rng, w.mm_min, denom)) : sig0;
+            x[i] = __dadd_rn((double)r.lg[i], sig);
+            lmx = fmax(lmx, x[i]);
+        } else x[i] = -INFINITY;
+    }
+    const double mx = warp_max_f64(lmx);
+    double ls = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4 * NC; ++i) {
+        x[i] = ((w.vb >> i) & 1u) ? exp(__dsub_rn(x[i], mx)) : 0.0;
+        ls = __dadd_rn(ls, x[i]);
+    }
+    const double sum = warp_sum_f64(ls);
+    return __ddiv_rn(1.0, sum);
+}
+
+// _select_action at an interior node (mcts.py:106-117):
+// argmax_a  softmax(logits + sigma)[a] - N(a) / (1 + sum_b N(b))   over the ROOT-valid actions.
+template <int NC, bool MZ>
+__device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, int &action, int &child)
+{
+    Row<NC> r;
+    row_load<NC, MZ>(p, w, node, lane, r);
+    double x[4 * NC];
+    const double inv = row_softmax<NC>(p, w, r, x);
+    const double dn = (double)(1 + r.sumN);
+    double best = -INFINITY; int ba = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 4 * NC; ++i) {
+        if ((w.vb >> i) & 1u) {
+            double sc = __dmul_rn(x[i], inv);
+            if (r.n[i] > 0) sc = __dsub_rn(sc, __ddiv_rn((double)r.n[i], dn));
+            const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
+            if (sc > best) { best = sc; ba = a; }
+        }
+    }
+    warp_argmax_lowidx(best, ba);
+    action = ba;
+    child = p.child[(w.nbase + (size_t)node) * (size_t)p.AP + ba];
+}
+
+// _select_leaf (mcts.py:88-104): root = first least-visited survivor (strict <, list order),
+// then interior selection until an unexpanded child is reached.  In AlphaZero mode the path
+// is replayed on the bitboards while descending (mcts.py:236-248).  Returns depth (edges).
+template <int NC, bool MZ>
+__device__ __forceinline__ int descend(const Params &p, const WG &w, short *path, int lane,
+                                       int &leaf_parent, int &leaf_action, u64 &P, u64 &M, int &colour)
+{
+    const unsigned key = lane < w.n_surv ? (((unsigned)w.s_n << 5) | (unsigned)lane) : 0xffffffffu;
+    const int bl = (int)(__reduce_min_sync(GMZ_FULL, key) & 31u);
+    int a = __shfl_sync(GMZ_FULL, w.s_act, bl);
+    int node = __shfl_sync(GMZ_FULL, w.s_child, bl);
+    int parent = 0, depth = 1;
+    if (lane == 0) path[0] = 0;
+    if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
+    while (node >= 0) {
+        if (lane == 0) path[depth] = (short)node;
+        int c;
+        select_interior<NC, MZ>(p, w, node, lane, a, c);
+        if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
+        parent = node; node = c; ++depth;
+    }
+    leaf_parent = parent; leaf_action = a;
+    return depth;
+}
+
+// leaf.expand (mcts.py:24-25, 260): write the new node's row (logits, no children) and link it.
+template <int NC>
+__device__ __forceinline__ void node_write_row(const Params &p, const WG &w, int node, const float *lg, int lane)
+{
+    const size_t ni = w.nbase + (size_t)node;
+    float *lrow = p.logits + ni * (size_t)p.AP;
+    short *crow = p.child + ni * (size_t)p.AP;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        *reinterpret_cast<float4 *>(lrow + 128 * j + 4 * lane) = make_float4(lg[4 * j], lg[4 * j + 1], lg[4 * j + 2], lg[4 * j + 3]);
+        *reinterpret_cast<short4 *>(crow + 128 * j + 4 * lane) = make_short4(-1, -1, -1, -1);
+    }
+}
+
+// _backpropagate for one leaf, `reps` times in sequence (mcts.py:119-138; MuZero applies the
+// same value len(selected) times, mcts.py:345).  Positions 0..depth-1 are path[], position
+// `depth` is the new node.  Lane l of a 32-wide segment owns position hi - l.  Also maintains
+// the survivor visit counts and the MinMaxStats (min/max are order-independent).
+template <bool MZ>
+__device__ __forceinline__ void backup(const Params &p, WG &w, const short *path, int depth, int new_node,
+                                       double value, double reward, int reps, int lane)
+{
+    double v = dclip1(value);
+    double qmin = INFINITY, qmax = -INFINITY;
+    for (int hi = depth; hi >= 0; hi -= 32) {
+        const int pos = hi - lane;
+        const bool act = pos >= 0;
+        const bool is_new = pos == depth;
+        const int node = act ? (is_new ? new_node : (int)path[pos]) : 0;
+        const size_t ni = w.nbase + (size_t)node;
+        int n = 0; double W = 0.0, R = 0.0;
+        if (act && !is_new) { n = p.nN[ni]; W = p.nW[ni]; if (MZ) R = p.nR[ni]; }
+        if (act && is_new && MZ) R = reward;
+        double myv = 0.0;
+        const int cnt = min(32, hi + 1);
+        for (int l = 0; l < cnt; ++l) {
+            const double Rl = MZ ? __shfl_sync(GMZ_FULL, R, l) : 0.0;
+            if (lane == l) myv = v;
+            v = dclip1(__dadd_rn(Rl, __dmul_rn(p.discount, v)));   // value = node.reward + DISCOUNT * value; clip
+        }
+        if (act) {
+            for (int r = 0; r < reps; ++r) {
+                W = __dadd_rn(W, myv); n += 1;
+                if (pos > 0) {   // min_max_stats.update(parent.get_qsa(node.action))
+                    const double q = __dadd_rn(R, __dmul_rn(p.discount, __ddiv_rn(W, (double)n)));
+                    qmin = fmin(qmin, q); qmax = fmax(qmax, q);
+                }
+            }
+            p.nN[ni] = n; p.nW[ni] = W;
+            if (MZ && is_new) p.nR[ni] = R;
+        }
+    }
+    qmin = warp_min_f64(qmin); qmax = warp_max_f64(qmax);
+    w.mm_min = fmin(w.mm_min, qmin); w.mm_max = fmax(w.mm_max, qmax);
+}
+
+// _ready_for_next_gumbel_phase (mcts.py:166-181), tables precomputed on the host.
+__device__ __forceinline__ bool halving_ready(const Params &p, WG &w)
+{
+    if (w.sim_count < w.next_thr) return false;
+    w.phase += 1;
+    if (w.phase > p.n_phases) { w.phase = p.n_phases + 1; return false; }   // current_num_top_actions < 1
+    w.next_thr = min(w.next_thr + p.extra_of_phase[w.phase], p.S);
+    return true;
+}
+
+// _sequential_halving (mcts.py:183-185): survivors = first m of the current survivors sorted
+// (stable, descending) by gumbel + logit + sigma(q) at the root.
+template <bool MZ>
+__device__ __forceinline__ void sequential_halving(const Params &p, WG &w, int lane)
+{
+    const bool mine = lane < w.n_init;
+    double q = 0.0;
+    const int n = mine ? w.s_n : 0;
+    if (mine && w.s_child >= 0) {
+        const size_t ci = w.nbase + (size_t)w.s_child;
+        const double val = __ddiv_rn(p.nW[ci], (double)n);
+        const double rew = MZ ? p.nR[ci] : 0.0;
+        q = __dadd_rn(rew, __dmul_rn(p.discount, val));
+    }
+    const int maxN = __reduce_max_sync(GMZ_FULL, n);
+    const double scale = __dmul_rn(__dadd_rn(p.c_visit, (double)maxN), p.c_scale);
+    const bool rng = w.mm_max > w.mm_min;
+    const double denom = __dadd_rn(__dsub_rn(w.mm_max, w.mm_min), p.delta);
+    const double sig = __dmul_rn(scale, mm_norm(q, rng, w.mm_min, denom));
+    const double score = __dadd_rn(__dadd_rn(w.s_g, (double)w.s_logit), sig);
+    int rank = 0;
+    for (int j = 0; j < w.n_surv; ++j) {
+        const double sj = __shfl_sync(GMZ_FULL, score, j);
+        if (sj > score || (sj == score && j < lane)) ++rank;
+    }
+    if (lane >= w.n_surv) rank = lane;
+    int src = lane;
+    for (int j = 0; j < 32; ++j) {
+        const int rj = __shfl_sync(GMZ_FULL, rank, j);
+        if (rj == lane) src = j;
+    }
+    w.s_act = __shfl_sync(GMZ_FULL, w.s_act, src);
+    w.s_child = __shfl_sync(GMZ_FULL, w.s_child, src);
+    w.s_n = __shfl_sync(GMZ_FULL, w.s_n, src);
+    w.s_g = __shfl_sync(GMZ_FULL, w.s_g, src);
+    w.s_logit = __shfl_sync(GMZ_FULL, w.s_logit, src);
+    w.n_surv = min(p.m_of_phase[w.phase], w.n_surv);
+}
+
+// After a backup through root child `first_node` (depth-1 node on the path): bump the
+// survivor's visit count (and record the child id if it was just created).
+__device__ __forceinline__ void survivor_visit(WG &w, int depth, const short *path, int new_node, int leaf_action, int reps, int lane)
+{
+    bool hit;
+    if (depth == 1) hit = lane < w.n_surv && w.s_act == leaf_action;
+    else hit = lane < w.n_surv && w.s_child == (int)path[1];
+    if (hit) { w.s_n += reps; if (depth == 1) w.s_child = new_node; }
+}
+
+// Root initialisation (mcts.py:217-226): expand root, first backup, halving schedule, Gumbel
+// top-k = first K valid actions by (gumbel + logit, action) descending.
+template <int NC>
+__device__ __forceinline__ void root_init(const Params &p, WG &w, const float *lg, const double *gum, double value, int lane)
+{
+    node_write_row<NC>(p, w, 0, lg, lane);
+    w.mm_min = INFINITY; w.mm_max = -INFINITY;
+    if (lane == 0) {   // backup of the root alone: N = 1, W = clip(v)
+        p.nN[w.nbase] = 1; p.nW[w.nbase] = dclip1(value);
+        if (p.nR) p.nR[w.nbase] = 0.0;
+    }
+    w.num_nodes = 1; w.sim_count = 1; w.phase = 0; w.next_thr = p.first_thr;
+    double sc[4 * NC];
+    unsigned rem = w.vb;
+#pragma unroll
+    for (int i = 0; i < 4 * NC; ++i) sc[i] = __dadd_rn(gum[i], (double)lg[i]);
+    w.s_act = -1; w.s_child = -1; w.s_n = 0; w.s_g = 0.0; w.s_logit = 0.f;
+    int cnt = 0;
+    for (int r = 0; r < p.K; ++r) {
+        double best = -INFINITY; int ba = -1;
+#pragma unroll
+        for (int i = 0; i < 4 * NC; ++i) {
+            if ((rem >> i) & 1u) {
+                const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
+                if (ba < 0 || sc[i] > best || (sc[i] == best && a > ba)) { best = sc[i]; ba = a; }
+            }
+        }
+        if (ba < 0) best = -INFINITY;
+        // lanes without candidates must lose: use (-inf, -1)
+        warp_argmax_highidx(best, ba);
+        if (ba < 0) break;
+        const int owner = (ba & 127) >> 2;
+        double gsel = 0.0; float lsel = 0.f;
+        if (lane == owner) {
+#pragma unroll
+            for (int i = 0; i < 4 * NC; ++i)
+                if (128 * (i >> 2) + 4 * lane + (i & 3) == ba) { gsel = gum[i]; lsel = lg[i]; rem &= ~(1u << i); }
+        }
+        gsel = __shfl_sync(GMZ_FULL, gsel, owner); lsel = __shfl_sync(GMZ_FULL, lsel, owner);
+        if (lane == r) { w.s_act = ba; w.s_g = gsel; w.s_logit = lsel; }
+        ++cnt;
+    }
+    w.n_init = cnt; w.n_surv = cnt;
+}
+
+// Observation planes of a position (game.py:12-17) for this lane's actions, from the
+// lane-distributed bitboards: own / opp relative to `to_move`, last-move one-hot.
+template <int NC, typename T>
+__device__ __forceinline__ void obs_write(T *obs, int A, u64 own_w, u64 opp_w, int last, int lane)
+{
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const u64 ow = shfl_u64(own_w, 2 * j + (lane >> 4)) >> ((lane & 15) * 4);
+        const u64 pw = shfl_u64(opp_w, 2 * j + (lane >> 4)) >> ((lane & 15) * 4);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int a = 128 * j + 4 * lane + t;
+            if (a < A) {
+                obs[a] = (T)(float)((ow >> t) & 1ull);
+                obs[A + a] = (T)(float)((pw >> t) & 1ull);
+                obs[2 * A + a] = (T)(a == last ? 1.0f : 0.0f);
+            }
+        }
+    }
+}

@@ -1,0 +1,198 @@
+"""GPU parity: the CUDA engine (through the C ABI) against (a) the golden vectors produced by
+the imported reference and (b) the CPU oracle on seeded random inputs.  Bar: visit counts,
+chosen moves, per-simulation leaf traces and terminal flags bit-exact; values / policies within
+1e-5 relative (north_star); in practice values are bit-exact and policies agree to ~1e-15."""
+import os
+
+import numpy as np
+import pytest
+
+from _golden_util import GOLDEN_DIR, load_search_cases
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # north_star tolerance for Q / value targets
+
+
+def _engine(c, G=1, mode=None):
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    return SearchEngine(G, board_size=c["N"], n_in_row=c["n_in_row"], num_simulations=c["S"], num_top_actions=c["K"],
+                        mode=mode or ("AlphaZero" if c["mode"] == "az" else "MuZero"), c_visit=c["c_visit"],
+                        c_scale=c["c_scale"], minmax_delta=c["delta"], discount=c["discount"])
+
+
+def _check(c, pol, val, act, vis, ta, td, tag):
+    assert np.array_equal(vis, c["visits"]), f"{tag}: visit counts"
+    assert int(act) == c["action"], f"{tag}: action {act} vs {c['action']}"
+    if ta is not None:
+        n = len(c["leaf_actions"])
+        assert np.array_equal(ta[:n], c["leaf_actions"]), f"{tag}: leaf action trace"
+        assert np.array_equal(td[:n], c["leaf_depths"]), f"{tag}: leaf depth trace"
+    np.testing.assert_allclose(val, c["value"], rtol=RTOL, atol=1e-12, err_msg=tag)
+    np.testing.assert_allclose(pol, c["policy"], rtol=RTOL, atol=1e-12, err_msg=tag)
+
+
+@pytest.mark.parametrize("N", [6, 9, 15])
+def test_fused_search_matches_reference_goldens(N):
+    for c in [c for c in load_search_cases("az", N) if c["kind"] == 0]:
+        eng = _engine(c, G=3)
+        eng.set_roots(np.tile(c["board"].reshape(1, -1), (3, 1)), [c["player"]] * 3, [c["last_move"]] * 3, [c["move_count"]] * 3)
+        ta, td = eng.search_e0(np.tile(c["gumbel"], (3, 1)), c["seed"], c["logit_div"], trace=True)
+        pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
+        ta, td = ta.cpu().numpy(), td.cpu().numpy()
+        for g in range(3):
+            _check(c, pol[g], val[g], act[g], vis[g], ta[g], td[g], f"fused az N={N} case {c['idx']} game {g}")
+
+
+@pytest.mark.parametrize("N", [6, 9, 15])
+def test_stepwise_search_matches_reference_goldens(N):
+    cases = [c for c in load_search_cases("az", N) if c["kind"] == 0]
+    if N == 15:
+        cases = cases[::3]
+    for c in cases:
+        eng = _engine(c, G=2)
+        eng.set_roots(np.tile(c["board"].reshape(1, -1), (2, 1)), [c["player"]] * 2, [c["last_move"]] * 2, [c["move_count"]] * 2)
+        ta, td = eng.search_stepwise_e0(np.tile(c["gumbel"], (2, 1)), c["seed"], c["logit_div"], trace=True)
+        pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
+        for g in range(2):
+            _check(c, pol[g], val[g], act[g], vis[g], None if ta is None else ta[g].cpu().numpy(),
+                   None if td is None else td[g].cpu().numpy(), f"stepwise az N={N} case {c['idx']} game {g}")
+
+
+@pytest.mark.parametrize("N", [6, 9, 15])
+def test_constant_evaluator_goldens(N):
+    """MockModel-style evaluator (tests/test_mcts_logic.py:60-80): logits 0, value const (incl. > 1 -> clip)."""
+    import torch
+    for c in [c for c in load_search_cases("az", N) if c["kind"] == 1]:
+        eng = _engine(c, G=1)
+        eng.set_roots(c["board"].reshape(1, -1), [c["player"]], [c["last_move"]], [c["move_count"]])
+        lg = torch.zeros((1, N * N), dtype=torch.float32, device="cuda")
+        v = torch.full((1,), c["const_value"], dtype=torch.float64, device="cuda")
+        eng.root_expand(lg, v, c["gumbel"].reshape(1, -1))
+        for _ in range(c["S"] - 1):
+            eng.select()
+            eng.expand_backup(lg, v)
+        pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
+        _check(c, pol[0], val[0], act[0], vis[0], None, None, f"const az N={N} case {c['idx']}")
+
+
+@pytest.mark.parametrize("N", [6, 9, 15])
+def test_muzero_search_matches_reference_goldens(N):
+    """MuZero mode through gmz_select_mz / gmz_expand_backup with the E0 recurrent evaluator run
+    on the host (hidden state = 64-bit hash per node slot)."""
+    import torch
+    import e0_py
+    cases = load_search_cases("mz", N)
+    if N == 15:
+        cases = cases[::2]
+    for c in cases:
+        A = N * N
+        eng = _engine(c, G=1)
+        eng.set_roots(c["board"].reshape(1, -1), [c["player"]], [c["last_move"]], [c["move_count"]])
+        hidden = {}
+        obs = eng.root_obs().cpu().numpy()[0]
+        if c["kind"] == 0:
+            h0 = e0_py.hash_obs(obs, c["seed"])
+            lg, v = e0_py.heads(h0, A, c["logit_div"])
+        else:
+            h0, lg, v = 1, np.zeros(A, np.float32), c["const_value"]
+        hidden[0] = h0
+        eng.root_expand(lg.reshape(1, -1), np.array([v], np.float64), c["gumbel"].reshape(1, -1))
+        trace_a, trace_d, n_eval = [], [], 0
+        for _ in range(c["S"]):
+            ps, ac, cs, dp = (int(t.cpu()[0]) for t in eng.select_mz())
+            if ps < 0:
+                break
+            if c["kind"] == 0:
+                hc = e0_py.child_hidden(hidden[ps], ac)
+                lg, v = e0_py.heads(hc, A, c["logit_div"])
+                r = e0_py.reward_of(hc)
+            else:
+                hc, lg, v, r = 2, np.zeros(A, np.float32), c["const_value"], c["const_reward"]
+            hidden[cs] = hc
+            trace_a.append(ac); trace_d.append(dp); n_eval += 1
+            eng.expand_backup(lg.reshape(1, -1), np.array([v], np.float64), np.array([r], np.float64))
+        assert n_eval == c["n_recurrent"], f"mz N={N} case {c['idx']}: {n_eval} evaluations vs {c['n_recurrent']}"
+        pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
+        _check(c, pol[0], val[0], act[0], vis[0], np.array(trace_a), np.array(trace_d), f"mz N={N} case {c['idx']}")
+
+
+def test_e0_kernel_matches_python():
+    import torch
+    import e0_py
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    rs = np.random.RandomState(5)
+    for N in (6, 9, 15, 19):
+        A = N * N
+        eng = SearchEngine(1, board_size=N, num_simulations=2)
+        B = 16
+        obs = np.zeros((B, 3, N, N), np.float32)
+        for b in range(B):
+            cells = rs.randint(-1, 2, size=(N, N))
+            obs[b, 0] = cells == 1; obs[b, 1] = cells == -1
+            if b % 4:
+                a = rs.randint(A); obs[b, 2, a // N, a % N] = 1
+        seed, div = int(rs.randint(1 << 30)), int(rs.choice([2, 4, 16]))
+        lg, v = eng.e0_eval(torch.from_numpy(obs).cuda(), seed, div)
+        lg, v = lg.cpu().numpy(), v.cpu().numpy()
+        for b in range(B):
+            h = e0_py.hash_obs(obs[b], seed)
+            l2, v2 = e0_py.heads(h, A, div)
+            assert np.array_equal(lg[b], l2) and v[b] == v2, (N, b)
+
+
+@pytest.mark.parametrize("N,S,G", [(9, 100, 64), (15, 400, 96), (19, 64, 16), (6, 50, 64)])
+def test_random_positions_match_oracle(N, S, G):
+    """Seeded random mid-game positions + random noise: fused kernel vs CPU oracle."""
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from oracle import oracle
+    A = N * N
+    rs = np.random.RandomState(N * 1000 + S)
+    boards = np.zeros((G, A), np.int8); players = np.ones(G, np.int8)
+    last = np.full(G, -1, np.int32); mc = np.zeros(G, np.int32)
+    for g in range(G):
+        k = int(rs.randint(0, A))
+        if g == 0:
+            k = A          # full board -> inactive game -> sentinel
+        p = 1
+        for a in rs.permutation(A)[:k]:
+            boards[g, a] = p; last[g] = a; p = -p
+        players[g] = p; mc[g] = k
+    gumbel = rs.gumbel(0, 1, (G, A))
+    seed = 77
+    eng = SearchEngine(G, board_size=N, num_simulations=S, num_top_actions=16)
+    eng.set_roots(boards, players, last, mc)
+    eng.search_e0(gumbel, seed)
+    pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
+    cfg = oracle.make_config(board_size=N, num_simulations=S, num_top_actions=16, eval_seed=seed)
+    opol, oval, oact, ovis = oracle.search_batch(cfg, boards, players, last, mc, gumbel)
+    assert act[0] == -1 and pol[0].sum() == 0 and val[0] == 0.0      # sentinel (mcts.py:214-215)
+    assert np.array_equal(vis, ovis)
+    assert np.array_equal(act, oact)
+    np.testing.assert_allclose(val, oval, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(pol, opol, rtol=RTOL, atol=1e-12)
+    assert np.array_equal(val, oval), "float64 value accumulation should be bit-exact"
+    # the roots must come back unchanged (search() must not mutate the game)
+    b2, p2, l2, m2 = (t.cpu().numpy() for t in eng.get_roots())
+    assert np.array_equal(b2.reshape(G, A), boards) and np.array_equal(p2, players)
+    assert np.array_equal(l2, last) and np.array_equal(m2, mc)
+
+
+def test_game_step_matches_reference_kat():
+    """do_move + get_game_ended (game.py:20-63) on device vs the reference KATs."""
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    z = np.load(os.path.join(GOLDEN_DIR, "game_kat.npz"))
+    for N, nir in sorted({(int(a), int(b)) for a, b in zip(z["N"], z["nir"])}):
+        sel = np.flatnonzero((z["N"] == N) & (z["nir"] == nir))
+        G, A = len(sel), N * N
+        boards = z["boards"][sel][:, :A].copy()
+        last = z["last"][sel].astype(np.int32)
+        colour = boards[np.arange(G), last].copy()
+        boards[np.arange(G), last] = 0                     # take the last stone back, then replay it
+        eng = SearchEngine(G, board_size=N, n_in_row=nir, num_simulations=2)
+        eng.set_roots(boards, colour, np.full(G, -1, np.int32), z["move_count"][sel] - 1)
+        w = eng.game_step(last).cpu().numpy()
+        assert np.array_equal(w, z["ended"][sel]), (N, nir)
+        b2, p2, l2, m2 = (t.cpu().numpy() for t in eng.get_roots())
+        assert np.array_equal(b2.reshape(G, A), z["boards"][sel][:, :A])
+        assert np.array_equal(p2, -colour) and np.array_equal(l2, last) and np.array_equal(m2, z["move_count"][sel])

@@ -1,0 +1,84 @@
+"""GPU parity of the PER SumTree kernels against KATs recorded from the reference's
+InMemoryReplayBuffer (tests/golden/per_kat.npz) and against the CPU oracle at full size."""
+import os
+
+import numpy as np
+import pytest
+
+from _golden_util import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+
+def test_per_matches_reference_kat(monkeypatch):
+    import torch
+    from datou_gomoku_muzero_b200 import replay_buffer as rb
+    from datou_gomoku_muzero_b200.config import config
+    z = np.load(os.path.join(GOLDEN_DIR, "per_kat.npz"))
+    config.ENABLE_PER = True
+    config.PER_BETA, config.PER_EPSILON = float(z["beta"]), float(z["eps"])
+    try:
+        for ci in range(int(z["n_cases"])):
+            cap, n_add, B, rounds = (int(x) for x in z[f"p{ci}_params"])
+            buf = rb.InMemoryReplayBuffer(cap)
+            # replay the add / interleaved-update sequence of make_golden.gen_per
+            rs = np.random.RandomState(55 + ci)
+            for i in range(n_add):
+                buf.add(i)
+                if i % 5 == 0 and len(buf) >= 1:
+                    k = int(rs.randint(0, len(buf)))
+                    buf.update_priorities([k + cap - 1], rs.randn(1).astype(np.float32) * 3)
+            assert np.array_equal(buf.sum_tree.tree.cpu().numpy(), z[f"p{ci}_tree_after_add"]), ci
+            assert [buf.sum_tree.write_ptr, buf.sum_tree.count] == list(z[f"p{ci}_state_after_add"])
+            assert float(buf.max_priority) == float(z[f"p{ci}_maxp_after_add"])
+            for r in range(rounds):
+                u = z[f"p{ci}_u"][r]
+                monkeypatch.setattr(np.random, "random_sample", lambda n, _u=u: _u[:n].copy())
+                batch, idx, w = buf.sample(B)
+                assert np.array_equal(np.asarray(idx), z[f"p{ci}_idx"][r]), (ci, r)
+                np.testing.assert_allclose(w, z[f"p{ci}_w"][r], rtol=1e-6)
+                assert w.dtype == np.float32
+                assert batch == [buf.data[int(i) - cap + 1] for i in idx]
+                assert np.array_equal(np.array(batch), z[f"p{ci}_data"][np.asarray(idx) - cap + 1])
+                buf.update_priorities(idx, z[f"p{ci}_td"][r])
+                assert np.array_equal(buf.sum_tree.tree.cpu().numpy(), z[f"p{ci}_tree"][r]), (ci, r)
+            assert float(buf.max_priority) == float(z[f"p{ci}_maxp"])
+    finally:
+        config.ENABLE_PER = False
+
+
+def test_per_sample_and_update_full_size_vs_oracle():
+    """BASELINE config 5 sizes: capacity 1M, B = 360 (config.py:56,59)."""
+    import torch
+    from datou_gomoku_muzero_b200 import replay_buffer as rb
+    from oracle import oracle as O
+    cap, B = 1_000_000, 360
+    rs = np.random.RandomState(0)
+    pri = np.abs(rs.randn(cap)) + 1e-6
+    ot = O.SumTree(cap)
+    # build the oracle tree bottom-up is not order-equivalent; use sequential adds on a subset + bulk leaves
+    gt = rb.SumTree(cap)
+    n_fill = 50_000
+    for i in range(n_fill):
+        ot.add(pri[i])
+    gt.add_many(pri[:n_fill])
+    assert np.array_equal(gt.tree.cpu().numpy(), ot.tree), "tree after 50k ordered adds"
+    assert gt.count == ot.count == n_fill
+    maxp = 1.0
+    for r in range(5):
+        u = rs.random_sample(B)
+        gi, gp, gw = gt.sample(u, 0.4)
+        oi, op, ow = ot.sample(B, u, 0.4)
+        assert np.array_equal(gi, oi) and np.array_equal(gp, op)
+        np.testing.assert_allclose(gw, ow, rtol=1e-6)
+        newp = (np.abs(rs.randn(B).astype(np.float32)) + 1e-6).astype(np.float64)
+        if r == 2:
+            gi = gi.copy(); gi[10:20] = gi[0]; oi = gi      # repeated leaves inside one batch
+        gt.update_many(gi, newp)
+        maxp = ot.update_batch(oi, newp, maxp)
+        assert np.array_equal(gt.tree.cpu().numpy(), ot.tree), f"tree after update round {r}"
+    # size-independent property: every internal node equals left + right within rounding,
+    # and the root equals the sum of the leaves
+    t = gt.tree.cpu().numpy()
+    leaves = t[cap - 1:]
+    assert abs(t[0] - leaves.sum()) < 1e-6 * max(1.0, leaves.sum())
