@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Headline benchmark: MCTS simulations/s (and self-play moves/s) of AlphaZero-mode 15x15 Gomoku
+self-play, 400 simulations per move, 4096 concurrent games per GPU (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--games G]
+
+A "step" is one self-play move for every game on the GPU: Gumbel noise, one full 400-simulation
+search per game, decision, do_move + win/draw detection, restart of finished games.  Rank 0
+prints ONE JSON line.  `--impl reference` times the CPU oracle port (oracle/, the reference is
+pure Python and cannot travel to the GPU box) on all host threads on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N, N_IN_ROW, S, K_TOP = 15, 5, 400, 16
+A = N * N
+E0_SEED, LOGIT_DIV = 2024, 16
+
+
+def algorithmic_bytes_per_sim(mean_depth: float) -> float:
+    """(d-1)(16A + ceil(A/8) + 16) + 32A + 26d + 220 bytes per AZ simulation."""
+    d = mean_depth
+    return (d - 1.0) * (16 * A + (A + 7) // 8 + 16) + 32 * A + 26 * d + 220
+
+
+def staggered_positions(G, rank, rs=None):
+    """Synthetic mid-game roots: game g starts with (g*37) % 160 random stones, colours alternating."""
+    rs = rs or np.random.RandomState(1234 + rank)
+    boards = np.zeros((G, A), np.int8)
+    players = np.ones(G, np.int8)
+    last = np.full(G, -1, np.int32)
+    mc = np.zeros(G, np.int32)
+    for g in range(G):
+        k = (g * 37) % 160
+        cells = rs.permutation(A)[:k]
+        boards[g, cells[0::2]] = 1
+        boards[g, cells[1::2]] = -1
+        players[g] = 1 if k % 2 == 0 else -1
+        last[g] = cells[-1] if k else -1
+        mc[g] = k
+    return boards, players, last, mc
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port (C restatement of the reference search, pinned to the reference's
+    golden vectors) on every host thread; each step = one search for `games` games of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    threads = oracle.max_threads()
+    games = args.cpu_games or threads * 8
+    cfg = oracle.make_config(board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP,
+                             eval_seed=E0_SEED, logit_div=LOGIT_DIV)
+    boards, players, last, mc = staggered_positions(games, 0)
+    rs = np.random.RandomState(7)
+    for _ in range(args.warmup):
+        oracle.search_batch(cfg, boards, players, last, mc, rs.gumbel(0, 1, (games, A)), n_threads=threads, want_visits=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.search_batch(cfg, boards, players, last, mc, rs.gumbel(0, 1, (games, A)), n_threads=threads, want_visits=False)
+    dt = time.perf_counter() - t0
+    sims = games * S * args.steps / dt
+    sample = f"{args.steps} steps x {games} searches of 15x15/400 sims (E0 evaluator) on {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "mcts_sims_per_sec", "value": sims, "unit": "sims/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "moves_per_sec": games * args.steps / dt,
+        "config": {"workload": "AlphaZero-mode 15x15 Gomoku, 400 sims, E0 fixed evaluator, CPU oracle port", "games": games},
+        "cpu_baseline": {"value": sims, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": sims, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def cpu_baseline_leg(budget_s=10.0):
+    from oracle import oracle
+    threads = oracle.max_threads()
+    games = threads * 8
+    cfg = oracle.make_config(board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP,
+                             eval_seed=E0_SEED, logit_div=LOGIT_DIV)
+    boards, players, last, mc = staggered_positions(games, 0)
+    rs = np.random.RandomState(7)
+    oracle.search_batch(cfg, boards, players, last, mc, rs.gumbel(0, 1, (games, A)), n_threads=threads, want_visits=False)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        oracle.search_batch(cfg, boards, players, last, mc, rs.gumbel(0, 1, (games, A)), n_threads=threads, want_visits=False)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": games * S * n / dt, "unit": "sims/s", "cores": threads, "kind": "port",
+            "sample": f"{n} batches x {games} searches of 15x15/400 sims (E0) on {threads} threads, {dt:.1f} s"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    G = args.games
+
+    eng = SearchEngine(G, board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP, device=dev)
+    sp = SelfPlayEngine(eng, "e0", seed=E0_SEED, logit_div=LOGIT_DIV, noise_seed=1000 + rank)
+    eng.set_roots(*staggered_positions(G, rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- mean leaf depth of this workload (one untimed traced search) for the algorithmic bytes
+    sp.e.fill_gumbel(sp.gumbel, 999, 0)
+    _, td = eng.search_e0(sp.gumbel, E0_SEED, LOGIT_DIV, trace=True)
+    mean_depth = float(td[:, : S - 1].float().mean().item())
+    del td
+
+    for _ in range(args.warmup):
+        sp.step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- timed region: K whole self-play moves, device resident
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    finished = torch.zeros((), dtype=torch.int64, device=dev)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        sp.e.fill_gumbel(sp.gumbel, sp.noise_seed, sp.noise_counter)
+        sp.noise_counter += sp.gumbel.numel()
+        k0[i].record()
+        eng.search_e0(sp.gumbel, E0_SEED, LOGIT_DIV)      # the dominant kernel, timed on its own stream
+        k1[i].record()
+        _, _, action, _ = eng.finalize(want_visits=False)
+        winner = eng.game_step(action)
+        torch.ne(winner, 2, out=sp.done_mask)
+        finished += sp.done_mask.sum()
+        eng.reset_games(sp.done_mask)
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = eng.launches - launches0
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)]))
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+
+    # ---- e2e: the public batch API with HOST buffers (H2D of roots + noise, D2H of results) per step
+    from datou_gomoku_muzero_b200.mcts import AlphaZeroMCTS
+    mcts = AlphaZeroMCTS.for_engine(eng, evaluator="e0", eval_seed=E0_SEED, logit_div=LOGIT_DIV)
+    hb, hp, hl, hm = staggered_positions(G, rank)
+    hgum = np.random.RandomState(5 + rank).gumbel(0, 1, (G, A))
+    for _ in range(2):
+        mcts.search_batch(hb, hp, hl, hm, hgum)
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pol, val, act = mcts.search_batch(hb, hp, hl, hm, hgum)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sims_per_step = G * S * world
+    value = sims_per_step * args.steps / (elapsed_ms * 1e-3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_per_launch = algorithmic_bytes_per_sim(mean_depth) * G * (S - 1)
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_search_e0_bytes_per_launch")
+    except Exception:
+        pass
+    out = {
+        "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "moves_per_sec": G * world * args.steps / (elapsed_ms * 1e-3),
+        "config": {"workload": "AlphaZero-mode 15x15 Gomoku self-play, 400 sims/move, 4096 concurrent games per GPU "
+                               "(BASELINE configs[1]), E0 fixed deterministic evaluator inlined in the search kernel",
+                   "games_per_gpu": G, "board": N, "num_simulations": S, "num_top_actions": K_TOP,
+                   "roots": "staggered synthetic mid-game positions (0..159 stones), finished games restarted",
+                   "l2": "node pools (2.6 GB per GPU) exceed the 126 MB L2; no explicit flush",
+                   "mean_leaf_depth": mean_depth},
+        "e2e": {"value": sims_per_step * e2e_steps / e2e_s, "unit": "sims/s",
+                "h2d_bytes_per_step": int(hb.nbytes + hp.nbytes + hl.nbytes + hm.nbytes + hgum.nbytes),
+                "d2h_bytes_per_step": int(pol.nbytes + val.nbytes + act.nbytes), "steps": e2e_steps,
+                "api": "AlphaZeroMCTS.search_batch(host boards, players, last_moves, move_counts, gumbel)"},
+        "gpu_launches": launches,
+        "games_finished_in_timed_region": int(finished.item()),
+        "roofline": {"bound": "hbm", "kernel": "k_search_e0<2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "kernel_ms_per_launch": kernel_ms,
+                     "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(mean_depth),
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                     "note": "one simulation in flight per game (bit-exact visit counts) => latency/occupancy bound, not HBM bound"},
+        "clocks": sampler.summary(),
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_leg(args.cpu_seconds)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
+    ap.add_argument("--cpu-games", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,7 +39,7 @@ SIGNATURES = {
     "gmz_get_roots": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "gmz_root_expand": (C.c_int, [_P, _P, _P, C.c_int, _P, _P]),
     "gmz_select": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
-    "gmz_select_mz": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "gmz_select_mz": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "gmz_expand_backup": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
     "gmz_finalize": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "gmz_e0_eval_obs": (C.c_int, [_P, C.c_int, C.c_int, C.c_uint64, C.c_int, _P, _P, _P]),

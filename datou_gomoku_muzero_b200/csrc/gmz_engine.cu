@@ -158,7 +158,7 @@ k_root_expand(Params p, const float *logits, const void *values, int vdtype, con
 
 template <int NC, bool MZ, typename T>
 __global__ void __launch_bounds__(CTA_THREADS)
-k_select(Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, int32_t *out_depth)
+k_select(Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, int32_t *out_depth, int32_t *out_reps)
 {
     // AZ: out_a = leaf action (trace).  MZ: out_a = parent slot, out_b = action, out_c = child slot.
     const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -175,6 +175,7 @@ k_select(Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, 
             if (out_b) out_b[g] = -1;
             if (out_c) out_c[g] = -1;
             if (out_depth) out_depth[g] = 0;
+            if (out_reps) out_reps[g] = 0;
             p.gs[g].leaf_depth = 0;
         }
         return;
@@ -195,6 +196,7 @@ k_select(Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, 
             if (out_c) out_c[g] = (int32_t)(w.nbase + (size_t)w.num_nodes);
         } else if (out_a) out_a[g] = la;
         if (out_depth) out_depth[g] = depth;
+        if (out_reps) out_reps[g] = MZ ? w.n_surv : 1;
     }
 }
 
@@ -605,16 +607,16 @@ extern "C" int gmz_select(gmz_engine *e, void *leaf_obs, int obs_dtype, int32_t 
     if (e->p.mode != GMZ_MODE_ALPHAZERO) return fail("gmz_select: engine is in MuZero mode, use gmz_select_mz");
     if (obs_dtype != GMZ_F32) return fail("gmz_select: only GMZ_F32 observations are supported");
     DISPATCH_NC(e, k_select<NC, false, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)leaf_obs, out_leaf_action,
-                                                                                     nullptr, nullptr, out_leaf_depth));
+                                                                                     nullptr, nullptr, out_leaf_depth, nullptr));
     return check_launch("k_select");
 }
 extern "C" int gmz_select_mz(gmz_engine *e, int32_t *out_parent_slot, int32_t *out_action, int32_t *out_child_slot,
-                             int32_t *out_leaf_depth, gmz_stream stream)
+                             int32_t *out_leaf_depth, int32_t *out_reps, gmz_stream stream)
 {
     if (!e) return fail("gmz_select_mz: null engine");
     if (e->p.mode != GMZ_MODE_MUZERO) return fail("gmz_select_mz: engine is in AlphaZero mode, use gmz_select");
     DISPATCH_NC(e, k_select<NC, true, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, nullptr, out_parent_slot, out_action,
-                                                                                    out_child_slot, out_leaf_depth));
+                                                                                    out_child_slot, out_leaf_depth, out_reps));
     return check_launch("k_select_mz");
 }
 extern "C" int gmz_expand_backup(gmz_engine *e, const float *logits, const void *values, const void *rewards,

@@ -138,14 +138,15 @@ class SearchEngine:
         self.launches += 1
         return self.leaf_obs
 
-    def select_mz(self):
-        """MuZero mode: (parent_slot, action, child_slot, depth) int32 [G]; -1 where nothing to evaluate."""
+    def select_mz(self, with_reps=False):
+        """MuZero mode: (parent_slot, action, child_slot, depth[, reps]) int32 [G]; -1 where nothing to evaluate."""
         if not hasattr(self, "_mz_out"):
-            self._mz_out = [torch.zeros(self.G, dtype=torch.int32, device=self.device) for _ in range(4)]
-        a, b, c, d = self._mz_out
-        check(self.lib.gmz_select_mz(self.handle, _ptr(a), _ptr(b), _ptr(c), _ptr(d), self._stream()), "gmz_select_mz")
+            self._mz_out = [torch.zeros(self.G, dtype=torch.int32, device=self.device) for _ in range(5)]
+        a, b, c, d, r = self._mz_out
+        check(self.lib.gmz_select_mz(self.handle, _ptr(a), _ptr(b), _ptr(c), _ptr(d), _ptr(r), self._stream()),
+              "gmz_select_mz")
         self.launches += 1
-        return a, b, c, d
+        return (a, b, c, d, r) if with_reps else (a, b, c, d)
 
     def expand_backup(self, logits, values, rewards=None):
         lg = self._dev(logits, torch.float32).reshape(self.G, self.A)

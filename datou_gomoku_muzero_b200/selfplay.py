@@ -1,0 +1,62 @@
+"""Batched self-play driver: the device-resident replacement of the reference's per-process game
+loop (workers.py:162-189): search -> record -> do_move -> get_game_ended -> restart, for G games
+at once with no host round trip inside a move.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import SearchEngine
+
+
+class SelfPlayEngine:
+    """evaluator: "e0" (fixed deterministic evaluator, fused persistent-kernel search) or a callable
+    `f(obs f32 [G,3,N,N]) -> (logits f32 [G,A], values f32/f64 [G])` run on the device (stepwise path)."""
+
+    def __init__(self, engine: SearchEngine, evaluator="e0", seed=0, logit_div=16, noise_seed=0):
+        self.e = engine
+        self.evaluator = evaluator
+        self.seed, self.logit_div, self.noise_seed = int(seed), int(logit_div), int(noise_seed)
+        G, A = engine.G, engine.A
+        self.gumbel = torch.empty((G, A), dtype=torch.float64, device=engine.device)
+        self.noise_counter = 0
+        self.moves_played = 0
+        self.games_finished = 0
+        self.done_mask = torch.zeros(G, dtype=torch.uint8, device=engine.device)
+        engine.reset_games()
+
+    def search(self, gumbel=None):
+        """One search for every game from its current root; returns finalize() outputs."""
+        e = self.e
+        if gumbel is None:
+            e.fill_gumbel(self.gumbel, self.noise_seed, self.noise_counter)
+            self.noise_counter += self.gumbel.numel()
+            gumbel = self.gumbel
+        if self.evaluator == "e0":
+            e.search_e0(gumbel, self.seed, self.logit_div)
+        else:
+            obs = e.root_obs()
+            lg, v = self.evaluator(obs)
+            e.root_expand(lg, v, gumbel)
+            for _ in range(e.S - 1):
+                obs = e.select()
+                lg, v = self.evaluator(obs)
+                e.expand_backup(lg, v)
+        return e.finalize(want_visits=False)
+
+    def step(self, restart=True):
+        """One self-play move for all G games (workers.py:168-181) + restart of finished games."""
+        e = self.e
+        _, _, action, _ = self.search()
+        winner = e.game_step(action)
+        self.moves_played += e.G
+        if restart:
+            torch.ne(winner, 2, out=self.done_mask)
+            e.reset_games(self.done_mask)
+        return winner
+
+    def count_finished(self, winner):
+        n = int((winner != 2).sum().item())
+        self.games_finished += n
+        return n

@@ -101,9 +101,11 @@ int gmz_select(gmz_engine *e, void *leaf_obs, int obs_dtype, int32_t *out_leaf_a
 /* MuZero mode: the len(selected_children_actions) identical selections of
  * mcts.py:326-332, deduplicated.  Outputs int32 [G]: parent_slot (index of the
  * parent's hidden state, g*S + node), action, child_slot (where the evaluator's
- * next hidden state belongs), or -1 for games with nothing to evaluate. */
+ * next hidden state belongs), or -1 for games with nothing to evaluate;
+ * out_reps = len(selected_children_actions), the number of identical rows the
+ * reference would have sent and of backups the leaf will receive. */
 int gmz_select_mz(gmz_engine *e, int32_t *out_parent_slot, int32_t *out_action, int32_t *out_child_slot,
-                  int32_t *out_leaf_depth, gmz_stream stream);
+                  int32_t *out_leaf_depth, int32_t *out_reps, gmz_stream stream);
 /* leaf.expand + _backpropagate + sim_count update + sequential halving
  * (mcts.py:260-268 / 340-350): logits f32 [G,A], values [G], rewards [G]
  * (same dtype as values; NULL = 0.0, AlphaZero mode). */
