@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libgmz.so")
+SO = os.environ.get("GMZ_LIB") or os.path.join(HERE, "libgmz.so")   # GMZ_LIB: development override
 
 GMZ_MODE_ALPHAZERO, GMZ_MODE_MUZERO = 0, 1
 GMZ_F32, GMZ_F64, GMZ_BF16 = 0, 1, 2

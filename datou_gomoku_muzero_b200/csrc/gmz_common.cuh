@@ -71,17 +71,53 @@ struct Params {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double dclip1(double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); }  // np.clip(v,-1,1)
 
-__device__ __forceinline__ double warp_max_f64(double v)
+// Order-preserving map double -> u64 (no NaNs on this path): a < b  <=>  key(a) < key(b).
+__device__ __forceinline__ u64 f64_key(double v)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(GMZ_FULL, v, o));
-    return v;
+    const u64 b = (u64)__double_as_longlong(v);
+    return b ^ ((b >> 63) ? ~0ull : 0x8000000000000000ull);
 }
-__device__ __forceinline__ double warp_min_f64(double v)
+__device__ __forceinline__ double f64_unkey(u64 k)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(GMZ_FULL, v, o));
-    return v;
+    return __longlong_as_double((long long)(k ^ ((k >> 63) ? 0x8000000000000000ull : ~0ull)));
+}
+// warp max of keys with two 32-bit REDUX instead of ten shuffles
+__device__ __forceinline__ u64 warp_max_key(u64 k)
+{
+    const unsigned hi = __reduce_max_sync(GMZ_FULL, (unsigned)(k >> 32));
+    const unsigned lo = __reduce_max_sync(GMZ_FULL, (unsigned)(k >> 32) == hi ? (unsigned)k : 0u);
+    return ((u64)hi << 32) | lo;
+}
+__device__ __forceinline__ double warp_max_f64(double v) { return f64_unkey(warp_max_key(f64_key(v))); }
+__device__ __forceinline__ double warp_min_f64(double v) { return -f64_unkey(warp_max_key(f64_key(-v))); }
+__device__ __forceinline__ double dmax2(double a, double b) { return b > a ? b : a; }
+__device__ __forceinline__ double dmin2(double a, double b) { return b < a ? b : a; }
+
+// exp(x) for x <= 0 (softmax arguments after subtracting the max), ~1 ulp: Cody-Waite range
+// reduction + degree-11 polynomial, 2^k applied to the exponent field.  A pure function of x,
+// so equal inputs give equal outputs (exact ties stay exact).  Far tail -> libdevice exp.
+static __device__ __noinline__ double exp_far_tail(double x) { return exp(x); }
+__device__ __forceinline__ double exp_nonpos(double x)
+{
+    if (x < -700.0) return exp_far_tail(x);
+    double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int k = __double2loint(t);
+    t -= 6755399441055744.0;
+    double r = fma(t, -6.93147180559945286e-01, x);
+    r = fma(t, -2.31904681384629956e-17, r);
+    double q = 2.5052097064908941e-08;
+    q = fma(q, r, 2.7626262793835868e-07);
+    q = fma(q, r, 2.7557414788000726e-06);
+    q = fma(q, r, 2.4801504602132958e-05);
+    q = fma(q, r, 1.9841269707468915e-04);
+    q = fma(q, r, 1.3888888932258898e-03);
+    q = fma(q, r, 8.3333333333978320e-03);
+    q = fma(q, r, 4.1666666666573905e-02);
+    q = fma(q, r, 1.6666666666666563e-01);
+    q = fma(q, r, 5.0000000000000056e-01);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    return __hiloint2double(__double2hiint(q) + (int)((unsigned)k << 20), __double2loint(q));
 }
 // xor-butterfly sum: a+b == b+a exactly, so every lane ends with the same bits
 __device__ __forceinline__ double warp_sum_f64(double v)
@@ -134,9 +170,11 @@ __device__ __forceinline__ u64 e0_hash_planes(u64 seed, u64 own_w, u64 opp_w, in
     for (int w = 0; w < nw; ++w) h = mix64(h ^ shfl_u64(opp_w, w));
     return mix64(h ^ (u64)(long long)(last + 1));
 }
-__device__ __forceinline__ float e0_logit(u64 h, int a, float logit_div)
+// logit = (k - 32) / logit_div; when logit_div is a power of two (inv_div != 0) the product with
+// the exact reciprocal is the same float, without the division sequence.
+__device__ __forceinline__ float e0_logit(u64 h, int a, float logit_div, float inv_div)
 {
-    int k = (int)(mix64(h + (u64)(a + 1) * E0_GOLD) >> 58);
-    return __fdiv_rn((float)(k - 32), logit_div);
+    const int k = (int)(mix64(h + (u64)(a + 1) * E0_GOLD) >> 58);
+    return inv_div != 0.0f ? __fmul_rn((float)(k - 32), inv_div) : __fdiv_rn((float)(k - 32), logit_div);
 }
 __device__ __forceinline__ double e0_value(u64 h) { return (double)((int)((mix64(h ^ E0_CV) >> 40) % 33) - 16) / 16.0; }

@@ -181,10 +181,11 @@ k_select(Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, 
         return;
     }
     wg_valid_bits<NC>(w, lane);
+    __shared__ SelScratch<NC> s_sel[WARPS_PER_CTA];
     short *path = p.path + (size_t)g * (p.S + 2);
     u64 P = w.P, M = w.M; int colour = w.to_move;
     int lp, la;
-    const int depth = descend<NC, MZ>(p, w, path, lane, lp, la, P, M, colour);
+    const int depth = descend<NC, MZ>(p, w, path, s_sel[threadIdx.x >> 5], lane, lp, la, P, M, colour);
     if (!MZ && leaf_obs)   // colour is now the player to move at the leaf; last move = la
         obs_write<NC, T>(leaf_obs + (size_t)g * 3 * p.A, p.A, colour > 0 ? P : M, colour > 0 ? M : P, la, lane);
     if (lane == 0) {
@@ -332,7 +333,7 @@ k_finalize(Params p, double *policy, double *value, int32_t *action, int32_t *vi
 // E0 evaluator kernels
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CTA_THREADS)
-k_e0_eval_obs(const float *obs, int B, int N, u64 seed, float logit_div, float *logits, double *values)
+k_e0_eval_obs(const float *obs, int B, int N, u64 seed, float logit_div, float inv_div, float *logits, double *values)
 {
     const int lane = threadIdx.x & 31, b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -352,17 +353,21 @@ k_e0_eval_obs(const float *obs, int B, int N, u64 seed, float logit_div, float *
         if (lane == w) { own = ow; opp = pw; }
     }
     const u64 h = e0_hash_planes(seed, own, opp, nw, last);
-    for (int a = lane; a < A; a += 32) logits[(size_t)b * A + a] = e0_logit(h, a, logit_div);
+    for (int a = lane; a < A; a += 32) logits[(size_t)b * A + a] = e0_logit(h, a, logit_div, inv_div);
     if (lane == 0) values[b] = e0_value(h);
 }
 
 // The whole search of mcts.py:197-280 for one game per warp, E0 inlined: root evaluation,
 // Gumbel top-k, then S-1 x { select, replay, evaluate, expand, backup, halving }.
+#ifndef GMZ_SEARCH_MIN_CTAS
+#define GMZ_SEARCH_MIN_CTAS 5
+#endif
 template <int NC>
-__global__ void __launch_bounds__(CTA_THREADS)
-k_search_e0(Params p, const double *gumbel, u64 seed, float logit_div, int32_t *trace_a, int32_t *trace_d)
+__global__ void __launch_bounds__(CTA_THREADS, GMZ_SEARCH_MIN_CTAS)
+k_search_e0(Params p, const double *gumbel, u64 seed, float logit_div, float inv_div, int32_t *trace_a, int32_t *trace_d)
 {
     extern __shared__ short s_path[];
+    __shared__ SelScratch<NC> s_sel[WARPS_PER_CTA];
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_CTA + wi;
     if (g >= p.G) return;
     WG w; wg_load(p, g, lane, w);
@@ -376,7 +381,7 @@ k_search_e0(Params p, const double *gumbel, u64 seed, float logit_div, int32_t *
 #pragma unroll
         for (int i = 0; i < 4 * NC; ++i) {
             const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
-            lg[i] = a < p.A ? e0_logit(h, a, logit_div) : 0.0f;
+            lg[i] = a < p.A ? e0_logit(h, a, logit_div, inv_div) : 0.0f;
             gum[i] = a < p.A ? gumbel[(size_t)g * p.A + a] : 0.0;
         }
         root_init<NC>(p, w, lg, gum, e0_value(h), lane);
@@ -386,15 +391,24 @@ k_search_e0(Params p, const double *gumbel, u64 seed, float logit_div, int32_t *
     while (w.sim_count < p.S) {
         u64 P = w.P, M = w.M; int colour = w.to_move;
         int lp, la;
-        const int depth = descend<NC, false>(p, w, path, lane, lp, la, P, M, colour);
+        const int depth = descend<NC, false>(p, w, path, s_sel[wi], lane, lp, la, P, M, colour);
         const u64 h = e0_hash_planes(seed, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la);
-#pragma unroll
-        for (int i = 0; i < 4 * NC; ++i) {
-            const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
-            lg[i] = a < p.A ? e0_logit(h, a, logit_div) : 0.0f;
-        }
         const int nn = w.num_nodes;
-        node_write_row<NC>(p, w, nn, lg, lane);
+        {   // evaluate + leaf.expand fused: logits go straight into the new node's row
+            float *lrow = p.logits + (w.nbase + (size_t)nn) * (size_t)p.AP;
+            short *crow = p.child + (w.nbase + (size_t)nn) * (size_t)p.AP;
+#pragma unroll 1
+            for (int j = 0; j < NC; ++j) {
+                const int a0 = 128 * j + 4 * lane;
+                float4 v;
+                v.x = a0 + 0 < p.A ? e0_logit(h, a0 + 0, logit_div, inv_div) : 0.0f;
+                v.y = a0 + 1 < p.A ? e0_logit(h, a0 + 1, logit_div, inv_div) : 0.0f;
+                v.z = a0 + 2 < p.A ? e0_logit(h, a0 + 2, logit_div, inv_div) : 0.0f;
+                v.w = a0 + 3 < p.A ? e0_logit(h, a0 + 3, logit_div, inv_div) : 0.0f;
+                *reinterpret_cast<float4 *>(lrow + a0) = v;
+                *reinterpret_cast<short4 *>(crow + a0) = make_short4(-1, -1, -1, -1);
+            }
+        }
         if (lane == 0) {
             p.child[(w.nbase + (size_t)lp) * (size_t)p.AP + la] = (short)nn;
             if (trace_a) trace_a[(size_t)g * p.S + ev] = la;
@@ -475,6 +489,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_game_step(Params p, const int32
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// exact reciprocal of a power-of-two divisor, else 0 (kernel then divides)
+static float pow2_inv(int d) { return (d > 0 && (d & (d - 1)) == 0) ? 1.0f / (float)d : 0.0f; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout { size_t gs, logits, child, nN, nW, nR, path, total; };
@@ -648,7 +664,7 @@ extern "C" int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint
     if (batch <= 0) return 0;
     if (board_size < 1 || board_size > GMZ_MAX_BOARD) return fail("gmz_e0_eval_obs: board_size out of range");
     k_e0_eval_obs<<<(batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA, CTA_THREADS, 0, (cudaStream_t)stream>>>(
-        obs, batch, board_size, (u64)seed, (float)logit_div, logits, values);
+        obs, batch, board_size, (u64)seed, (float)logit_div, pow2_inv(logit_div), logits, values);
     return check_launch("k_e0_eval_obs");
 }
 extern "C" int gmz_search_e0(gmz_engine *e, const double *gumbel, uint64_t seed, int logit_div,
@@ -659,7 +675,8 @@ extern "C" int gmz_search_e0(gmz_engine *e, const double *gumbel, uint64_t seed,
     const size_t smem = (size_t)WARPS_PER_CTA * (e->p.S + 2) * sizeof(short);
     DISPATCH_NC(e, {
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_search_e0<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_search_e0<NC><<<GRID(e), smem, (cudaStream_t)stream>>>(e->p, gumbel, (u64)seed, (float)logit_div, trace_leaf_action, trace_leaf_depth);
+        k_search_e0<NC><<<GRID(e), smem, (cudaStream_t)stream>>>(e->p, gumbel, (u64)seed, (float)logit_div, pow2_inv(logit_div),
+                                                                 trace_leaf_action, trace_leaf_depth);
     });
     return check_launch("k_search_e0");
 }

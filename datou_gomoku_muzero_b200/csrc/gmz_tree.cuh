@@ -130,7 +130,7 @@ __device__ __forceinline__ double row_softmax(const Params &p, const WG &w, cons
         if ((w.vb >> i) & 1u) {
             const double sig = r.ch[i] >= 0 ? __dmul_rn(scale, mm_norm(r.q[i], rng, w.mm_min, denom)) : sig0;
             x[i] = __dadd_rn((double)r.lg[i], sig);
-            lmx = fmax(lmx, x[i]);
+            lmx = dmax2(lmx, x[i]);
         } else x[i] = -INFINITY;
     }
     const double mx = warp_max_f64(lmx);
@@ -144,36 +144,133 @@ __device__ __forceinline__ double row_softmax(const Params &p, const WG &w, cons
     return __ddiv_rn(1.0, sum);
 }
 
+// Per-warp shared scratch for the visited children of the node being scored.
+template <int NC>
+struct SelScratch {
+    int key[128 * NC];      // (action << 16) | child node id
+    float lg[128 * NC];     // logit of that action
+    int n[128 * NC];        // child visit count
+    double x[128 * NC];     // child value_sum, then logit + sigma, then exp(...)
+    double dx[128 * NC];    // dense pass: element i of lane l at [32*i + l] (keeps the exp loop rolled:
+                            // small code matters more than registers here, the kernel is I-cache bound)
+};
+
 // _select_action at an interior node (mcts.py:106-117):
 // argmax_a  softmax(logits + sigma)[a] - N(a) / (1 + sum_b N(b))   over the ROOT-valid actions.
+// Most of a node's A children are unvisited (q = 0, N = 0, same sigma): those are scored in a
+// branch-free dense pass from the row alone.  The few visited children are compacted into
+// `sc` (one per lane) and scored in a sparse pass that gathers their N / W.
 template <int NC, bool MZ>
-__device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, int &action, int &child)
+__device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelScratch<NC> &sc,
+                                                int &action, int &child)
 {
-    Row<NC> r;
-    row_load<NC, MZ>(p, w, node, lane, r);
-    double x[4 * NC];
-    const double inv = row_softmax<NC>(p, w, r, x);
-    const double dn = (double)(1 + r.sumN);
-    double best = -INFINITY; int ba = 0x7fffffff;
+    constexpr int E = 4 * NC;
+    const size_t ni = w.nbase + (size_t)node;
+    const float *lrow = p.logits + ni * (size_t)p.AP;
+    const short *crow = p.child + ni * (size_t)p.AP;
+    float lg[E]; short ch[E];
 #pragma unroll
-    for (int i = 0; i < 4 * NC; ++i) {
-        if ((w.vb >> i) & 1u) {
-            double sc = __dmul_rn(x[i], inv);
-            if (r.n[i] > 0) sc = __dsub_rn(sc, __ddiv_rn((double)r.n[i], dn));
-            const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
-            if (sc > best) { best = sc; ba = a; }
+    for (int j = 0; j < NC; ++j) {
+        const float4 t = *reinterpret_cast<const float4 *>(lrow + 128 * j + 4 * lane);
+        const short4 c = *reinterpret_cast<const short4 *>(crow + 128 * j + 4 * lane);
+        lg[4 * j + 0] = t.x; lg[4 * j + 1] = t.y; lg[4 * j + 2] = t.z; lg[4 * j + 3] = t.w;
+        ch[4 * j + 0] = c.x; ch[4 * j + 1] = c.y; ch[4 * j + 2] = c.z; ch[4 * j + 3] = c.w;
+    }
+    unsigned vm = 0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) vm |= (ch[i] >= 0 ? 1u : 0u) << i;
+    // compact the visited children: lane prefix over popc(vm)
+    int total = 0;
+    if (__any_sync(GMZ_FULL, vm != 0)) {
+        const int cnt = __popc(vm);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(GMZ_FULL, inc, o); if (lane >= o) inc += t; }
+        total = __shfl_sync(GMZ_FULL, inc, 31);
+        int pos = inc - cnt;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            if ((vm >> i) & 1u) {
+                sc.key[pos] = ((128 * (i >> 2) + 4 * lane + (i & 3)) << 16) | (int)ch[i];
+                sc.lg[pos] = lg[i];
+                ++pos;
+            }
+        }
+        __syncwarp();
+    }
+    // sparse pass A: gather N and W of the visited children (one memory round trip)
+    int lmax = 0, lsum = 0;
+    for (int k = lane; k < total; k += 32) {
+        const size_t ci = w.nbase + (size_t)(sc.key[k] & 0xffff);
+        const int nn = p.nN[ci];
+        sc.n[k] = nn; sc.x[k] = p.nW[ci];
+        lmax = max(lmax, nn); lsum += nn;
+    }
+    int maxN = 0, sumN = 0;
+    if (total > 0) { maxN = __reduce_max_sync(GMZ_FULL, lmax); sumN = __reduce_add_sync(GMZ_FULL, lsum); }
+    const double scale = __dmul_rn(__dadd_rn(p.c_visit, (double)maxN), p.c_scale);
+    const bool rng = w.mm_max > w.mm_min;
+    const double denom = __dadd_rn(__dsub_rn(w.mm_max, w.mm_min), p.delta);
+    const double sig0 = __dmul_rn(scale, mm_norm(0.0, rng, w.mm_min, denom));   // unvisited: q = 0.0
+    double lmx = -INFINITY;
+    // sparse pass B: q -> sigma -> x
+    for (int k = lane; k < total; k += 32) {
+        const double val = __ddiv_rn(sc.x[k], (double)sc.n[k]);                 // child.get_value()
+        const double rew = MZ ? p.nR[w.nbase + (size_t)(sc.key[k] & 0xffff)] : 0.0;
+        const double q = __dadd_rn(rew, __dmul_rn(p.discount, val));
+        const double x = __dadd_rn((double)sc.lg[k], __dmul_rn(scale, mm_norm(q, rng, w.mm_min, denom)));
+        sc.x[k] = x; lmx = dmax2(lmx, x);
+    }
+    const unsigned dv = w.vb & ~vm;      // valid and unvisited: the dense set
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const double xi = __dadd_rn((double)lg[i], sig0);
+        sc.dx[32 * i + lane] = xi;
+        if ((dv >> i) & 1u) lmx = dmax2(lmx, xi);
+    }
+    const double mx = warp_max_f64(lmx);
+    double ls = 0.0;
+#pragma unroll 2
+    for (int i = 0; i < E; ++i) {
+        double e = exp_nonpos(dmin2(__dsub_rn(sc.dx[32 * i + lane], mx), 0.0));
+        e = ((dv >> i) & 1u) ? e : 0.0;
+        sc.dx[32 * i + lane] = e;
+        ls = __dadd_rn(ls, e);
+    }
+    for (int k = lane; k < total; k += 32) {
+        const double e = exp_nonpos(__dsub_rn(sc.x[k], mx));
+        sc.x[k] = e; ls = __dadd_rn(ls, e);
+    }
+    const double sum = warp_sum_f64(ls);
+    const double inv = __ddiv_rn(1.0, sum);
+    double best = -INFINITY; int ba = 0x7fffffff, bc = -1;
+#pragma unroll 4
+    for (int i = 0; i < E; ++i) {
+        const double s = __dmul_rn(sc.dx[32 * i + lane], inv);
+        if (((dv >> i) & 1u) && s > best) { best = s; ba = 128 * (i >> 2) + 4 * lane + (i & 3); }
+    }
+    if (total > 0) {
+        const double dn = (double)(1 + sumN);
+        for (int k = lane; k < total; k += 32) {
+            const double s = __dsub_rn(__dmul_rn(sc.x[k], inv), __ddiv_rn((double)sc.n[k], dn));
+            const int a = sc.key[k] >> 16;
+            if (s > best || (s == best && a < ba)) { best = s; ba = a; bc = sc.key[k] & 0xffff; }
         }
     }
-    warp_argmax_lowidx(best, ba);
-    action = ba;
-    child = p.child[(w.nbase + (size_t)node) * (size_t)p.AP + ba];
+    // warp argmax, lowest action wins ties (np.argmax, mcts.py:117)
+    const u64 mk = warp_max_key(f64_key(best));
+    const int a = __reduce_min_sync(GMZ_FULL, f64_key(best) == mk ? ba : 0x7fffffff);
+    const unsigned own = __ballot_sync(GMZ_FULL, f64_key(best) == mk && ba == a);
+    action = a;
+    child = __shfl_sync(GMZ_FULL, bc, __ffs(own) - 1);
+    __syncwarp();
 }
 
 // _select_leaf (mcts.py:88-104): root = first least-visited survivor (strict <, list order),
 // then interior selection until an unexpanded child is reached.  In AlphaZero mode the path
 // is replayed on the bitboards while descending (mcts.py:236-248).  Returns depth (edges).
 template <int NC, bool MZ>
-__device__ __forceinline__ int descend(const Params &p, const WG &w, short *path, int lane,
+__device__ __forceinline__ int descend(const Params &p, const WG &w, short *path, SelScratch<NC> &sc, int lane,
                                        int &leaf_parent, int &leaf_action, u64 &P, u64 &M, int &colour)
 {
     const unsigned key = lane < w.n_surv ? (((unsigned)w.s_n << 5) | (unsigned)lane) : 0xffffffffu;
@@ -186,7 +283,7 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, short *path
     while (node >= 0) {
         if (lane == 0) path[depth] = (short)node;
         int c;
-        select_interior<NC, MZ>(p, w, node, lane, a, c);
+        select_interior<NC, MZ>(p, w, node, lane, sc, a, c);
         if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
         parent = node; node = c; ++depth;
     }
@@ -239,7 +336,7 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const short *path
                 W = __dadd_rn(W, myv); n += 1;
                 if (pos > 0) {   // min_max_stats.update(parent.get_qsa(node.action))
                     const double q = __dadd_rn(R, __dmul_rn(p.discount, __ddiv_rn(W, (double)n)));
-                    qmin = fmin(qmin, q); qmax = fmax(qmax, q);
+                    qmin = dmin2(qmin, q); qmax = dmax2(qmax, q);
                 }
             }
             p.nN[ni] = n; p.nW[ni] = W;
@@ -247,7 +344,7 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const short *path
         }
     }
     qmin = warp_min_f64(qmin); qmax = warp_max_f64(qmax);
-    w.mm_min = fmin(w.mm_min, qmin); w.mm_max = fmax(w.mm_max, qmax);
+    w.mm_min = dmin2(w.mm_min, qmin); w.mm_max = dmax2(w.mm_max, qmax);
 }
 
 // _ready_for_next_gumbel_phase (mcts.py:166-181), tables precomputed on the host.
