@@ -165,39 +165,38 @@ def run_ours(args):
     mean_depth = float(td[:, : S - 1].float().mean().item())
     del td
 
+    from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
+    traj = TrajectoryStore(eng, extra_slots=max(64, G // 2))
     for _ in range(args.warmup):
-        sp.step()
+        sp.play(moves_per_game=1, traj=traj)          # warm-up steps: G moves each
+    traj.harvest(copy_policies=False)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    # ---- timed region: K whole self-play moves, device resident
+    # ---- timed region: K steps = K*G self-play moves (noise, 400-sim search, decision, trajectory
+    # record, do_move, win/draw check, restart), ONE persistent launch, games advance independently
     launches0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    finished = torch.zeros((), dtype=torch.int64, device=dev)
+    m0, f0 = eng.play_counters()
     barrier()
     ev0.record()
-    for i in range(args.steps):
-        sp.e.fill_gumbel(sp.gumbel, sp.noise_seed, sp.noise_counter)
-        sp.noise_counter += sp.gumbel.numel()
-        k0[i].record()
-        eng.search_e0(sp.gumbel, E0_SEED, LOGIT_DIV)      # the dominant kernel, timed on its own stream
-        k1[i].record()
-        _, _, action, _ = eng.finalize(want_visits=False)
-        winner = eng.game_step(action)
-        torch.ne(winner, 2, out=sp.done_mask)
-        finished += sp.done_mask.sum()
-        eng.reset_games(sp.done_mask)
+    sp.play(moves_per_game=args.steps, traj=traj)
     ev1.record()
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = eng.launches - launches0
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(k0, k1)]))
+    m1, f1 = eng.play_counters()
+    moves_done, finished = m1 - m0, f1 - f0
+    kernel_ms = elapsed_ms / args.steps               # the play kernel IS the timed region
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
+    md = torch.tensor([moves_done], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(md, op=dist.ReduceOp.SUM)
+    moves_total = float(md.item())
+    harvested = len(traj.harvest(copy_policies=False))
 
     # ---- e2e: the public batch API with HOST buffers (H2D of roots + noise, D2H of results) per step
     from datou_gomoku_muzero_b200.mcts import AlphaZeroMCTS
@@ -225,29 +224,30 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     sims_per_step = G * S * world
-    value = sims_per_step * args.steps / (elapsed_ms * 1e-3)
+    value = moves_total * S / (elapsed_ms * 1e-3)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    bytes_per_launch = algorithmic_bytes_per_sim(mean_depth) * G * (S - 1)
+    bytes_per_launch = algorithmic_bytes_per_sim(mean_depth) * (moves_done / args.steps) * (S - 1)   # per step
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_search_e0_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_play_e0_bytes_per_step")
     except Exception:
         pass
     out = {
         "metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "moves_per_sec": G * world * args.steps / (elapsed_ms * 1e-3),
+        "moves_per_sec": moves_total / (elapsed_ms * 1e-3),
         "config": {"workload": "AlphaZero-mode 15x15 Gomoku self-play, 400 sims/move, 4096 concurrent games per GPU "
                                "(BASELINE configs[1]), E0 fixed deterministic evaluator inlined in the search kernel",
                    "games_per_gpu": G, "board": N, "num_simulations": S, "num_top_actions": K_TOP,
-                   "roots": "staggered synthetic mid-game positions (0..159 stones), finished games restarted",
+                   "roots": "staggered synthetic mid-game positions (0..159 stones), finished games restarted in-kernel",
+                   "step": "G self-play moves; the K timed steps run as one persistent ticketed launch of K*G moves",
                    "l2": "node pools (2.6 GB per GPU) exceed the 126 MB L2; no explicit flush",
                    "mean_leaf_depth": mean_depth},
         "e2e": {"value": sims_per_step * e2e_steps / e2e_s, "unit": "sims/s",
@@ -255,9 +255,9 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(pol.nbytes + val.nbytes + act.nbytes), "steps": e2e_steps,
                 "api": "AlphaZeroMCTS.search_batch(host boards, players, last_moves, move_counts, gumbel)"},
         "gpu_launches": launches,
-        "games_finished_in_timed_region": int(finished.item()),
-        "roofline": {"bound": "hbm", "kernel": "k_search_e0<2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel_ms_per_launch": kernel_ms,
+        "games_finished_in_timed_region": int(finished), "games_harvested": harvested,
+        "roofline": {"bound": "hbm", "kernel": "k_play_e0<2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "kernel_ms_per_step": kernel_ms,
                      "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(mean_depth),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "note": "one simulation in flight per game (bit-exact visit counts) => latency/occupancy bound, not HBM bound"},

@@ -21,6 +21,13 @@ class GmzConfig(C.Structure):
                 ("discount", C.c_double)]
 
 
+class GmzTraj(C.Structure):
+    _fields_ = [("n_slots", C.c_int32), ("max_moves", C.c_int32), ("fin_cap", C.c_int32), ("reserved", C.c_int32),
+                ("policy", C.c_void_p), ("value", C.c_void_p), ("action", C.c_void_p), ("start_board", C.c_void_p),
+                ("start_info", C.c_void_p), ("free_slots", C.c_void_p), ("free_top", C.c_void_p),
+                ("fin_queue", C.c_void_p), ("fin_count", C.c_void_p)]
+
+
 class GmzError(RuntimeError):
     pass
 
@@ -46,6 +53,10 @@ SIGNATURES = {
     "gmz_search_e0": (C.c_int, [_P, _P, C.c_uint64, C.c_int, _P, _P, _P]),
     "gmz_fill_gumbel": (C.c_int, [_P, C.c_size_t, C.c_uint64, C.c_uint64, _P]),
     "gmz_game_step": (C.c_int, [_P, _P, _P, _P]),
+    "gmz_traj_init": (C.c_int, [_P, C.POINTER(GmzTraj), _P]),
+    "gmz_selfplay_e0": (C.c_int, [_P, C.POINTER(GmzTraj), C.c_uint64, C.c_int, C.c_uint64, C.c_int64, C.c_int, _P]),
+    "gmz_selfplay_unpark": (C.c_int, [_P, C.POINTER(GmzTraj), _P]),
+    "gmz_play_counters": (C.c_int, [_P, _P, _P]),
     "gmz_per_update": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, _P]),
     "gmz_per_sample": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, C.c_double, _P, _P, _P, _P]),
 }

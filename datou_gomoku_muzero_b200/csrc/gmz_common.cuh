@@ -47,8 +47,12 @@ struct __align__(128) GState {
     int leaf_depth;           // edges root -> leaf, 0 = nothing pending
     int leaf_reps;            // number of backups the pending leaf receives (MuZero: n_surv)
     int winner;               // get_game_ended(): +-1, 0 draw, 2 = None
-    int pad0;
-    char pad1[112];
+    int busy;                 // play kernel: game is owned by a warp (acquire/release flag)
+    int parked;               // finished, waiting for the host to hand out a trajectory slot
+    int traj_slot;            // trajectory slot this game records into
+    int traj_len;             // moves recorded in the current game
+    unsigned noise_ctr;       // searches done by this game (Gumbel noise counter)
+    char pad1[96];
 };
 static_assert(sizeof(GState) == 1024, "GState must be 1 KiB");
 
@@ -66,6 +70,8 @@ struct Params {
     double *nW;      // [G*S]      node.value_sum
     double *nR;      // [G*S]      node.reward (MuZero mode only)
     short *path;     // [G][S+2]   node ids root..leaf-parent of the pending simulation
+    short *pyset;    // [ceil(G/4)*4][4096] scratch for the CPython-set tie-break (rare path)
+    struct PlayCtl *ctl;   // play-kernel ticket counter + statistics
 };
 
 // ---------------------------------------------------------------------------------------------

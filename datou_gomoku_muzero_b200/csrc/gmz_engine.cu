@@ -7,6 +7,7 @@
 
 #include "../../include/gmz.h"
 #include "gmz_tree.cuh"
+#include "gmz_play.cuh"
 
 #define WARPS_PER_CTA 4
 #define CTA_THREADS (32 * WARPS_PER_CTA)
@@ -74,18 +75,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_games_reset(Params p, const uin
     const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (g >= p.G) return;
     if (mask && !mask[g]) return;
-    GState *s = p.gs + g;
-    if (lane < GMZ_WORDS) {
-        u64 v = 0;
-        const int lo = 64 * lane;
-        if (lo < p.A) v = (p.A - lo >= 64) ? ~0ull : ((1ull << (p.A - lo)) - 1ull);
-        s->p1[lane] = 0; s->m1[lane] = 0; s->valid[lane] = v;
-    }
-    if (lane == 0) {
-        s->to_move = 1; s->last_move = -1; s->move_count = 0; s->active = 1;
-        s->sim_count = 0; s->num_nodes = 0; s->leaf_depth = 0; s->n_surv = 0; s->n_init = 0;
-        s->winner = GMZ_WINNER_NONE;
-    }
+    game_reset(p, p.gs + g, lane);
 }
 
 __global__ void __launch_bounds__(CTA_THREADS)
@@ -230,103 +220,18 @@ k_expand_backup(Params p, const float *logits, const void *values, const void *r
     if (lane == 0) p.gs[g].leaf_depth = 0;
 }
 
-// CPython set iteration order over the valid actions, to break ties of the final
-// max(visit_counts, key=visit_counts.get) the way the reference does (mcts.py:274-275).
-// Runs on one lane, only when the maximum visit count is not unique.  Restates
-// Objects/setobject.c (set_add_entry / set_table_resize / set_insert_clean).
-__device__ int pyset_first_max(const u64 *vw, int A, const short *nvis, int maxn, short *table /*2048*/)
-{
-    int mask = 7, fill = 0;
-    for (int i = 0; i < 8; ++i) table[i] = -1;
-    short *cur = table, *alt = table + 2048;   // two halves of a 4096-entry scratch
-    for (int a = 0; a < A; ++a) {
-        if (!((vw[a >> 6] >> (a & 63)) & 1ull)) continue;
-        unsigned i = (unsigned)a & mask, perturb = (unsigned)a, e;
-        for (;;) {
-            e = i;
-            int probes = (i + 9 <= (unsigned)mask) ? 9 : 0; bool found = false;
-            do { if (cur[e] < 0) { found = true; break; } ++e; } while (probes--);
-            if (found) break;
-            perturb >>= 5; i = (i * 5 + 1 + perturb) & mask;
-        }
-        cur[e] = (short)a; ++fill;
-        if (fill * 5 >= mask * 3) {
-            int newsize = 8; const int minused = fill * 4;
-            while (newsize <= minused) newsize <<= 1;
-            const int nmask = newsize - 1;
-            for (int j = 0; j < newsize; ++j) alt[j] = -1;
-            for (int j = 0; j <= mask; ++j) {
-                if (cur[j] < 0) continue;
-                const unsigned h2 = (unsigned)cur[j];
-                unsigned ii = h2 & nmask, pp = h2, ee;
-                for (;;) {
-                    ee = ii;
-                    if (alt[ee] < 0) break;
-                    bool ok = false;
-                    if (ii + 9 <= (unsigned)nmask) { for (int q = 0; q < 9; ++q) { ++ee; if (alt[ee] < 0) { ok = true; break; } } }
-                    if (ok) break;
-                    pp >>= 5; ii = (ii * 5 + 1 + pp) & nmask;
-                }
-                alt[ee] = cur[j];
-            }
-            short *t = cur; cur = alt; alt = t; mask = nmask;
-        }
-    }
-    for (int j = 0; j <= mask; ++j) if (cur[j] >= 0 && nvis[cur[j]] == maxn) return cur[j];
-    return -1;
-}
-
 template <int NC, bool MZ>
 __global__ void __launch_bounds__(CTA_THREADS)
 k_finalize(Params p, double *policy, double *value, int32_t *action, int32_t *visits)
 {
-    __shared__ short s_table[WARPS_PER_CTA][4096];
     __shared__ short s_nvis[WARPS_PER_CTA][128 * NC];
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_CTA + wi;
     if (g >= p.G) return;
     WG w; wg_load(p, g, lane, w);
-    if (!w.active || w.sim_count < 1) {   // sentinel (np.zeros(A), 0.0, -1), mcts.py:214-215
-        for (int a = lane; a < p.A; a += 32) {
-            if (policy) policy[(size_t)g * p.A + a] = 0.0;
-            if (visits) visits[(size_t)g * p.A + a] = 0;
-        }
-        if (lane == 0) { if (value) value[g] = 0.0; if (action) action[g] = -1; }
-        return;
-    }
-    wg_valid_bits<NC>(w, lane);
-    Row<NC> r;
-    row_load<NC, MZ>(p, w, 0, lane, r);
-    double x[4 * NC];
-    const double inv = row_softmax<NC>(p, w, r, x);
-    int bn = -1, ba = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < 4 * NC; ++i) {
-        const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
-        s_nvis[wi][128 * (i >> 2) + 4 * lane + (i & 3)] = (short)r.n[i];
-        if (a < p.A) {
-            if (policy) policy[(size_t)g * p.A + a] = __dmul_rn(x[i], inv);
-            if (visits) visits[(size_t)g * p.A + a] = r.n[i];
-            if (((w.vb >> i) & 1u) && r.n[i] > bn) { bn = r.n[i]; ba = a; }
-        }
-    }
-    const int maxn = __reduce_max_sync(GMZ_FULL, bn);
-    int ties = 0;
-#pragma unroll
-    for (int i = 0; i < 4 * NC; ++i) ties += (((w.vb >> i) & 1u) && r.n[i] == maxn) ? 1 : 0;
-    ties = __reduce_add_sync(GMZ_FULL, ties);
-    int best = __reduce_min_sync(GMZ_FULL, bn == maxn ? ba : 0x7fffffff);
-    u64 vw[GMZ_WORDS];
-#pragma unroll
-    for (int k = 0; k < GMZ_WORDS; ++k) vw[k] = shfl_u64(w.V, k);
-    __syncwarp();
-    if (ties > 1) {
-        if (lane == 0) best = pyset_first_max(vw, p.A, s_nvis[wi], maxn, s_table[wi]);
-        best = __shfl_sync(GMZ_FULL, best, 0);
-    }
-    if (lane == 0) {
-        if (value) value[g] = __ddiv_rn(p.nW[w.nbase], (double)p.nN[w.nbase]);
-        if (action) action[g] = best;
-    }
+    double v; int a;
+    finalize_root<NC, MZ>(p, w, lane, policy ? policy + (size_t)g * p.A : nullptr, visits ? visits + (size_t)g * p.A : nullptr,
+                          s_nvis[wi], p.pyset + ((size_t)blockIdx.x * WARPS_PER_CTA + wi) * 4096, v, a);
+    if (lane == 0) { if (value) value[g] = v; if (action) action[g] = a; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -357,83 +262,35 @@ k_e0_eval_obs(const float *obs, int B, int N, u64 seed, float logit_div, float i
     if (lane == 0) values[b] = e0_value(h);
 }
 
-// The whole search of mcts.py:197-280 for one game per warp, E0 inlined: root evaluation,
-// Gumbel top-k, then S-1 x { select, replay, evaluate, expand, backup, halving }.
-#ifndef GMZ_SEARCH_MIN_CTAS
-#define GMZ_SEARCH_MIN_CTAS 5
-#endif
-template <int NC>
-__global__ void __launch_bounds__(CTA_THREADS, GMZ_SEARCH_MIN_CTAS)
-k_search_e0(Params p, const double *gumbel, u64 seed, float logit_div, float inv_div, int32_t *trace_a, int32_t *trace_d)
-{
-    extern __shared__ short s_path[];
-    __shared__ SelScratch<NC> s_sel[WARPS_PER_CTA];
-    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_CTA + wi;
-    if (g >= p.G) return;
-    WG w; wg_load(p, g, lane, w);
-    if (!w.active) return;
-    wg_valid_bits<NC>(w, lane);
-    short *path = s_path + (size_t)wi * (p.S + 2);
-    float lg[4 * NC];
-    {   // root: obs = get_board_state(current_player, last_move)  (mcts.py:203)
-        const u64 h = e0_hash_planes(seed, w.to_move > 0 ? w.P : w.M, w.to_move > 0 ? w.M : w.P, p.NW, w.last_move);
-        double gum[4 * NC];
-#pragma unroll
-        for (int i = 0; i < 4 * NC; ++i) {
-            const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
-            lg[i] = a < p.A ? e0_logit(h, a, logit_div, inv_div) : 0.0f;
-            gum[i] = a < p.A ? gumbel[(size_t)g * p.A + a] : 0.0;
-        }
-        root_init<NC>(p, w, lg, gum, e0_value(h), lane);
-    }
-    __syncwarp();
-    int ev = 0;
-    while (w.sim_count < p.S) {
-        u64 P = w.P, M = w.M; int colour = w.to_move;
-        int lp, la;
-        const int depth = descend<NC, false>(p, w, path, s_sel[wi], lane, lp, la, P, M, colour);
-        const u64 h = e0_hash_planes(seed, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la);
-        const int nn = w.num_nodes;
-        {   // evaluate + leaf.expand fused: logits go straight into the new node's row
-            float *lrow = p.logits + (w.nbase + (size_t)nn) * (size_t)p.AP;
-            short *crow = p.child + (w.nbase + (size_t)nn) * (size_t)p.AP;
-#pragma unroll 1
-            for (int j = 0; j < NC; ++j) {
-                const int a0 = 128 * j + 4 * lane;
-                float4 v;
-                v.x = a0 + 0 < p.A ? e0_logit(h, a0 + 0, logit_div, inv_div) : 0.0f;
-                v.y = a0 + 1 < p.A ? e0_logit(h, a0 + 1, logit_div, inv_div) : 0.0f;
-                v.z = a0 + 2 < p.A ? e0_logit(h, a0 + 2, logit_div, inv_div) : 0.0f;
-                v.w = a0 + 3 < p.A ? e0_logit(h, a0 + 3, logit_div, inv_div) : 0.0f;
-                *reinterpret_cast<float4 *>(lrow + a0) = v;
-                *reinterpret_cast<short4 *>(crow + a0) = make_short4(-1, -1, -1, -1);
-            }
-        }
-        if (lane == 0) {
-            p.child[(w.nbase + (size_t)lp) * (size_t)p.AP + la] = (short)nn;
-            if (trace_a) trace_a[(size_t)g * p.S + ev] = la;
-            if (trace_d) trace_d[(size_t)g * p.S + ev] = depth;
-        }
-        w.num_nodes = nn + 1; ++ev;
-        __syncwarp();
-        backup<false>(p, w, path, depth, nn, e0_value(h), 0.0, 1, lane);
-        survivor_visit(w, depth, path, nn, la, 1, lane);
-        w.sim_count += 1;
-        __syncwarp();
-        if (halving_ready(p, w)) sequential_halving<false>(p, w, lane);
-    }
-    wg_store_search(p, lane, w);
-    if (lane == 0) p.gs[g].leaf_depth = 0;
-}
-
 // Gumbel(0,1) = -log(-log(u)), u from a counter-based splitmix64 stream, 53-bit mantissa in (0,1).
 __global__ void k_fill_gumbel(double *out, size_t n, u64 seed, u64 offset)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const u64 z = mix64(mix64(seed ^ E0_GOLD) + (offset + i) * E0_GOLD);
-    const double u = ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
-    out[i] = -log(-log(u));
+    out[i] = gumbel_at(mix64(seed ^ E0_GOLD), offset + i);
+}
+
+// parked games (finished, no free trajectory slot at the time): take a slot and restart
+__global__ void __launch_bounds__(CTA_THREADS) k_unpark(Params p, TrajDev t)
+{
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= p.G) return;
+    GState *s = p.gs + g;
+    if (!s->parked) return;
+    int ok = 0, slot = -1;
+    if (lane == 0) ok = traj_pop_slot(t, slot);
+    ok = __shfl_sync(GMZ_FULL, ok, 0); slot = __shfl_sync(GMZ_FULL, slot, 0);
+    if (!ok) return;
+    game_reset(p, s, lane);
+    if (lane == 0) s->traj_slot = slot;
+}
+// give every game its initial trajectory slot (slot g) and clear the play bookkeeping
+__global__ void k_traj_init(Params p, TrajDev t)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.G) { GState *s = p.gs + i; s->traj_slot = i; s->traj_len = 0; s->parked = 0; s->busy = 0; }
+    if (i < t.n_slots - p.G) t.free_slots[i] = p.G + i;
+    if (i == 0) { *t.free_top = t.n_slots - p.G; *t.fin_count = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -446,44 +303,8 @@ __global__ void __launch_bounds__(CTA_THREADS) k_game_step(Params p, const int32
     GState *s = p.gs + g;
     const int a = actions[g];
     if (a < 0 || a >= p.A) { if (lane == 0 && out_winner) out_winner[g] = s->winner; return; }
-    const int colour = s->to_move;
-    u64 P = lane < GMZ_WORDS ? s->p1[lane] : 0ull, M = lane < GMZ_WORDS ? s->m1[lane] : 0ull;
-    bb_do_move(P, M, colour, a, lane);
-    const int mc = s->move_count + 1;
-    // check_win(last_move): 4 directions, up to n_in_row+1 stones each way (game.py:25-58).
-    // Lane l tests the cell at offset (l - span) along the direction; the ballot is the line.
-    const int r = a / p.N, c = a % p.N, span = p.n_in_row + 1;
-    const int off = lane - span;
-    bool win = false;
-    const int DR[4] = {0, 1, 1, 1}, DC[4] = {1, 0, 1, -1};
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-        const int rr = r + off * DR[d], cc = c + off * DC[d];
-        const bool in = lane <= 2 * span && rr >= 0 && rr < p.N && cc >= 0 && cc < p.N;
-        const int cell = in ? rr * p.N + cc : 0;
-        const u64 mine = shfl_u64(colour > 0 ? P : M, cell >> 6);
-        const unsigned line = __ballot_sync(GMZ_FULL, in && ((mine >> (cell & 63)) & 1ull));
-        // contiguous run through bit `span`
-        const unsigned up = line >> (span + 1);               // cells after the stone
-        const int fwd = __ffs(~up) - 1;
-        const unsigned dn = __brev(line << (32 - span));      // cells before the stone, nearest first
-        const int bwd = span > 0 ? (__ffs(~dn) - 1) : 0;
-        const int cnt = 1 + min(fwd, span) + min(bwd, span);
-        win = win || cnt >= p.n_in_row;
-    }
-    const int wv = win ? colour : (mc >= p.A ? 0 : GMZ_WINNER_NONE);
-    if (lane < GMZ_WORDS) {
-        s->p1[lane] = P; s->m1[lane] = M;
-        u64 fullm = 0; const int lo = 64 * lane;
-        if (lo < p.A) fullm = (p.A - lo >= 64) ? ~0ull : ((1ull << (p.A - lo)) - 1ull);
-        s->valid[lane] = ~(P | M) & fullm;
-    }
-    if (lane == 0) {
-        s->to_move = -colour; s->last_move = a; s->move_count = mc; s->winner = wv;
-        s->active = (wv == GMZ_WINNER_NONE);
-        s->sim_count = 0; s->leaf_depth = 0;
-        if (out_winner) out_winner[g] = wv;
-    }
+    const int wv = game_do_move(p, s, a, lane);
+    if (lane == 0 && out_winner) out_winner[g] = wv;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -493,7 +314,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_game_step(Params p, const int32
 static float pow2_inv(int d) { return (d > 0 && (d & (d - 1)) == 0) ? 1.0f / (float)d : 0.0f; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct Layout { size_t gs, logits, child, nN, nW, nR, path, total; };
+struct Layout { size_t gs, logits, child, nN, nW, nR, path, pyset, ctl, total; };
 
 static int validate(const gmz_config *c)
 {
@@ -518,6 +339,8 @@ static Layout make_layout(const gmz_config *c)
     L.nW = o; o = align_up(o + G * S * sizeof(double), 256);
     L.nR = o; if (c->mode == GMZ_MODE_MUZERO) o = align_up(o + G * S * sizeof(double), 256);
     L.path = o; o = align_up(o + G * (S + 2) * sizeof(short), 256);
+    L.pyset = o; o = align_up(o + ((G + 3) / 4 * 4) * 4096 * sizeof(short), 256);
+    L.ctl = o; o = align_up(o + sizeof(PlayCtl), 256);
     L.total = o;
     return L;
 }
@@ -565,7 +388,9 @@ extern "C" int gmz_create(const gmz_config *cfg, void *workspace, size_t workspa
     p.nN = (int *)(base + L.nN); p.nW = (double *)(base + L.nW);
     p.nR = cfg->mode == GMZ_MODE_MUZERO ? (double *)(base + L.nR) : nullptr;
     p.path = (short *)(base + L.path);
+    p.pyset = (short *)(base + L.pyset); p.ctl = (PlayCtl *)(base + L.ctl);
     cudaError_t err = cudaMemsetAsync(base + L.gs, 0, (size_t)p.G * sizeof(GState), (cudaStream_t)stream);
+    if (err == cudaSuccess) err = cudaMemsetAsync(base + L.ctl, 0, sizeof(PlayCtl), (cudaStream_t)stream);
     if (err != cudaSuccess) { free(e); return fail("cudaMemsetAsync: %s", cudaGetErrorString(err)); }
     *out = e;
     return 0;
@@ -667,18 +492,97 @@ extern "C" int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint
         obs, batch, board_size, (u64)seed, (float)logit_div, pow2_inv(logit_div), logits, values);
     return check_launch("k_e0_eval_obs");
 }
+// launch the ticketed play kernel: grid = what fits on the GPU at once (persistent), capped by the game count
+template <int NC>
+static int launch_play(gmz_engine *e, const PlayArgs &a, cudaStream_t st)
+{
+    const size_t smem = (size_t)GMZ_PLAY_WARPS * (e->p.S + 2) * sizeof(short);
+    static int occ_cache[4] = {0, 0, 0, 0};
+    if (smem + sizeof(SelScratch<NC>) * GMZ_PLAY_WARPS > 48 * 1024)
+        cudaFuncSetAttribute(k_play_e0<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!occ_cache[NC]) {
+        int occ = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(k_play_e0<NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_play_e0<NC>, 32 * GMZ_PLAY_WARPS, smem);
+        occ_cache[NC] = (occ > 0 ? occ : 1) * (sms > 0 ? sms : 148);
+    }
+    int grid = (e->p.G + GMZ_PLAY_WARPS - 1) / GMZ_PLAY_WARPS;
+    if (grid > occ_cache[NC]) grid = occ_cache[NC];
+    if (cudaMemsetAsync(&e->p.ctl->next_ticket, 0, sizeof(unsigned long long), st) != cudaSuccess) return fail("cudaMemsetAsync(ctl)");
+    k_play_e0<NC><<<grid, 32 * GMZ_PLAY_WARPS, smem, st>>>(e->p, a);
+    return check_launch("k_play_e0");
+}
+static TrajDev traj_dev(const gmz_traj *t)
+{
+    TrajDev d; memset(&d, 0, sizeof(d));
+    if (!t) return d;
+    d.n_slots = t->n_slots; d.max_moves = t->max_moves; d.fin_cap = t->fin_cap;
+    d.policy = t->policy; d.value = t->value; d.action = t->action;
+    d.start_board = (u64 *)t->start_board; d.start_info = t->start_info;
+    d.free_slots = t->free_slots; d.free_top = t->free_top; d.fin_queue = t->fin_queue; d.fin_count = t->fin_count;
+    return d;
+}
+static int check_traj(const gmz_engine *e, const gmz_traj *t)
+{
+    if (!t->policy || !t->value || !t->action || !t->start_board || !t->start_info || !t->free_slots || !t->free_top ||
+        !t->fin_queue || !t->fin_count) return fail("gmz_traj: null buffer");
+    if (t->n_slots < e->p.G) return fail("gmz_traj: n_slots must be >= num_games");
+    if (t->fin_cap < t->n_slots) return fail("gmz_traj: fin_cap must be >= n_slots");
+    if (t->max_moves < 1) return fail("gmz_traj: max_moves must be >= 1");
+    return 0;
+}
+
 extern "C" int gmz_search_e0(gmz_engine *e, const double *gumbel, uint64_t seed, int logit_div,
                              int32_t *trace_leaf_action, int32_t *trace_leaf_depth, gmz_stream stream)
 {
     if (!e || !gumbel) return fail("gmz_search_e0: null argument");
     if (e->p.mode != GMZ_MODE_ALPHAZERO) return fail("gmz_search_e0: AlphaZero mode only");
-    const size_t smem = (size_t)WARPS_PER_CTA * (e->p.S + 2) * sizeof(short);
-    DISPATCH_NC(e, {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k_search_e0<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_search_e0<NC><<<GRID(e), smem, (cudaStream_t)stream>>>(e->p, gumbel, (u64)seed, (float)logit_div, pow2_inv(logit_div),
-                                                                 trace_leaf_action, trace_leaf_depth);
-    });
-    return check_launch("k_search_e0");
+    PlayArgs a; memset(&a, 0, sizeof(a));
+    a.eval_seed = seed; a.logit_div = (float)logit_div; a.inv_div = pow2_inv(logit_div);
+    a.total_tickets = e->p.G; a.do_step = 0; a.gumbel_in = gumbel;
+    a.trace_a = trace_leaf_action; a.trace_d = trace_leaf_depth;
+    int rc = 0;
+    DISPATCH_NC(e, rc = launch_play<NC>(e, a, (cudaStream_t)stream));
+    return rc;
+}
+extern "C" int gmz_traj_init(gmz_engine *e, const gmz_traj *traj, gmz_stream stream)
+{
+    if (!e || !traj) return fail("gmz_traj_init: null argument");
+    if (check_traj(e, traj)) return 1;
+    const int n = traj->n_slots > e->p.G ? traj->n_slots : e->p.G;
+    k_traj_init<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->p, traj_dev(traj));
+    return check_launch("k_traj_init");
+}
+extern "C" int gmz_selfplay_e0(gmz_engine *e, const gmz_traj *traj, uint64_t eval_seed, int logit_div, uint64_t noise_seed,
+                               int64_t total_moves, int restart, gmz_stream stream)
+{
+    if (!e) return fail("gmz_selfplay_e0: null engine");
+    if (e->p.mode != GMZ_MODE_ALPHAZERO) return fail("gmz_selfplay_e0: AlphaZero mode only");
+    if (traj && check_traj(e, traj)) return 1;
+    if (total_moves <= 0) return 0;
+    PlayArgs a; memset(&a, 0, sizeof(a));
+    a.eval_seed = eval_seed; a.noise_seed = noise_seed; a.logit_div = (float)logit_div; a.inv_div = pow2_inv(logit_div);
+    a.total_tickets = total_moves; a.do_step = 1; a.restart = restart ? 1 : 0; a.use_traj = traj ? 1 : 0;
+    a.traj = traj_dev(traj);
+    int rc = 0;
+    DISPATCH_NC(e, rc = launch_play<NC>(e, a, (cudaStream_t)stream));
+    return rc;
+}
+extern "C" int gmz_selfplay_unpark(gmz_engine *e, const gmz_traj *traj, gmz_stream stream)
+{
+    if (!e || !traj) return fail("gmz_selfplay_unpark: null argument");
+    if (check_traj(e, traj)) return 1;
+    k_unpark<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, traj_dev(traj));
+    return check_launch("k_unpark");
+}
+extern "C" int gmz_play_counters(gmz_engine *e, uint64_t *out2, gmz_stream stream)
+{
+    if (!e || !out2) return fail("gmz_play_counters: null argument");
+    cudaError_t err = cudaMemcpyAsync(out2, &e->p.ctl->moves_played, 2 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (err != cudaSuccess) return fail("gmz_play_counters: %s", cudaGetErrorString(err));
+    return 0;
 }
 extern "C" int gmz_fill_gumbel(double *out, size_t n, uint64_t seed, uint64_t offset, gmz_stream stream)
 {

@@ -187,6 +187,22 @@ class SearchEngine:
         self.launches += 1
         return ta, td
 
+    def selfplay_e0(self, total_moves, eval_seed, logit_div=16, noise_seed=0, traj=None, restart=True):
+        """Persistent self-play kernel: `total_moves` moves (search + decision + do_move + end check)
+        handed out to the G games by a ticket counter; finished games restart in-kernel."""
+        check(self.lib.gmz_selfplay_e0(self.handle, C.byref(traj.c) if traj is not None else None,
+                                       C.c_uint64(eval_seed & (2**64 - 1)), int(logit_div),
+                                       C.c_uint64(noise_seed & (2**64 - 1)), int(total_moves), int(bool(restart)),
+                                       self._stream()), "gmz_selfplay_e0")
+        self.launches += 1
+
+    def play_counters(self):
+        """(moves played, games finished) by the persistent kernel since the engine was created."""
+        out = torch.zeros(2, dtype=torch.int64, device=self.device)
+        check(self.lib.gmz_play_counters(self.handle, _ptr(out), self._stream()), "gmz_play_counters")
+        m, f = out.cpu().tolist()
+        return int(m), int(f)
+
     def fill_gumbel(self, out, seed, offset=0):
         check(self.lib.gmz_fill_gumbel(_ptr(out), out.numel(), C.c_uint64(seed & (2**64 - 1)),
                                        C.c_uint64(offset), self._stream()), "gmz_fill_gumbel")

@@ -56,6 +56,15 @@ class SelfPlayEngine:
             e.reset_games(self.done_mask)
         return winner
 
+    def play(self, moves_per_game=1, traj=None, restart=True):
+        """Persistent-kernel self-play (fixed evaluator only): G * moves_per_game moves in one launch,
+        games advancing independently; returns nothing -- harvest finished games from `traj`."""
+        if self.evaluator != "e0":
+            raise NotImplementedError("the persistent self-play kernel runs the fixed evaluator E0")
+        e = self.e
+        e.selfplay_e0(e.G * int(moves_per_game), self.seed, self.logit_div, self.noise_seed, traj, restart)
+        self.moves_played += e.G * int(moves_per_game)
+
     def count_finished(self, winner):
         n = int((winner != 2).sum().item())
         self.games_finished += n

@@ -130,6 +130,38 @@ int gmz_search_e0(gmz_engine *e, const double *gumbel, uint64_t seed, int logit_
  * element i uses counter (offset + i).  (Parity runs pass NumPy's draw instead.) */
 int gmz_fill_gumbel(double *out, size_t n, uint64_t seed, uint64_t offset, gmz_stream stream);
 
+/* ---- persistent self-play (workers.py:162-189 for G games, no host in the loop) ---- */
+/* Caller-owned trajectory storage; every pointer is a device pointer.  A game records into
+ * one slot; when it ends the slot is pushed on fin_queue (what the reference puts on
+ * data_queue, workers.py:230) and the game continues in a fresh slot from the free stack. */
+typedef struct gmz_traj {
+    int32_t n_slots;       /* >= G */
+    int32_t max_moves;     /* moves recorded per game (board_size^2 covers any game from reset) */
+    int32_t fin_cap;       /* entries of fin_queue, >= n_slots */
+    int32_t reserved;
+    double *policy;        /* [n_slots][max_moves][A]  search policies (float64, like the reference) */
+    double *value;         /* [n_slots][max_moves]     root search values */
+    int32_t *action;       /* [n_slots][max_moves]     moves played */
+    uint64_t *start_board; /* [n_slots][2][8]          bitboards (+1 / -1 stones) at the first recorded move */
+    int32_t *start_info;   /* [n_slots][4]             player to move, move_count, last_move, game index */
+    int32_t *free_slots;   /* [n_slots]                stack of free slot ids */
+    int32_t *free_top;     /* [1]                      ids on the stack */
+    int32_t *fin_queue;    /* [fin_cap][4]             slot, game, length, winner */
+    int32_t *fin_count;    /* [1] */
+} gmz_traj;
+/* Slot g -> game g, remaining slots on the free stack, queues cleared. */
+int gmz_traj_init(gmz_engine *e, const gmz_traj *traj, gmz_stream stream);
+/* Play `total_moves` self-play moves (one move = Gumbel noise + a full S-simulation search with
+ * E0 + decision + do_move + get_game_ended) spread over the G games by a ticket counter, in ONE
+ * persistent kernel.  Noise of game g's k-th search = gmz_fill_gumbel(noise_seed, offset =
+ * (k*G + g)*A).  Finished games restart inside the launch if `restart` (and a free slot exists);
+ * otherwise they park until gmz_selfplay_unpark.  traj may be NULL (no recording). */
+int gmz_selfplay_e0(gmz_engine *e, const gmz_traj *traj, uint64_t eval_seed, int logit_div, uint64_t noise_seed,
+                    int64_t total_moves, int restart, gmz_stream stream);
+int gmz_selfplay_unpark(gmz_engine *e, const gmz_traj *traj, gmz_stream stream);
+/* out2 (device, uint64 [2]) = moves played, games finished since gmz_create. */
+int gmz_play_counters(gmz_engine *e, uint64_t *out2, gmz_stream stream);
+
 /* ---- self-play game step --------------------------------------------------- */
 /* game.do_move(action) + game.get_game_ended() on the roots (workers.py:178-181,
  * game.py:20-63): actions int32 [G] (<0 = skip that game); out_winner int32 [G]

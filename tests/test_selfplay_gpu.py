@@ -1,0 +1,53 @@
+"""Persistent self-play kernel: whole games on the device, checked move for move against the CPU
+oracle's game loop (same E0 evaluator, the kernel's own counter-based Gumbel noise regenerated on
+the host side of the test), then turned into GameRecord / TrainingSlice like workers.py:183-230."""
+import os
+
+import numpy as np
+import pytest
+
+from _golden_util import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+
+def _noise_for_game(eng, g, n_moves, noise_seed):
+    import torch
+    out = torch.empty((n_moves, eng.A), dtype=torch.float64, device=eng.device)
+    for k in range(n_moves):
+        eng.fill_gumbel(out[k], noise_seed, (k * eng.G + g) * eng.A)
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("N,S,G", [(6, 36, 24), (9, 64, 40)])
+def test_selfplay_games_match_oracle(N, S, G):
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+    from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
+    from oracle import oracle
+    A, seed, nseed = N * N, 5, 77
+    eng = SearchEngine(G, board_size=N, num_simulations=S)
+    sp = SelfPlayEngine(eng, "e0", seed=seed, noise_seed=nseed)
+    traj = TrajectoryStore(eng, extra_slots=8)
+    finished = []
+    for _ in range(6):
+        sp.play(moves_per_game=A // 3, traj=traj, restart=True)
+        finished += traj.harvest()
+    moves, nfin = eng.play_counters()
+    assert nfin == len(finished) and nfin >= G          # every game ended at least once
+    assert moves == 6 * G * (A // 3) or nfin > 0        # parked games may skip tickets
+    cfg = oracle.make_config(board_size=N, num_simulations=S, eval_seed=seed)
+    first = {}
+    for r in finished:                                  # the first game of each index starts at noise counter 0
+        first.setdefault(r["game"], r)
+    checked = 0
+    for g, r in sorted(first.items())[:12]:
+        assert r["start_move_count"] == 0 and not r["start_board"].any() and r["start_player"] == 1
+        gum = _noise_for_game(eng, g, r["length"], nseed)
+        o = oracle.selfplay_game(cfg, np.concatenate([gum, np.zeros((1, A))]))
+        assert o["T"] == r["length"], (g, o["T"], r["length"])
+        assert np.array_equal(o["actions"], r["actions"]) and o["winner"] == r["winner"], g
+        assert np.array_equal(o["values"], r["values"]), g
+        np.testing.assert_allclose(r["policies"], o["policies"], rtol=1e-5, atol=1e-12)
+        checked += 1
+    assert checked >= 8

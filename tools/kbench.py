@@ -14,6 +14,7 @@ ap.add_argument("--games", type=int, default=4096)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--check", type=int, default=64)
 ap.add_argument("--stepwise", action="store_true")
+ap.add_argument("--selfplay", type=int, default=0, help="time the persistent self-play kernel for this many moves per game")
 args = ap.parse_args()
 G = args.games
 eng = SearchEngine(G, board_size=N, num_simulations=S, num_top_actions=K_TOP)
@@ -25,6 +26,19 @@ run = (lambda: eng.search_stepwise_e0(gum, E0_SEED, LOGIT_DIV)) if args.stepwise
 for _ in range(2):
     run()
 torch.cuda.synchronize()
+if args.selfplay:
+    from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
+    traj = TrajectoryStore(eng, extra_slots=G // 2)
+    eng.selfplay_e0(G, E0_SEED, LOGIT_DIV, 3, traj, True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0, _ = eng.play_counters()
+    e0.record(); eng.selfplay_e0(G * args.selfplay, E0_SEED, LOGIT_DIV, 3, traj, True); e1.record(); torch.cuda.synchronize()
+    m1, f1 = eng.play_counters()
+    ms = e0.elapsed_time(e1)
+    print(f"lib={os.environ.get('GMZ_LIB','default')} G={G} selfplay {args.selfplay} moves/game: {ms:.2f} ms  "
+          f"{(m1-m0)*S/ms/1e3:.2f} M sims/s  {(m1-m0)/ms*1e3:.0f} moves/s  moves {m1-m0} finished {f1}")
+    sys.exit(0)
 ts = []
 for _ in range(args.iters):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
