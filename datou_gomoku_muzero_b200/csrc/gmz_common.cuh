@@ -71,6 +71,7 @@ struct Params {
     double *nR;      // [G*S]      node.reward (MuZero mode only)
     short *path;     // [G][S+2]   node ids root..leaf-parent of the pending simulation
     short *pyset;    // [ceil(G/4)*4][4096] scratch for the CPython-set tie-break (rare path)
+    char *sel_overflow;   // [ceil(G/4)*4][128*NC*20 B] select scratch for nodes with > 64 visited children
     struct PlayCtl *ctl;   // play-kernel ticket counter + statistics
 };
 

@@ -171,11 +171,12 @@ k_select(Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, 
         return;
     }
     wg_valid_bits<NC>(w, lane);
-    __shared__ SelScratch<NC> s_sel[WARPS_PER_CTA];
+    __shared__ SelSmem s_sel[WARPS_PER_CTA];
     short *path = p.path + (size_t)g * (p.S + 2);
     u64 P = w.P, M = w.M; int colour = w.to_move;
     int lp, la;
-    const int depth = descend<NC, MZ>(p, w, path, s_sel[threadIdx.x >> 5], lane, lp, la, P, M, colour);
+    const int depth = descend<NC, MZ>(p, w, path, s_sel[threadIdx.x >> 5], blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane,
+                                      lp, la, P, M, colour);
     if (!MZ && leaf_obs)   // colour is now the player to move at the leaf; last move = la
         obs_write<NC, T>(leaf_obs + (size_t)g * 3 * p.A, p.A, colour > 0 ? P : M, colour > 0 ? M : P, la, lane);
     if (lane == 0) {
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_game_step(Params p, const int32
 static float pow2_inv(int d) { return (d > 0 && (d & (d - 1)) == 0) ? 1.0f / (float)d : 0.0f; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct Layout { size_t gs, logits, child, nN, nW, nR, path, pyset, ctl, total; };
+struct Layout { size_t gs, logits, child, nN, nW, nR, path, pyset, selov, ctl, total; };
 
 static int validate(const gmz_config *c)
 {
@@ -340,6 +341,7 @@ static Layout make_layout(const gmz_config *c)
     L.nR = o; if (c->mode == GMZ_MODE_MUZERO) o = align_up(o + G * S * sizeof(double), 256);
     L.path = o; o = align_up(o + G * (S + 2) * sizeof(short), 256);
     L.pyset = o; o = align_up(o + ((G + 3) / 4 * 4) * 4096 * sizeof(short), 256);
+    L.selov = o; o = align_up(o + ((G + 3) / 4 * 4) * AP * 20, 256);
     L.ctl = o; o = align_up(o + sizeof(PlayCtl), 256);
     L.total = o;
     return L;
@@ -388,7 +390,7 @@ extern "C" int gmz_create(const gmz_config *cfg, void *workspace, size_t workspa
     p.nN = (int *)(base + L.nN); p.nW = (double *)(base + L.nW);
     p.nR = cfg->mode == GMZ_MODE_MUZERO ? (double *)(base + L.nR) : nullptr;
     p.path = (short *)(base + L.path);
-    p.pyset = (short *)(base + L.pyset); p.ctl = (PlayCtl *)(base + L.ctl);
+    p.pyset = (short *)(base + L.pyset); p.sel_overflow = base + L.selov; p.ctl = (PlayCtl *)(base + L.ctl);
     cudaError_t err = cudaMemsetAsync(base + L.gs, 0, (size_t)p.G * sizeof(GState), (cudaStream_t)stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(base + L.ctl, 0, sizeof(PlayCtl), (cudaStream_t)stream);
     if (err != cudaSuccess) { free(e); return fail("cudaMemsetAsync: %s", cudaGetErrorString(err)); }
@@ -496,22 +498,18 @@ extern "C" int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint
 template <int NC>
 static int launch_play(gmz_engine *e, const PlayArgs &a, cudaStream_t st)
 {
-    const size_t smem = (size_t)GMZ_PLAY_WARPS * (e->p.S + 2) * sizeof(short);
     static int occ_cache[4] = {0, 0, 0, 0};
-    if (smem + sizeof(SelScratch<NC>) * GMZ_PLAY_WARPS > 48 * 1024)
-        cudaFuncSetAttribute(k_play_e0<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (!occ_cache[NC]) {
         int occ = 0, dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncSetAttribute(k_play_e0<NC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_play_e0<NC>, 32 * GMZ_PLAY_WARPS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_play_e0<NC>, 32 * GMZ_PLAY_WARPS, 0);
         occ_cache[NC] = (occ > 0 ? occ : 1) * (sms > 0 ? sms : 148);
     }
     int grid = (e->p.G + GMZ_PLAY_WARPS - 1) / GMZ_PLAY_WARPS;
     if (grid > occ_cache[NC]) grid = occ_cache[NC];
     if (cudaMemsetAsync(&e->p.ctl->next_ticket, 0, sizeof(unsigned long long), st) != cudaSuccess) return fail("cudaMemsetAsync(ctl)");
-    k_play_e0<NC><<<grid, 32 * GMZ_PLAY_WARPS, smem, st>>>(e->p, a);
+    k_play_e0<NC><<<grid, 32 * GMZ_PLAY_WARPS, 0, st>>>(e->p, a);
     return check_launch("k_play_e0");
 }
 static TrajDev traj_dev(const gmz_traj *t)

@@ -216,10 +216,33 @@ __device__ __forceinline__ bool traj_pop_slot(const TrajDev &t, int &slot)
     return true;
 }
 
+struct PlayArgs;
+// Root of a search inside the play kernel: evaluate the root with E0, draw (or load) the Gumbel
+// noise, expand + top-k (mcts.py:203-226).  Out of line: it runs once per 400 simulations, and
+// keeping its registers out of the simulation loop's allocation is worth more than the call.
+template <int NC>
+__device__ __noinline__ void play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane);
+
 #ifndef GMZ_PLAY_MIN_CTAS
 #define GMZ_PLAY_MIN_CTAS 5
 #endif
 #define GMZ_PLAY_WARPS 4
+
+template <int NC>
+__device__ __noinline__ void play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane)
+{
+    const int g = w.g;
+    const u64 h = e0_hash_planes(a.eval_seed, w.to_move > 0 ? w.P : w.M, w.to_move > 0 ? w.M : w.P, p.NW, w.last_move);
+    const u64 nctr = ((u64)noise_ctr * (u64)p.G + (u64)g) * (u64)p.A;
+    float lg[4 * NC]; double gum[4 * NC];
+#pragma unroll 1
+    for (int i = 0; i < 4 * NC; ++i) {
+        const int ac = 128 * (i >> 2) + 4 * lane + (i & 3);
+        lg[i] = ac < p.A ? e0_logit(h, ac, a.logit_div, a.inv_div) : 0.0f;
+        gum[i] = ac < p.A ? (a.gumbel_in ? a.gumbel_in[(size_t)g * p.A + ac] : gumbel_at(noise_mixed, nctr + ac)) : 0.0;
+    }
+    root_init<NC>(p, w, lg, gum, e0_value(h), lane);
+}
 
 // One search (mcts.py:197-280) -- and in self-play mode one whole move (workers.py:168-189) --
 // per ticket, one game per warp, E0 inlined.
@@ -227,11 +250,11 @@ template <int NC>
 __global__ void __launch_bounds__(32 * GMZ_PLAY_WARPS, GMZ_PLAY_MIN_CTAS)
 k_play_e0(Params p, PlayArgs a)
 {
-    extern __shared__ short s_path[];
-    __shared__ SelScratch<NC> s_sel[GMZ_PLAY_WARPS];
+    __shared__ SelSmem s_sel[GMZ_PLAY_WARPS];
+    __shared__ short s_nvis[GMZ_PLAY_WARPS][128 * NC];
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-    short *path = s_path + (size_t)wi * (p.S + 2);
-    short *table = p.pyset + ((size_t)blockIdx.x * GMZ_PLAY_WARPS + wi) * 4096;
+    const int warp_slot = blockIdx.x * GMZ_PLAY_WARPS + wi;
+    short *table = p.pyset + (size_t)warp_slot * 4096;
     const u64 noise_mixed = mix64(a.noise_seed ^ E0_GOLD);
     for (;;) {
         unsigned long long t = 0;
@@ -260,6 +283,7 @@ k_play_e0(Params p, PlayArgs a)
         if (!got) { if (a.do_step) break; else continue; }
         __threadfence();                    // acquire: everything the previous owner wrote is visible
         GState *s = p.gs + g;
+        short *path = p.path + (size_t)g * (p.S + 2);   // root..leaf-parent node ids (global, L1-resident)
 
         if (a.do_step && s->winner != GMZ_WINNER_NONE) {   // finished earlier, could not restart then
             game_reset(p, s, lane);
@@ -269,40 +293,26 @@ k_play_e0(Params p, PlayArgs a)
         double value = 0.0; int action = -1;
         if (w.active) {
             wg_valid_bits<NC>(w, lane);
-            {   // root: obs = get_board_state(current_player, last_move)  (mcts.py:203)
-                const u64 h = e0_hash_planes(a.eval_seed, w.to_move > 0 ? w.P : w.M, w.to_move > 0 ? w.M : w.P, p.NW, w.last_move);
-                const u64 nctr = ((u64)s->noise_ctr * (u64)p.G + (u64)g) * (u64)p.A;
-                float lg[4 * NC]; double gum[4 * NC];
-#pragma unroll
-                for (int i = 0; i < 4 * NC; ++i) {
-                    const int ac = 128 * (i >> 2) + 4 * lane + (i & 3);
-                    lg[i] = ac < p.A ? e0_logit(h, ac, a.logit_div, a.inv_div) : 0.0f;
-                    gum[i] = ac < p.A ? (a.gumbel_in ? a.gumbel_in[(size_t)g * p.A + ac] : gumbel_at(noise_mixed, nctr + ac)) : 0.0;
-                }
-                root_init<NC>(p, w, lg, gum, e0_value(h), lane);
-            }
+            play_root<NC>(p, a, w, s->noise_ctr, noise_mixed, lane);
             __syncwarp();
             int ev = 0;
             while (w.sim_count < p.S) {
                 u64 P = w.P, M = w.M; int colour = w.to_move;
                 int lp, la;
-                const int depth = descend<NC, false>(p, w, path, s_sel[wi], lane, lp, la, P, M, colour);
+                const int depth = descend<NC, false>(p, w, path, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
                 const u64 h = e0_hash_planes(a.eval_seed, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la);
                 const int nn = w.num_nodes;
                 {   // evaluate + leaf.expand fused: logits go straight into the new node's row
                     float *lrow = p.logits + (w.nbase + (size_t)nn) * (size_t)p.AP;
                     short *crow = p.child + (w.nbase + (size_t)nn) * (size_t)p.AP;
 #pragma unroll 1
-                    for (int j = 0; j < NC; ++j) {
-                        const int a0 = 128 * j + 4 * lane;
-                        float4 v;
-                        v.x = a0 + 0 < p.A ? e0_logit(h, a0 + 0, a.logit_div, a.inv_div) : 0.0f;
-                        v.y = a0 + 1 < p.A ? e0_logit(h, a0 + 1, a.logit_div, a.inv_div) : 0.0f;
-                        v.z = a0 + 2 < p.A ? e0_logit(h, a0 + 2, a.logit_div, a.inv_div) : 0.0f;
-                        v.w = a0 + 3 < p.A ? e0_logit(h, a0 + 3, a.logit_div, a.inv_div) : 0.0f;
-                        *reinterpret_cast<float4 *>(lrow + a0) = v;
-                        *reinterpret_cast<short4 *>(crow + a0) = make_short4(-1, -1, -1, -1);
+                    for (int i = 0; i < 4 * NC; ++i) {      // rolled on purpose (instruction-fetch bound)
+                        const int ac = 128 * (i >> 2) + 4 * lane + (i & 3);
+                        lrow[ac] = ac < p.A ? e0_logit(h, ac, a.logit_div, a.inv_div) : 0.0f;
                     }
+#pragma unroll
+                    for (int j = 0; j < NC; ++j)
+                        *reinterpret_cast<short4 *>(crow + 128 * j + 4 * lane) = make_short4(-1, -1, -1, -1);
                 }
                 if (lane == 0) {
                     p.child[(w.nbase + (size_t)lp) * (size_t)p.AP + la] = (short)nn;
@@ -342,7 +352,7 @@ k_play_e0(Params p, PlayArgs a)
             if (a.out_policy) pol = a.out_policy + (size_t)g * p.A;
             if (a.out_visits) vis = a.out_visits + (size_t)g * p.A;
         }
-        finalize_root<NC, false>(p, w, lane, pol, vis, reinterpret_cast<short *>(s_sel[wi].n), table, value, action);
+        finalize_root<NC, false>(p, w, lane, pol, vis, s_nvis[wi], table, value, action);
         if (!a.do_step) {
             if (lane == 0) { if (a.out_value) a.out_value[g] = value; if (a.out_action) a.out_action[g] = action; }
         } else if (action >= 0) {

@@ -144,16 +144,34 @@ __device__ __forceinline__ double row_softmax(const Params &p, const WG &w, cons
     return __ddiv_rn(1.0, sum);
 }
 
-// Per-warp shared scratch for the visited children of the node being scored.
-template <int NC>
-struct SelScratch {
-    int key[128 * NC];      // (action << 16) | child node id
-    float lg[128 * NC];     // logit of that action
-    int n[128 * NC];        // child visit count
-    double x[128 * NC];     // child value_sum, then logit + sigma, then exp(...)
-    double dx[128 * NC];    // dense pass: element i of lane l at [32*i + l] (keeps the exp loop rolled:
-                            // small code matters more than registers here, the kernel is I-cache bound)
+// Per-warp scratch for the visited children of the node being scored.  Nodes almost always have
+// <= GMZ_SPARSE_SMEM visited children, so that many entries live in shared memory; the rare
+// bigger node uses this warp's slice of a global overflow area (Params::sel_overflow) instead.
+// Shared memory is kept small on purpose: it is carved out of the same 228 KB as the L1 cache
+// that serves the node-header gathers.
+#ifndef GMZ_SPARSE_SMEM
+#define GMZ_SPARSE_SMEM 64
+#endif
+struct SelSmem {
+    double dx[256];                // dense pass: element i of lane l at [32*i + l] (NC <= 2; NC = 3 keeps registers)
+    int key[GMZ_SPARSE_SMEM];      // (action << 16) | child node id
+    float lg[GMZ_SPARSE_SMEM];     // logit of that action
+    int n[GMZ_SPARSE_SMEM];        // child visit count
+    double x[GMZ_SPARSE_SMEM];     // child value_sum, then logit + sigma, then exp(...)
 };
+// Working pointers for one select call (shared or global, chosen per node).
+struct SelPtr { int *key; float *lg; int *n; double *x; };
+template <int NC>
+__device__ __forceinline__ SelPtr sel_global(const Params &p, int warp_slot)
+{   // layout per warp: x[128*NC] doubles, then key / lg / n [128*NC] each
+    char *base = p.sel_overflow + (size_t)warp_slot * (size_t)(128 * NC * 20);
+    SelPtr s;
+    s.x = reinterpret_cast<double *>(base);
+    s.key = reinterpret_cast<int *>(base + 128 * NC * 8);
+    s.lg = reinterpret_cast<float *>(base + 128 * NC * 12);
+    s.n = reinterpret_cast<int *>(base + 128 * NC * 16);
+    return s;
+}
 
 // _select_action at an interior node (mcts.py:106-117):
 // argmax_a  softmax(logits + sigma)[a] - N(a) / (1 + sum_b N(b))   over the ROOT-valid actions.
@@ -161,7 +179,7 @@ struct SelScratch {
 // branch-free dense pass from the row alone.  The few visited children are compacted into
 // `sc` (one per lane) and scored in a sparse pass that gathers their N / W.
 template <int NC, bool MZ>
-__device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelScratch<NC> &sc,
+__device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
                                                 int &action, int &child)
 {
     constexpr int E = 4 * NC;
@@ -181,12 +199,14 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
     for (int i = 0; i < E; ++i) vm |= (ch[i] >= 0 ? 1u : 0u) << i;
     // compact the visited children: lane prefix over popc(vm)
     int total = 0;
+    SelPtr sc; sc.key = sm.key; sc.lg = sm.lg; sc.n = sm.n; sc.x = sm.x;
     if (__any_sync(GMZ_FULL, vm != 0)) {
         const int cnt = __popc(vm);
         int inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(GMZ_FULL, inc, o); if (lane >= o) inc += t; }
         total = __shfl_sync(GMZ_FULL, inc, 31);
+        if (total > GMZ_SPARSE_SMEM) sc = sel_global<NC>(p, warp_slot);
         int pos = inc - cnt;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
@@ -222,32 +242,63 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         sc.x[k] = x; lmx = dmax2(lmx, x);
     }
     const unsigned dv = w.vb & ~vm;      // valid and unvisited: the dense set
-#pragma unroll
-    for (int i = 0; i < E; ++i) {
-        const double xi = __dadd_rn((double)lg[i], sig0);
-        sc.dx[32 * i + lane] = xi;
-        if ((dv >> i) & 1u) lmx = dmax2(lmx, xi);
-    }
-    const double mx = warp_max_f64(lmx);
-    double ls = 0.0;
-#pragma unroll 2
-    for (int i = 0; i < E; ++i) {
-        double e = exp_nonpos(dmin2(__dsub_rn(sc.dx[32 * i + lane], mx), 0.0));
-        e = ((dv >> i) & 1u) ? e : 0.0;
-        sc.dx[32 * i + lane] = e;
-        ls = __dadd_rn(ls, e);
-    }
-    for (int k = lane; k < total; k += 32) {
-        const double e = exp_nonpos(__dsub_rn(sc.x[k], mx));
-        sc.x[k] = e; ls = __dadd_rn(ls, e);
-    }
-    const double sum = warp_sum_f64(ls);
-    const double inv = __ddiv_rn(1.0, sum);
     double best = -INFINITY; int ba = 0x7fffffff, bc = -1;
-#pragma unroll 4
-    for (int i = 0; i < E; ++i) {
-        const double s = __dmul_rn(sc.dx[32 * i + lane], inv);
-        if (((dv >> i) & 1u) && s > best) { best = s; ba = 128 * (i >> 2) + 4 * lane + (i & 3); }
+    double inv;
+    if (NC <= 2) {
+        // Rolled loops over this lane's E elements, staged in shared memory: the kernel is bound by
+        // instruction fetch (every warp is at a different PC of a ~30 KB loop), so the exp / score
+        // bodies are kept small enough to be re-served by the L0 instruction cache.
+        double *dx = sm.dx + lane;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const double xi = __dadd_rn((double)lg[i], sig0);
+            dx[32 * i] = xi;
+            if ((dv >> i) & 1u) lmx = dmax2(lmx, xi);
+        }
+        const double mx = warp_max_f64(lmx);
+        double ls = 0.0;
+#pragma unroll 1
+        for (int i = 0; i < E; ++i) {
+            double e = exp_nonpos(dmin2(__dsub_rn(dx[32 * i], mx), 0.0));
+            e = ((dv >> i) & 1u) ? e : 0.0;
+            dx[32 * i] = e;
+            ls = __dadd_rn(ls, e);
+        }
+        for (int k = lane; k < total; k += 32) {
+            const double e = exp_nonpos(__dsub_rn(sc.x[k], mx));
+            sc.x[k] = e; ls = __dadd_rn(ls, e);
+        }
+        inv = __ddiv_rn(1.0, warp_sum_f64(ls));
+#pragma unroll 1
+        for (int i = 0; i < E; ++i) {
+            const double s = __dmul_rn(dx[32 * i], inv);
+            if (((dv >> i) & 1u) && s > best) { best = s; ba = 128 * (i >> 2) + 4 * lane + (i & 3); }
+        }
+    } else {
+        double x[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            x[i] = __dadd_rn((double)lg[i], sig0);
+            if ((dv >> i) & 1u) lmx = dmax2(lmx, x[i]);
+        }
+        const double mx = warp_max_f64(lmx);
+        double ls = 0.0;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const double e = exp_nonpos(dmin2(__dsub_rn(x[i], mx), 0.0));
+            x[i] = ((dv >> i) & 1u) ? e : 0.0;
+            ls = __dadd_rn(ls, x[i]);
+        }
+        for (int k = lane; k < total; k += 32) {
+            const double e = exp_nonpos(__dsub_rn(sc.x[k], mx));
+            sc.x[k] = e; ls = __dadd_rn(ls, e);
+        }
+        inv = __ddiv_rn(1.0, warp_sum_f64(ls));
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const double s = __dmul_rn(x[i], inv);
+            if (((dv >> i) & 1u) && s > best) { best = s; ba = 128 * (i >> 2) + 4 * lane + (i & 3); }
+        }
     }
     if (total > 0) {
         const double dn = (double)(1 + sumN);
@@ -270,7 +321,7 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
 // then interior selection until an unexpanded child is reached.  In AlphaZero mode the path
 // is replayed on the bitboards while descending (mcts.py:236-248).  Returns depth (edges).
 template <int NC, bool MZ>
-__device__ __forceinline__ int descend(const Params &p, const WG &w, short *path, SelScratch<NC> &sc, int lane,
+__device__ __forceinline__ int descend(const Params &p, const WG &w, short *path, SelSmem &sc, int warp_slot, int lane,
                                        int &leaf_parent, int &leaf_action, u64 &P, u64 &M, int &colour)
 {
     const unsigned key = lane < w.n_surv ? (((unsigned)w.s_n << 5) | (unsigned)lane) : 0xffffffffu;
@@ -283,7 +334,7 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, short *path
     while (node >= 0) {
         if (lane == 0) path[depth] = (short)node;
         int c;
-        select_interior<NC, MZ>(p, w, node, lane, sc, a, c);
+        select_interior<NC, MZ>(p, w, node, lane, sc, warp_slot, a, c);
         if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
         parent = node; node = c; ++depth;
     }
