@@ -135,6 +135,46 @@ def cpu_baseline_leg(budget_s=10.0):
             "sample": f"{n} batches x {games} searches of 15x15/400 sims (E0) on {threads} threads, {dt:.1f} s"}
 
 
+def net_leg(eng, dev, peaks):
+    """Same workload with the REAL network as evaluator (E1): GomokuNetEZ 8 blocks x 128 filters,
+    random init (torch.manual_seed(0)), bf16, BatchNorm folded, cuDNN fused conv ops, CUDA graph;
+    one full 400-simulation search for all G games through the stepwise kernels."""
+    import torch
+    from datou_gomoku_muzero_b200.config import Config
+    from datou_gomoku_muzero_b200.network import DeviceEvaluator, GomokuNetEZ
+    torch.manual_seed(0)
+    cfg = Config(BOARD_SIZE=N, ACTION_SPACE_SIZE=A, NUM_RES_BLOCKS=8, NUM_FILTERS=128, HEAD_HIDDEN_DIM=64)
+    ev = DeviceEvaluator(GomokuNetEZ(cfg), eng.leaf_obs, dtype=torch.bfloat16, graph=True)
+    G = eng.G
+    gum = torch.empty((G, A), dtype=torch.float64, device=dev)
+    eng.fill_gumbel(gum, 4242, 0)
+    eng.set_roots(*staggered_positions(G, 0))
+
+    def search(n_sims):
+        lg, v = ev(eng.root_obs()); eng.root_expand(lg, v, gum)
+        for _ in range(n_sims - 1):
+            lg, v = ev(eng.select()); eng.expand_backup(lg, v)
+    search(8)                                   # warm-up (partial search)
+    eng.set_roots(*staggered_positions(G, 0))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); search(S); eng.finalize(want_visits=False); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record()
+    for _ in range(10):
+        ev(eng.leaf_obs)
+    n1.record(); torch.cuda.synchronize()
+    net_ms = n0.elapsed_time(n1) / 10
+    tf = 1.064e9 * G / (net_ms * 1e-3) / 1e12
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    return {"evaluator": "GomokuNetEZ 8x128 bf16 (random init, BN folded, cuDNN fused conv+bias+relu, CUDA graph)",
+            "sims_per_sec": G * S / (ms * 1e-3), "moves_per_sec": G / (ms * 1e-3), "ms_per_search": ms,
+            "net_forward_ms": net_ms, "tree_and_glue_ms_per_sim_step": ms / S - net_ms,
+            "tensor": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                       "flop_per_eval": 1.064e9, "note": "algorithmic conv FLOPs (SURVEY 8d) / measured cuBLAS bf16 burst peak"}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -263,6 +303,11 @@ def run_ours(args):
                      "note": "one simulation in flight per game (bit-exact visit counts) => latency/occupancy bound, not HBM bound"},
         "clocks": sampler.summary(),
     }
+    if not args.no_net:
+        try:
+            out["net"] = net_leg(eng, dev, peaks)
+        except Exception as ex:      # the headline (fixed evaluator) stands on its own
+            out["net"] = {"error": repr(ex)[:200]}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg(args.cpu_seconds)
     print(json.dumps(out))
@@ -280,6 +325,7 @@ def main():
     ap.add_argument("--cpu-games", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-net", action="store_true", help="skip the real-network (E1) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -4,7 +4,7 @@ Runs only in the build container (the reference does not travel to the GPU box);
 files it writes next to itself are committed and are what tests/ read.  Usage:
 
     python tests/golden/make_golden.py all          # every group (a few minutes)
-    python tests/golden/make_golden.py search_az | search_mz | selfplay | game | per | tactics
+    python tests/golden/make_golden.py search_az | search_mz | selfplay | game | per | tactics | network
 
 Nothing here is copied from the reference: the reference is imported and driven through its
 public interface with (a) the E0 evaluator behind its queue protocol and (b) np.random.seed
@@ -334,6 +334,30 @@ def gen_tactics():
     print(f"[tactics] {len(rows)} boards", flush=True)
 
 
+def gen_network():
+    """GomokuNetEZ forward KAT (network.py:109-152): a small seeded network's state_dict + outputs."""
+    import torch
+    config, _, _ = _import_reference(6)
+    config.NUM_RES_BLOCKS, config.NUM_FILTERS, config.HEAD_HIDDEN_DIM = 2, 16, 8
+    import network
+    torch.manual_seed(0)
+    net = network.GomokuNetEZ(config)
+    with torch.no_grad():      # make BatchNorm statistics and the zero-initialised bn2 gains non-trivial
+        for m in net.modules():
+            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5); m.weight.normal_(1, 0.2); m.bias.normal_(0, 0.2)
+    net.eval()
+    obs = (torch.rand(5, 3, 6, 6) < 0.3).float()
+    act = torch.tensor([[0], [7], [35], [12], [3]])
+    p, v, h = net.initial_inference(obs)
+    p2, v2, h2, r2 = net.recurrent_inference(h, act)
+    out = {"sd_" + k: t.numpy() for k, t in net.state_dict().items()}
+    out.update(obs=obs.numpy(), act=act.numpy(), p=p.numpy(), v=v.numpy(), h=h.numpy(), p2=p2.numpy(), v2=v2.numpy(),
+               h2=h2.numpy(), r2=r2.numpy(), cfg=np.array([6, 2, 16, 8], np.int64))
+    np.savez_compressed(os.path.join(HERE, "network_kat.npz"), **out)
+    print(f"[network] {len(net.state_dict())} tensors, {sum(t.numel() for t in net.parameters())} params", flush=True)
+
+
 def _sub(*args):
     subprocess.check_call([sys.executable, os.path.abspath(__file__), *map(str, args)])
 
@@ -344,7 +368,7 @@ if __name__ == "__main__":
         for N in (6, 9, 15):
             _sub("search_az", N); _sub("search_mz", N)
         _sub("selfplay", 6, 36, 11, "az"); _sub("selfplay", 9, 100, 12, "az"); _sub("selfplay", 6, 50, 13, "mz")
-        _sub("game"); _sub("per"); _sub("tactics")
+        _sub("game"); _sub("per"); _sub("tactics"); _sub("network")
     elif cmd in ("search_az", "search_mz"):
         gen_search(cmd[-2:], int(sys.argv[2]))
     elif cmd == "selfplay":
@@ -355,5 +379,7 @@ if __name__ == "__main__":
         gen_per()
     elif cmd == "tactics":
         gen_tactics()
+    elif cmd == "network":
+        gen_network()
     else:
         raise SystemExit(f"unknown group {cmd}")
