@@ -238,18 +238,26 @@ def run_ours(args):
     moves_total = float(md.item())
     harvested = len(traj.harvest(copy_policies=False))
 
-    # ---- e2e: the public batch API with HOST buffers (H2D of roots + noise, D2H of results) per step
-    from datou_gomoku_muzero_b200.mcts import AlphaZeroMCTS
-    mcts = AlphaZeroMCTS.for_engine(eng, evaluator="e0", eval_seed=E0_SEED, logit_div=LOGIT_DIV)
+    # ---- e2e: the public batch API with HOST buffers (pinned staging, H2D of roots + noise, search,
+    # decision, D2H of policy/value/action every step), double-buffered over two engines so the heavy
+    # tail of one batch overlaps the next batch (PipelinedBatchSearch)
+    from datou_gomoku_muzero_b200.mcts import PipelinedBatchSearch
+    eng2 = SearchEngine(G, board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP, device=dev)
+    pipe = PipelinedBatchSearch([eng, eng2], evaluator="e0", eval_seed=E0_SEED, logit_div=LOGIT_DIV)
     hb, hp, hl, hm = staggered_positions(G, rank)
-    hgum = np.random.RandomState(5 + rank).gumbel(0, 1, (G, A))
-    for _ in range(2):
-        mcts.search_batch(hb, hp, hl, hm, hgum)
+    hgums = [np.random.RandomState(5 + rank + 17 * i).gumbel(0, 1, (G, A)) for i in range(3)]
+    for i in range(2):
+        pipe.result(pipe.submit(hb, hp, hl, hm, hgums[i]))
     barrier()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(4, min(args.steps, 10))
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        pol, val, act = mcts.search_batch(hb, hp, hl, hm, hgum)
+    prev = None
+    for i in range(e2e_steps):
+        tk = pipe.submit(hb, hp, hl, hm, hgums[i % 3])
+        if prev is not None:
+            pol, val, act = pipe.result(prev)
+        prev = tk
+    pol, val, act = pipe.result(prev)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -293,7 +301,7 @@ def run_ours(args):
         "e2e": {"value": sims_per_step * e2e_steps / e2e_s, "unit": "sims/s",
                 "h2d_bytes_per_step": int(hb.nbytes + hp.nbytes + hl.nbytes + hm.nbytes + hgum.nbytes),
                 "d2h_bytes_per_step": int(pol.nbytes + val.nbytes + act.nbytes), "steps": e2e_steps,
-                "api": "AlphaZeroMCTS.search_batch(host boards, players, last_moves, move_counts, gumbel)"},
+                "api": "PipelinedBatchSearch.submit/result(host boards, players, last_moves, move_counts, gumbel), depth 2"},
         "gpu_launches": launches,
         "games_finished_in_timed_region": int(finished), "games_harvested": harvested,
         "roofline": {"bound": "hbm", "kernel": "k_play_e0<2>", "achieved": achieved, "peak": peak, "unit": "GB/s",

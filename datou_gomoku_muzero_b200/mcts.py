@@ -116,6 +116,15 @@ class _GumbelEngineMCTS(MCTS):
         [G], move_counts [G], gumbel float64 [G,A] (drawn with np.random.gumbel if omitted, like the reference).
         Returns host arrays (policy float64 [G,A], value float64 [G], action int32 [G])."""
         import torch
+        self.enqueue_batch(boards, players, last_moves, move_counts, gumbel)
+        torch.cuda.current_stream(self._batch["engine"].device).synchronize()
+        b = self._batch
+        return b["o_policy"].numpy(), b["o_value"].numpy(), b["o_action"].numpy()
+
+    def enqueue_batch(self, boards, players, last_moves, move_counts, gumbel=None):
+        """Asynchronous half of search_batch: stages the inputs in pinned memory and enqueues H2D copies,
+        the search, the decision and the D2H copies on the current stream.  The pinned output arrays
+        (`_batch["o_*"]`) are valid once that stream has been synchronised."""
         b = self._batch
         if b is None:
             raise RuntimeError("search_batch needs an instance made with for_engine()")
@@ -146,7 +155,42 @@ class _GumbelEngineMCTS(MCTS):
         b["o_policy"].copy_(pol, non_blocking=True)
         b["o_value"].copy_(val, non_blocking=True)
         b["o_action"].copy_(act, non_blocking=True)
-        torch.cuda.current_stream(eng.device).synchronize()
+
+
+class PipelinedBatchSearch:
+    """Double-buffered `search_batch`: consecutive host batches alternate between engines (own node
+    pools, own CUDA stream), so batch i+1's copies and the bulk of its search overlap the tail of
+    batch i (per-search work is heavy tailed; a lone batch ends with a few slow games on an idle GPU).
+
+        pipe = PipelinedBatchSearch([eng_a, eng_b], evaluator="e0", eval_seed=...)
+        t0 = pipe.submit(boards0, ...); t1 = pipe.submit(boards1, ...)
+        policy, value, action = pipe.result(t0)        # host arrays, valid until that lane is reused
+    """
+
+    def __init__(self, engines, cls=None, evaluator="e0", eval_seed=0, logit_div=16):
+        import torch
+        cls = cls or AlphaZeroMCTS
+        self.lanes = [cls.for_engine(e, evaluator, eval_seed, logit_div) for e in engines]
+        self.streams = [torch.cuda.Stream(device=e.device) for e in engines]
+        self.events = [None] * len(engines)
+        self.n = 0
+
+    def submit(self, boards, players, last_moves, move_counts, gumbel=None):
+        import torch
+        i = self.n % len(self.lanes)
+        if self.events[i] is not None:
+            self.events[i].synchronize()           # the lane's pinned buffers are about to be overwritten
+        with torch.cuda.stream(self.streams[i]):
+            self.lanes[i].enqueue_batch(boards, players, last_moves, move_counts, gumbel)
+            ev = torch.cuda.Event()
+            ev.record(self.streams[i])
+        self.events[i] = ev
+        self.n += 1
+        return i
+
+    def result(self, ticket):
+        self.events[ticket].synchronize()
+        b = self.lanes[ticket]._batch
         return b["o_policy"].numpy(), b["o_value"].numpy(), b["o_action"].numpy()
 
 

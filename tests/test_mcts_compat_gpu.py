@@ -127,3 +127,35 @@ def test_search_batch_host_api():
     opol, oval, oact, _ = oracle.search_batch(cfgo, boards, players, last, mc, gum)
     assert np.array_equal(act, oact) and np.array_equal(val, oval)
     np.testing.assert_allclose(pol, opol, rtol=1e-5, atol=1e-12)
+
+
+def test_pipelined_batch_search_matches_oracle():
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.mcts import PipelinedBatchSearch
+    from oracle import oracle
+    N, S, G, seed = 9, 48, 24, 21
+    A = N * N
+    rs = np.random.RandomState(9)
+    engines = [SearchEngine(G, board_size=N, num_simulations=S) for _ in range(2)]
+    pipe = PipelinedBatchSearch(engines, evaluator="e0", eval_seed=seed)
+    cfgo = oracle.make_config(board_size=N, num_simulations=S, eval_seed=seed)
+    batches, tickets = [], []
+    for b in range(5):
+        boards = np.zeros((G, A), np.int8); players = np.ones(G, np.int8)
+        last = np.full(G, -1, np.int32); mc = np.zeros(G, np.int32)
+        for g in range(G):
+            p = 1
+            for a in rs.permutation(A)[: (g + b) % 30]:
+                boards[g, a] = p; last[g] = a; p = -p; mc[g] += 1
+            players[g] = p
+        gum = rs.gumbel(0, 1, (G, A))
+        batches.append((boards, players, last, mc, gum))
+        tickets.append(pipe.submit(*batches[-1]))
+        if b >= 1:      # depth-2 pipeline: collect the previous batch while this one runs
+            pol, val, act = (x.copy() for x in pipe.result(tickets[b - 1]))
+            opol, oval, oact, _ = oracle.search_batch(cfgo, *batches[b - 1])
+            assert np.array_equal(act, oact) and np.array_equal(val, oval), b
+            np.testing.assert_allclose(pol, opol, rtol=1e-5, atol=1e-12)
+    pol, val, act = pipe.result(tickets[-1])
+    opol, oval, oact, _ = oracle.search_batch(cfgo, *batches[-1])
+    assert np.array_equal(act, oact) and np.array_equal(val, oval)

@@ -196,3 +196,62 @@ def test_game_step_matches_reference_kat():
         b2, p2, l2, m2 = (t.cpu().numpy() for t in eng.get_roots())
         assert np.array_equal(b2.reshape(G, A), z["boards"][sel][:, :A])
         assert np.array_equal(p2, -colour) and np.array_equal(l2, last) and np.array_equal(m2, z["move_count"][sel])
+
+
+@pytest.mark.parametrize("N,S,G", [(9, 100, 48), (15, 400, 32), (6, 50, 40)])
+def test_muzero_device_search_matches_oracle(N, S, G):
+    """MuZero mode entirely on the device (hidden-state pool + E0 as torch integer ops) vs the oracle."""
+    import torch
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.muzero import MuZeroDeviceSearch, TorchE0, evals_per_search
+    from oracle import oracle
+    A, seed = N * N, 31
+    rs = np.random.RandomState(N + S)
+    boards = np.zeros((G, A), np.int8); players = np.ones(G, np.int8)
+    last = np.full(G, -1, np.int32); mc = np.zeros(G, np.int32)
+    for g in range(G):
+        k = int(rs.randint(0, A - 1)) if g % 5 else A - 1 - (g % 3)      # some games with < 16 valid moves
+        p = 1
+        for a in rs.permutation(A)[:k]:
+            boards[g, a] = p; last[g] = a; p = -p
+        players[g] = p; mc[g] = k
+    gumbel = rs.gumbel(0, 1, (G, A))
+    eng = SearchEngine(G, board_size=N, num_simulations=S, mode="MuZero")
+    eng.set_roots(boards, players, last, mc)
+    e0 = TorchE0(N, seed=seed)
+    mz = MuZeroDeviceSearch(eng, e0.initial, e0.recurrent)
+    mz.search(torch.from_numpy(gumbel).cuda())
+    pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
+    cfg = oracle.make_config(board_size=N, num_simulations=S, mode=1, eval_seed=seed)
+    opol, oval, oact, ovis = oracle.search_batch(cfg, boards, players, last, mc, gumbel)
+    assert np.array_equal(vis, ovis) and np.array_equal(act, oact)
+    assert np.array_equal(val, oval)
+    np.testing.assert_allclose(pol, opol, rtol=RTOL, atol=1e-12)
+    assert evals_per_search(S, 16, 16) == {100: 33, 400: 100, 50: 22}[S]      # SURVEY App. A.6 batch schedule
+
+
+def test_folded_recurrent_inference_matches_module():
+    import torch
+    from datou_gomoku_muzero_b200.config import Config
+    from datou_gomoku_muzero_b200.muzero import FoldedRecurrentInference
+    from datou_gomoku_muzero_b200.network import FoldedInitialInference, GomokuNetEZ
+    torch.manual_seed(1)
+    cfg = Config(BOARD_SIZE=9, ACTION_SPACE_SIZE=81, NUM_RES_BLOCKS=2, NUM_FILTERS=32, HEAD_HIDDEN_DIM=16)
+    net = GomokuNetEZ(cfg).cuda().eval()
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5); m.weight.normal_(1, 0.2); m.bias.normal_(0, 0.2)
+    obs = (torch.rand(16, 3, 9, 9, device="cuda") < 0.3).float()
+    act = torch.randint(0, 81, (16,), device="cuda")
+    p, v, h = net.initial_inference(obs)
+    p2, v2, h2, r2 = net.recurrent_inference(h, act.reshape(-1, 1))
+    fi, fr = FoldedInitialInference(net, torch.float32), FoldedRecurrentInference(net, torch.float32)
+    fp, fv, fh = fi(obs.contiguous(memory_format=torch.channels_last))
+    torch.testing.assert_close(fp, p, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(fv, v, rtol=1e-3, atol=1e-3)
+    lp, lv, lr, lh = fr(fh, act)
+    torch.testing.assert_close(lp, p2, rtol=1e-3, atol=2e-3)
+    torch.testing.assert_close(lv, v2.reshape(-1), rtol=1e-3, atol=2e-3)
+    torch.testing.assert_close(lr, r2.reshape(-1), rtol=1e-3, atol=2e-3)
+    torch.testing.assert_close(lh, h2, rtol=1e-3, atol=2e-3)
