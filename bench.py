@@ -299,7 +299,7 @@ def run_ours(args):
                    "l2": "node pools (2.6 GB per GPU) exceed the 126 MB L2; no explicit flush",
                    "mean_leaf_depth": mean_depth},
         "e2e": {"value": sims_per_step * e2e_steps / e2e_s, "unit": "sims/s",
-                "h2d_bytes_per_step": int(hb.nbytes + hp.nbytes + hl.nbytes + hm.nbytes + hgum.nbytes),
+                "h2d_bytes_per_step": int(hb.nbytes + hp.nbytes + hl.nbytes + hm.nbytes + hgums[0].nbytes),
                 "d2h_bytes_per_step": int(pol.nbytes + val.nbytes + act.nbytes), "steps": e2e_steps,
                 "api": "PipelinedBatchSearch.submit/result(host boards, players, last_moves, move_counts, gumbel), depth 2"},
         "gpu_launches": launches,

@@ -76,7 +76,7 @@ class MuZeroDeviceSearch:
         base = torch.arange(e.G, device=e.device) * self.nodes
         pool.index_copy_(0, base, h)
         e.root_expand(lg, v, gumbel)
-        steps, limit = 0, int(max_steps) if max_steps else e.S
+        steps, limit = 0, int(max_steps) if max_steps else e.S - 1      # at most S-1 evaluations (sim_count starts at 1)
         while steps < limit:
             parent, action, child, depth = e.select_mz()
             if steps % 8 == 7 and int(parent.max().item()) < 0:       # every game is done
