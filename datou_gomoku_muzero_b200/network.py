@@ -230,6 +230,22 @@ class DeviceEvaluator:
         self.logits.copy_(p)
         self.values.copy_(v.reshape(-1))
 
+    def update_weights(self, state_dict):
+        """Hot-swap the evaluator's weights (the reference's ModelWeightsUpdate message,
+        workers.py:331-335, ipc_messages.py:75-77): load the full state_dict and refold IN PLACE,
+        so a captured CUDA graph keeps replaying against the same buffers."""
+        self.net.load_state_dict({k: v.to(self.dtype) if v.is_floating_point() else v for k, v in state_dict.items()})
+        if self.folded is not None:
+            fresh = FoldedInitialInference(self.net.float(), self.dtype)
+            self.net.to(self.dtype)
+            old, new = self.folded, fresh
+            with torch.no_grad():
+                for a, b in zip([old.stem, *sum(([x, y] for x, y in old.blocks), []), old.pol, old.val,
+                                 old.policy_fc, old.value_fc1, old.value_fc2],
+                                [new.stem, *sum(([x, y] for x, y in new.blocks), []), new.pol, new.val,
+                                 new.policy_fc, new.value_fc1, new.value_fc2]):
+                    a[0].copy_(b[0]); a[1].copy_(b[1])
+
     def __call__(self, obs):
         if obs.data_ptr() != self.obs.data_ptr():
             self.obs.copy_(obs)

@@ -51,3 +51,48 @@ def test_selfplay_games_match_oracle(N, S, G):
         np.testing.assert_allclose(r["policies"], o["policies"], rtol=1e-5, atol=1e-12)
         checked += 1
     assert checked >= 8
+
+
+def test_reanalysis_matches_oracle_per_position():
+    """Surge re-analysis (workers.py:243-305): every stored position of finished games searched again in
+    one batch; policies / values must equal a per-position oracle search with the same noise."""
+    from datou_gomoku_muzero_b200.config import config
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.mcts import AlphaZeroMCTS
+    from datou_gomoku_muzero_b200.reanalysis import positions_of, reanalyse
+    from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+    from datou_gomoku_muzero_b200.trajectory import TrajectoryStore, build_game_record
+    from oracle import oracle
+    N, S, G, seed = 6, 24, 16, 3
+    A = N * N
+    eng = SearchEngine(G, board_size=N, num_simulations=S)
+    sp = SelfPlayEngine(eng, "e0", seed=seed, noise_seed=9)
+    traj = TrajectoryStore(eng, extra_slots=16)
+    recs = []
+    while len(recs) < 3:
+        sp.play(moves_per_game=6, traj=traj)
+        recs += traj.harvest()
+    games = [build_game_record(r) for r in recs[:3]]
+    eng2 = SearchEngine(32, board_size=N, num_simulations=S)
+    new_seed = seed + 1                                       # "the latest model"
+    bs = AlphaZeroMCTS.for_engine(eng2, "e0", eval_seed=new_seed)
+    rs = np.random.RandomState(4)
+    noise = []
+    def gumbel_fn(n, a):
+        noise.append(rs.gumbel(0, 1, (n, a))); return noise[-1]
+    saved = config.BOARD_SIZE
+    config.BOARD_SIZE = N
+    try:
+        out = reanalyse(games, bs, board_size=N, gumbel_fn=gumbel_fn)
+    finally:
+        config.BOARD_SIZE = saved
+    allnoise = np.concatenate(noise)
+    cfg = oracle.make_config(board_size=N, num_simulations=S, eval_seed=new_seed)
+    off = 0
+    for gr, (pol, targets) in zip(games, out):
+        b, pl, lm, mc = positions_of(gr, N)
+        T = len(gr.actions)
+        opol, oval, oact, _ = oracle.search_batch(cfg, b, pl, lm, mc, allnoise[off:off + T])
+        np.testing.assert_allclose(pol, opol, rtol=1e-5, atol=1e-12)
+        assert len(targets) == T and all(isinstance(t, float) for t in targets)
+        off += T
