@@ -104,26 +104,24 @@ __device__ __forceinline__ double dmin2(double a, double b) { return b < a ? b :
 // reduction + degree-11 polynomial, 2^k applied to the exponent field.  A pure function of x,
 // so equal inputs give equal outputs (exact ties stay exact).  Far tail -> libdevice exp.
 static __device__ __noinline__ double exp_far_tail(double x) { return exp(x); }
+// Coefficients live in the constant bank so each Horner step is ONE DFMA with a c[][] operand
+// (as 64-bit immediates ptxas rebuilds them with two moves per step, tripling the exp's cost).
+static __constant__ double c_exp[16] = {
+    1.4426950408889634, 6755399441055744.0, -6.93147180559945286e-01, -2.31904681384629956e-17,
+    2.5052097064908941e-08, 2.7626262793835868e-07, 2.7557414788000726e-06, 2.4801504602132958e-05,
+    1.9841269707468915e-04, 1.3888888932258898e-03, 8.3333333333978320e-03, 4.1666666666573905e-02,
+    1.6666666666666563e-01, 5.0000000000000056e-01, 1.0, 1.0};
 __device__ __forceinline__ double exp_nonpos(double x)
 {
     if (x < -700.0) return exp_far_tail(x);
-    double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    double t = fma(x, c_exp[0], c_exp[1]);
     const int k = __double2loint(t);
-    t -= 6755399441055744.0;
-    double r = fma(t, -6.93147180559945286e-01, x);
-    r = fma(t, -2.31904681384629956e-17, r);
-    double q = 2.5052097064908941e-08;
-    q = fma(q, r, 2.7626262793835868e-07);
-    q = fma(q, r, 2.7557414788000726e-06);
-    q = fma(q, r, 2.4801504602132958e-05);
-    q = fma(q, r, 1.9841269707468915e-04);
-    q = fma(q, r, 1.3888888932258898e-03);
-    q = fma(q, r, 8.3333333333978320e-03);
-    q = fma(q, r, 4.1666666666573905e-02);
-    q = fma(q, r, 1.6666666666666563e-01);
-    q = fma(q, r, 5.0000000000000056e-01);
-    q = fma(q, r, 1.0);
-    q = fma(q, r, 1.0);
+    t -= c_exp[1];
+    double r = fma(t, c_exp[2], x);
+    r = fma(t, c_exp[3], r);
+    double q = c_exp[4];
+#pragma unroll
+    for (int i = 5; i < 16; ++i) q = fma(q, r, c_exp[i]);
     return __hiloint2double(__double2hiint(q) + (int)((unsigned)k << 20), __double2loint(q));
 }
 // xor-butterfly sum: a+b == b+a exactly, so every lane ends with the same bits

@@ -305,8 +305,8 @@ k_play_e0(Params p, PlayArgs a)
                 {   // evaluate + leaf.expand fused: logits go straight into the new node's row
                     float *lrow = p.logits + (w.nbase + (size_t)nn) * (size_t)p.AP;
                     short *crow = p.child + (w.nbase + (size_t)nn) * (size_t)p.AP;
-#pragma unroll 1
-                    for (int i = 0; i < 4 * NC; ++i) {      // rolled on purpose (instruction-fetch bound)
+#pragma unroll kExpUnroll
+                    for (int i = 0; i < 4 * NC; ++i) {      // lightly unrolled: two independent hash chains in flight
                         const int ac = 128 * (i >> 2) + 4 * lane + (i & 3);
                         lrow[ac] = ac < p.A ? e0_logit(h, ac, a.logit_div, a.inv_div) : 0.0f;
                     }

@@ -149,6 +149,10 @@ __device__ __forceinline__ double row_softmax(const Params &p, const WG &w, cons
 // bigger node uses this warp's slice of a global overflow area (Params::sel_overflow) instead.
 // Shared memory is kept small on purpose: it is carved out of the same 228 KB as the L1 cache
 // that serves the node-header gathers.
+#ifndef GMZ_EXP_UNROLL
+#define GMZ_EXP_UNROLL 2
+#endif
+constexpr int kExpUnroll = GMZ_EXP_UNROLL;
 #ifndef GMZ_SPARSE_SMEM
 #define GMZ_SPARSE_SMEM 64
 #endif
@@ -257,7 +261,7 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         }
         const double mx = warp_max_f64(lmx);
         double ls = 0.0;
-#pragma unroll 1
+#pragma unroll kExpUnroll
         for (int i = 0; i < E; ++i) {
             double e = exp_nonpos(dmin2(__dsub_rn(dx[32 * i], mx), 0.0));
             e = ((dv >> i) & 1u) ? e : 0.0;
@@ -269,11 +273,13 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
             sc.x[k] = e; ls = __dadd_rn(ls, e);
         }
         inv = __ddiv_rn(1.0, warp_sum_f64(ls));
-#pragma unroll 1
+        int bi = -1;
+#pragma unroll 2
         for (int i = 0; i < E; ++i) {
             const double s = __dmul_rn(dx[32 * i], inv);
-            if (((dv >> i) & 1u) && s > best) { best = s; ba = 128 * (i >> 2) + 4 * lane + (i & 3); }
+            if (((dv >> i) & 1u) && s > best) { best = s; bi = i; }
         }
+        if (bi >= 0) ba = 128 * (bi >> 2) + 4 * lane + (bi & 3);
     } else {
         double x[E];
 #pragma unroll
