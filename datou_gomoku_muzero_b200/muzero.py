@@ -94,7 +94,7 @@ class MuZeroDeviceSearch:
 
 class TorchE0:
     """The fixed evaluator E0 in MuZero mode, as torch integer ops on the device (hidden state = the
-    64-bit hash, one int64 per node).  Same integers as tests/golden/e0_py.py and the C oracle."""
+    64-bit hash, one int64 per node).  Same integers as the CUDA E0 (csrc/gmz_common.cuh) and tests/golden/e0_py.py."""
 
     GOLD, CV, CA, CR = 0x9E3779B97F4A7C15, 0xD1B54A32D192ED03, 0x8CB92BA72F3D8DD7, 0xA24BAED4963EE407
 

@@ -40,9 +40,10 @@ class TrajectoryStore:
         check(e.lib.gmz_traj_init(e.handle, C.byref(self.c), e._stream()), "gmz_traj_init")
         e.launches += 1
 
-    def harvest(self, copy_policies=True):
-        """Finished games since the last harvest -> list of dicts (host arrays); recycles their slots
-        and restarts parked games."""
+    def harvest(self, copy_policies=True, recycle=True):
+        """Finished games since the last harvest -> list of dicts (host arrays).  With `recycle` their
+        slots go back on the free stack and parked games restart; a DeviceSliceStore keeps the slots
+        (the games stay resident for sampling) and recycles them itself when it evicts."""
         e = self.e
         n = int(self.fin_count.item())
         if n == 0:
@@ -60,18 +61,90 @@ class TrajectoryStore:
             T = int(q[i, 2])
             bits = np.unpackbits(sb[i].view(np.uint8).reshape(2, 64), axis=1, bitorder="little")[:, :e.A]
             board = bits[0].astype(np.int8) - bits[1].astype(np.int8)
-            out.append(dict(game=int(q[i, 1]), length=T, winner=int(q[i, 3]), actions=act[i, :T].copy(),
+            out.append(dict(slot=int(q[i, 0]), game=int(q[i, 1]), length=T, winner=int(q[i, 3]), actions=act[i, :T].copy(),
                             values=val[i, :T].copy(), policies=None if pol is None else pol[i, :T].copy(),
                             start_board=board.reshape(e.N, e.N), start_player=int(si[i, 0]),
                             start_move_count=int(si[i, 1]), start_last_move=int(si[i, 2])))
-        # recycle: push the harvested slots back on the free stack, clear the queue, restart parked games
-        top = int(self.free_top.item())
-        self.free_slots[top:top + n] = slots.to(torch.int32)
-        self.free_top.fill_(top + n)
         self.fin_count.zero_()
+        if recycle:
+            self.release(slots)
+        return out
+
+    def release(self, slots):
+        """Push slots back on the free stack and restart games that were parked waiting for one."""
+        e = self.e
+        slots = torch.as_tensor(slots, device=e.device).to(torch.int32).reshape(-1)
+        n = int(slots.numel())
+        if n == 0:
+            return
+        top = int(self.free_top.item())
+        self.free_slots[top:top + n] = slots
+        self.free_top.fill_(top + n)
         check(e.lib.gmz_selfplay_unpark(e.handle, C.byref(self.c), e._stream()), "gmz_selfplay_unpark")
         e.launches += 1
-        return out
+
+
+class DeviceSliceStore:
+    """Replay data resident on the GPU: finished games stay in their trajectory slots, a training
+    sample is the pair (slot, t), and `batch()` builds the trainer tuple (obs, act, rew, pi, val) of
+    workers.py:430-433 with one kernel.  n-step value targets are computed on the device when a game
+    is ingested (workers.py:144-152, 205).  Oldest games are evicted (slots recycled) past `capacity_games`."""
+
+    def __init__(self, traj: "TrajectoryStore", capacity_games=None):
+        self.traj, e = traj, traj.e
+        self.e = e
+        n = traj.n_slots
+        self.capacity_games = int(capacity_games) if capacity_games else max(1, n - e.G - 1)
+        self.targets = torch.zeros((n, traj.max_moves), dtype=torch.float32, device=e.device)
+        self.length = torch.zeros(n, dtype=torch.int32, device=e.device)
+        self.winner = torch.zeros(n, dtype=torch.int32, device=e.device)
+        self.resident = []          # slots in ingestion order
+        self.index = []             # (slot, t) of every stored slice, the order add() would have produced
+
+    def ingest(self, finished):
+        """finished: records from TrajectoryStore.harvest(recycle=False).  Returns the new (slot, t) samples."""
+        if not finished:
+            return []
+        e = self.e
+        slots = torch.tensor([r["slot"] for r in finished], dtype=torch.int32, device=e.device)
+        lens = torch.tensor([r["length"] for r in finished], dtype=torch.int32, device=e.device)
+        wins = torch.tensor([r["winner"] for r in finished], dtype=torch.int32, device=e.device)
+        self.length[slots.long()] = lens
+        self.winner[slots.long()] = wins
+        dpow = torch.tensor([config.DISCOUNT ** i for i in range(config.N_STEPS + 1)], dtype=torch.float64, device=e.device)
+        check(e.lib.gmz_value_targets(C.byref(self.traj.c), slots.data_ptr(), lens.data_ptr(), wins.data_ptr(), len(finished),
+                                      dpow.data_ptr(), int(config.N_STEPS), self.targets.data_ptr(), e._stream()),
+              "gmz_value_targets")
+        e.launches += 1
+        new = []
+        for r in finished:
+            self.resident.append(r["slot"])
+            new += [(r["slot"], t) for t in range(r["length"])]
+        self.index += new
+        while len(self.resident) > self.capacity_games:
+            old = self.resident.pop(0)
+            self.index = [st for st in self.index if st[0] != old]
+            self.traj.release([old])
+        return new
+
+    def batch(self, samples):
+        """samples: sequence of (slot, t).  Returns device tensors (obs f32 [B,U+1,3,N,N], act i32 [B,U],
+        rew f32 [B,U], pi f64 [B,U+1,A], val f32 [B,U+1])."""
+        e = self.e
+        B, U, N, A = len(samples), int(config.NUM_UNROLL_STEPS), e.N, e.A
+        st = torch.tensor(samples, dtype=torch.int32, device=e.device).reshape(B, 2)
+        s_slot, s_t = st[:, 0].contiguous(), st[:, 1].contiguous()
+        obs = torch.empty((B, U + 1, 3, N, N), dtype=torch.float32, device=e.device)
+        act = torch.empty((B, U), dtype=torch.int32, device=e.device)
+        rew = torch.empty((B, U), dtype=torch.float32, device=e.device)
+        pi = torch.empty((B, U + 1, A), dtype=torch.float64, device=e.device)
+        val = torch.empty((B, U + 1), dtype=torch.float32, device=e.device)
+        check(e.lib.gmz_build_batch(C.byref(self.traj.c), N, self.targets.data_ptr(), self.length.data_ptr(),
+                                    self.winner.data_ptr(), s_slot.data_ptr(), s_t.data_ptr(), B, U, obs.data_ptr(),
+                                    act.data_ptr(), rew.data_ptr(), pi.data_ptr(), val.data_ptr(), e._stream()),
+              "gmz_build_batch")
+        e.launches += 1
+        return obs, act, rew, pi, val
 
 
 def final_rewards(num_moves, winner):

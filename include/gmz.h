@@ -168,6 +168,19 @@ int gmz_play_counters(gmz_engine *e, uint64_t *out2, gmz_stream stream);
  * = +-1, 0 (draw) or GMZ_WINNER_NONE. */
 int gmz_game_step(gmz_engine *e, const int32_t *actions, int32_t *out_winner, gmz_stream stream);
 
+/* ---- trajectory post-processing on the device (workers.py:144-152, 183-222, 430-433) ---- */
+/* n-step value targets of finished games: slots / lengths / winners int32 [n_games] (device),
+ * discount_pow f64 [n_steps+1] = discount**i as the host computes them, out targets f32
+ * [n_slots][max_moves].  Final rewards follow workers.py:183-187. */
+int gmz_value_targets(const gmz_traj *traj, const int32_t *slots, const int32_t *lengths, const int32_t *winners,
+                      int n_games, const double *discount_pow, int n_steps, float *targets, gmz_stream stream);
+/* A batch of TrainingSlices (data_structures.py:20-26) rebuilt from resident games: sample b is
+ * (sample_slot[b], sample_t[b]).  Outputs: obs f32 [B,U+1,3,N,N], act i32 [B,U] (pad -1), rew f32
+ * [B,U], pi f64 [B,U+1,A], val f32 [B,U+1] -- the tuple data_loader_worker stacks (workers.py:430-433). */
+int gmz_build_batch(const gmz_traj *traj, int board_size, const float *targets, const int32_t *len_by_slot,
+                    const int32_t *win_by_slot, const int32_t *sample_slot, const int32_t *sample_t, int batch,
+                    int unroll, float *obs, int32_t *act, float *rew, double *pi, float *val, gmz_stream stream);
+
 /* ---- prioritized replay: SumTree (replay_buffer.py:4-106) ------------------- */
 /* tree f64 [2*capacity-1] lives in caller memory.  Sequential reference
  * semantics are preserved bit for bit (each node receives its += in batch order). */

@@ -96,3 +96,59 @@ def test_reanalysis_matches_oracle_per_position():
         np.testing.assert_allclose(pol, opol, rtol=1e-5, atol=1e-12)
         assert len(targets) == T and all(isinstance(t, float) for t in targets)
         off += T
+
+
+def test_device_slice_store_matches_reference_slices():
+    """Device-side n-step targets + batch assembly vs the TrainingSlices the reference's universal_worker
+    cut (tests/golden/selfplay_az_9_100.npz), and vs the host post-processing on kernel-played games."""
+    import torch
+    from datou_gomoku_muzero_b200.config import config
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+    from datou_gomoku_muzero_b200.trajectory import (DeviceSliceStore, TrajectoryStore, build_game_record,
+                                                     cut_training_slices)
+    z = np.load(os.path.join(GOLDEN_DIR, "selfplay_az_9_100.npz"))
+    N, nir, S, K, seed, U, n_steps, version = (int(x) for x in z["params"])
+    A = N * N
+    saved = (config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS)
+    config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS = float(z["discount"]), n_steps, U
+    try:
+        eng = SearchEngine(4, board_size=N, num_simulations=8)
+        traj = TrajectoryStore(eng, extra_slots=8)
+        store = DeviceSliceStore(traj)
+        # plant the reference's game in a free slot, as if the kernel had just finished it
+        T, slot = len(z["actions"]), 6
+        traj.policy[slot, :T] = torch.from_numpy(z["policies"]).cuda()
+        traj.value[slot, :T] = torch.from_numpy(z["search_values"]).cuda()
+        traj.action[slot, :T] = torch.from_numpy(z["actions"]).cuda()
+        traj.start_board[slot].zero_()
+        traj.start_info[slot] = torch.tensor([1, 0, -1, 0], dtype=torch.int32).cuda()
+        new = store.ingest([dict(slot=slot, game=0, length=T, winner=int(z["winner"]))])
+        assert new == [(slot, t) for t in range(T)]
+        np.testing.assert_array_equal(store.targets[slot, :T].cpu().numpy(), z["values_targets"].astype(np.float32))
+        obs, act, rew, pi, val = (x.cpu().numpy() for x in store.batch(new))
+        assert np.array_equal(obs, z["slice_obs"]) and np.array_equal(act, z["slice_act"])
+        assert np.array_equal(rew, z["slice_rew"]) and np.array_equal(pi, z["slice_pi"]) and np.array_equal(val, z["slice_val"])
+        assert obs.dtype == z["slice_obs"].dtype and pi.dtype == np.float64 and act.dtype == np.int32
+        # games the kernel played itself: device batch == host build_game_record + cut_training_slices
+        eng2 = SearchEngine(12, board_size=6, num_simulations=20)
+        sp = SelfPlayEngine(eng2, "e0", seed=2, noise_seed=3)
+        traj2 = TrajectoryStore(eng2, extra_slots=24)
+        store2 = DeviceSliceStore(traj2)
+        fin = []
+        while len(fin) < 6:
+            sp.play(moves_per_game=5, traj=traj2)
+            fin += traj2.harvest(recycle=False)
+        samples = store2.ingest(fin)
+        obs, act, rew, pi, val = (x.cpu().numpy() for x in store2.batch(samples))
+        off = 0
+        for r in fin:
+            sl = cut_training_slices(build_game_record(r))
+            for s in sl:
+                assert np.array_equal(obs[off], s.observation) and np.array_equal(act[off], s.action_history)
+                assert np.array_equal(rew[off], s.reward_history) and np.array_equal(pi[off], s.policy_history)
+                assert np.array_equal(val[off], s.value_history)
+                off += 1
+        assert off == len(samples)
+    finally:
+        config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS = saved
