@@ -181,6 +181,13 @@ int gmz_build_batch(const gmz_traj *traj, int board_size, const float *targets, 
                     const int32_t *win_by_slot, const int32_t *sample_slot, const int32_t *sample_t, int batch,
                     int unroll, float *obs, int32_t *act, float *rew, double *pi, float *val, gmz_stream stream);
 
+/* ---- tactics classifier (find_winning_moves_rebuilt, workers.py:49-123) ---- */
+/* boards int8 [B,A], players int8 [B] (the side to move) -> out_cls int8 [B,A]: per empty cell
+ * 1 = 'five', 2 = 'open_four', 3 = 'combo', 0 = none (occupied cells: 0).  Feeds the missed-win
+ * statistics of the self-play and re-analysis loops (workers.py:191-203, 270-289). */
+int gmz_tactics_classify(const int8_t *boards, const int8_t *players, int batch, int board_size, int n_in_row,
+                         int8_t *out_cls, gmz_stream stream);
+
 /* ---- prioritized replay: SumTree (replay_buffer.py:4-106) ------------------- */
 /* tree f64 [2*capacity-1] lives in caller memory.  Sequential reference
  * semantics are preserved bit for bit (each node receives its += in batch order). */
