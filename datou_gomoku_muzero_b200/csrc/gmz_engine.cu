@@ -508,7 +508,7 @@ static int launch_play(gmz_engine *e, const PlayArgs &a, cudaStream_t st)
     }
     int grid = (e->p.G + GMZ_PLAY_WARPS - 1) / GMZ_PLAY_WARPS;
     if (grid > occ_cache[NC]) grid = occ_cache[NC];
-    if (cudaMemsetAsync(&e->p.ctl->next_ticket, 0, sizeof(unsigned long long), st) != cudaSuccess) return fail("cudaMemsetAsync(ctl)");
+    if (cudaMemsetAsync(&e->p.ctl->next_ticket, 0, 2 * sizeof(unsigned long long), st) != cudaSuccess) return fail("cudaMemsetAsync(ctl)");
     k_play_e0<NC><<<grid, 32 * GMZ_PLAY_WARPS, 0, st>>>(e->p, a);
     return check_launch("k_play_e0");
 }
@@ -578,7 +578,7 @@ extern "C" int gmz_selfplay_unpark(gmz_engine *e, const gmz_traj *traj, gmz_stre
 extern "C" int gmz_play_counters(gmz_engine *e, uint64_t *out2, gmz_stream stream)
 {
     if (!e || !out2) return fail("gmz_play_counters: null argument");
-    cudaError_t err = cudaMemcpyAsync(out2, &e->p.ctl->moves_played, 2 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    cudaError_t err = cudaMemcpyAsync(out2, &e->p.ctl->moves_played, 4 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     if (err != cudaSuccess) return fail("gmz_play_counters: %s", cudaGetErrorString(err));
     return 0;
 }

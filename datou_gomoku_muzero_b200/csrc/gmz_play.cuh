@@ -175,10 +175,13 @@ __device__ __forceinline__ double gumbel_at(u64 seed_mixed, u64 counter)
 
 // Device-side control block of the play kernel.
 struct PlayCtl {
-    unsigned long long next_ticket;
+    unsigned long long next_ticket;        // round-robin game cursor of the current launch
+    unsigned long long moves_started;      // moves handed out in the current launch
     unsigned long long moves_played;
     unsigned long long games_finished;
-    unsigned long long pad;
+    unsigned long long tickets_unserved;   // no playable game found (everything busy / parked)
+    unsigned long long tickets_idle;       // game acquired but no move came out of it
+    unsigned long long pad[2];
 };
 
 // Caller-owned trajectory storage (gmz_traj in include/gmz.h), device pointers.
@@ -257,30 +260,41 @@ k_play_e0(Params p, PlayArgs a)
     short *table = p.pyset + (size_t)warp_slot * 4096;
     const u64 noise_mixed = mix64(a.noise_seed ^ E0_GOLD);
     for (;;) {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(&p.ctl->next_ticket, 1ull);
-        t = __shfl_sync(GMZ_FULL, t, 0);
-        if ((long long)t >= a.total_tickets) break;
-        int g = (int)(t % (unsigned long long)p.G);
-        // acquire a playable game: linear probe from the ticket's game
-        bool got = false;
-        for (int tries = 0; tries < p.G; ++tries) {
+        // Pick a game: every attempt draws the next position of ONE global cursor that sweeps the
+        // games round-robin, so the cursor always points at the game that has been idle longest
+        // (a per-warp linear probe instead can run in lock-step with the window of busy games and
+        // starve).  A busy / parked game is simply skipped; a move is only counted once a game is held.
+        int g = 0;
+        bool got = false, done = false;
+        for (int tries = 0; tries < 4 * p.G; ++tries) {
+            unsigned long long t = 0;
             int ok = 0;
             if (lane == 0) {
-                GState *s = p.gs + g;
-                if (atomicCAS(&s->busy, 0, 1) == 0) {
-                    __threadfence();
-                    const volatile GState *vs = s;
-                    ok = 1;
-                    if (a.do_step && (vs->parked || (vs->winner != GMZ_WINNER_NONE && !a.restart))) { ok = 0; atomicExch(&s->busy, 0); }
+                t = atomicAdd(&p.ctl->next_ticket, 1ull);
+                if (!a.do_step && (long long)t >= a.total_tickets) ok = -1;      // search-only: one ticket per game
+                else {
+                    GState *s = p.gs + (int)(t % (unsigned long long)p.G);
+                    if (atomicCAS(&s->busy, 0, 1) == 0) {
+                        __threadfence();
+                        const volatile GState *vs = s;
+                        ok = 1;
+                        if (a.do_step && (vs->parked || (vs->winner != GMZ_WINNER_NONE && !a.restart))) ok = 0;
+                        if (ok && a.do_step && (long long)atomicAdd(&p.ctl->moves_started, 1ull) >= a.total_tickets) ok = -1;
+                        if (ok != 1) atomicExch(&s->busy, 0);
+                    }
                 }
             }
             ok = __shfl_sync(GMZ_FULL, ok, 0);
-            if (ok) { got = true; break; }
-            if (!a.do_step) break;          // search-only tickets map 1:1 to games
-            g = g + 1 == p.G ? 0 : g + 1;
+            t = __shfl_sync(GMZ_FULL, t, 0);
+            g = (int)(t % (unsigned long long)p.G);
+            if (ok == 1) { got = true; break; }
+            if (ok < 0) { done = true; break; }
         }
-        if (!got) { if (a.do_step) break; else continue; }
+        if (done) break;
+        if (!got) {                          // nothing playable (everything parked): give up
+            if (lane == 0) atomicAdd(&p.ctl->tickets_unserved, 1ull);
+            break;
+        }
         __threadfence();                    // acquire: everything the previous owner wrote is visible
         GState *s = p.gs + g;
         short *path = p.path + (size_t)g * (p.S + 2);   // root..leaf-parent node ids (global, L1-resident)
@@ -355,7 +369,9 @@ k_play_e0(Params p, PlayArgs a)
         finalize_root<NC, false>(p, w, lane, pol, vis, s_nvis[wi], table, value, action);
         if (!a.do_step) {
             if (lane == 0) { if (a.out_value) a.out_value[g] = value; if (a.out_action) a.out_action[g] = action; }
-        } else if (action >= 0) {
+        } else if (action < 0) {
+            if (lane == 0) atomicAdd(&p.ctl->tickets_idle, 1ull);
+        } else {
             if (a.use_traj && lane == 0 && tl < a.traj.max_moves) {
                 a.traj.value[(size_t)slot * a.traj.max_moves + tl] = value;
                 a.traj.action[(size_t)slot * a.traj.max_moves + tl] = action;

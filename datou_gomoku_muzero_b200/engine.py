@@ -198,9 +198,10 @@ class SearchEngine:
 
     def play_counters(self):
         """(moves played, games finished) by the persistent kernel since the engine was created."""
-        out = torch.zeros(2, dtype=torch.int64, device=self.device)
+        out = torch.zeros(4, dtype=torch.int64, device=self.device)
         check(self.lib.gmz_play_counters(self.handle, _ptr(out), self._stream()), "gmz_play_counters")
-        m, f = out.cpu().tolist()
+        m, f, unserved, idle = out.cpu().tolist()
+        self.tickets_unserved, self.tickets_idle = int(unserved), int(idle)
         return int(m), int(f)
 
     def fill_gumbel(self, out, seed, offset=0):

@@ -159,7 +159,8 @@ int gmz_traj_init(gmz_engine *e, const gmz_traj *traj, gmz_stream stream);
 int gmz_selfplay_e0(gmz_engine *e, const gmz_traj *traj, uint64_t eval_seed, int logit_div, uint64_t noise_seed,
                     int64_t total_moves, int restart, gmz_stream stream);
 int gmz_selfplay_unpark(gmz_engine *e, const gmz_traj *traj, gmz_stream stream);
-/* out2 (device, uint64 [2]) = moves played, games finished since gmz_create. */
+/* out (device, uint64 [4]) = moves played, games finished, tickets that found no playable game,
+ * tickets whose game produced no move -- all since gmz_create. */
 int gmz_play_counters(gmz_engine *e, uint64_t *out2, gmz_stream stream);
 
 /* ---- self-play game step --------------------------------------------------- */
