@@ -242,22 +242,23 @@ def run_ours(args):
     # decision, D2H of policy/value/action every step), double-buffered over two engines so the heavy
     # tail of one batch overlaps the next batch (PipelinedBatchSearch)
     from datou_gomoku_muzero_b200.mcts import PipelinedBatchSearch
-    eng2 = SearchEngine(G, board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP, device=dev)
-    pipe = PipelinedBatchSearch([eng, eng2], evaluator="e0", eval_seed=E0_SEED, logit_div=LOGIT_DIV)
+    engs = [eng] + [SearchEngine(G, board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP, device=dev)
+                    for _ in range(args.e2e_depth - 1)]
+    pipe = PipelinedBatchSearch(engs, evaluator="e0", eval_seed=E0_SEED, logit_div=LOGIT_DIV)
     hb, hp, hl, hm = staggered_positions(G, rank)
     hgums = [np.random.RandomState(5 + rank + 17 * i).gumbel(0, 1, (G, A)) for i in range(3)]
-    for i in range(2):
-        pipe.result(pipe.submit(hb, hp, hl, hm, hgums[i]))
+    for i in range(args.e2e_depth):
+        pipe.result(pipe.submit(hb, hp, hl, hm, hgums[i % 3]))
     barrier()
-    e2e_steps = max(4, min(args.steps, 10))
+    e2e_steps = max(2 * args.e2e_depth, min(args.steps, 12))
     t0 = time.perf_counter()
-    prev = None
+    inflight = []
     for i in range(e2e_steps):
-        tk = pipe.submit(hb, hp, hl, hm, hgums[i % 3])
-        if prev is not None:
-            pol, val, act = pipe.result(prev)
-        prev = tk
-    pol, val, act = pipe.result(prev)
+        inflight.append(pipe.submit(hb, hp, hl, hm, hgums[i % 3]))
+        if len(inflight) >= args.e2e_depth:
+            pol, val, act = pipe.result(inflight.pop(0))
+    while inflight:
+        pol, val, act = pipe.result(inflight.pop(0))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -301,7 +302,8 @@ def run_ours(args):
         "e2e": {"value": sims_per_step * e2e_steps / e2e_s, "unit": "sims/s",
                 "h2d_bytes_per_step": int(hb.nbytes + hp.nbytes + hl.nbytes + hm.nbytes + hgums[0].nbytes),
                 "d2h_bytes_per_step": int(pol.nbytes + val.nbytes + act.nbytes), "steps": e2e_steps,
-                "api": "PipelinedBatchSearch.submit/result(host boards, players, last_moves, move_counts, gumbel), depth 2"},
+                "api": "PipelinedBatchSearch.submit/result(host boards, players, last_moves, move_counts, gumbel)",
+                "pipeline_depth": args.e2e_depth},
         "gpu_launches": launches,
         "games_finished_in_timed_region": int(finished), "games_harvested": harvested,
         "roofline": {"bound": "hbm", "kernel": "k_play_e0<2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -334,6 +336,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-net", action="store_true", help="skip the real-network (E1) leg")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="host batches in flight in the end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
