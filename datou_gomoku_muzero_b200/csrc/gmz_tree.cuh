@@ -145,23 +145,19 @@ __device__ __forceinline__ double row_softmax(const Params &p, const WG &w, cons
 }
 
 // Per-warp scratch for the visited children of the node being scored.  Nodes almost always have
-// <= GMZ_SPARSE_SMEM visited children, so that many entries live in shared memory; the rare
-// bigger node uses this warp's slice of a global overflow area (Params::sel_overflow) instead.
+// <= 32 visited children: then child k is handed to lane k through 256 bytes of shared memory and
+// scored in registers.  The rare bigger node takes select_interior_big, which loops over this
+// warp's slice of a global overflow area (Params::sel_overflow).
 // Shared memory is kept small on purpose: it is carved out of the same 228 KB as the L1 cache
 // that serves the node-header gathers.
 #ifndef GMZ_EXP_UNROLL
 #define GMZ_EXP_UNROLL 2
 #endif
 constexpr int kExpUnroll = GMZ_EXP_UNROLL;
-#ifndef GMZ_SPARSE_SMEM
-#define GMZ_SPARSE_SMEM 64
-#endif
 struct SelSmem {
     double dx[256];                // dense pass: element i of lane l at [32*i + l] (NC <= 2; NC = 3 keeps registers)
-    int key[GMZ_SPARSE_SMEM];      // (action << 16) | child node id
-    float lg[GMZ_SPARSE_SMEM];     // logit of that action
-    int n[GMZ_SPARSE_SMEM];        // child visit count
-    double x[GMZ_SPARSE_SMEM];     // child value_sum, then logit + sigma, then exp(...)
+    int key[32];                   // visited child k -> (action << 16) | child node id   (fast path: <= 32 children)
+    float lg[32];                  // logit of that action
 };
 // Working pointers for one select call (shared or global, chosen per node).
 struct SelPtr { int *key; float *lg; int *n; double *x; };
@@ -183,8 +179,8 @@ __device__ __forceinline__ SelPtr sel_global(const Params &p, int warp_slot)
 // branch-free dense pass from the row alone.  The few visited children are compacted into
 // `sc` (one per lane) and scored in a sparse pass that gathers their N / W.
 template <int NC, bool MZ>
-__device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
-                                                int &action, int &child)
+__device__ __noinline__ void select_interior_big(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
+                                                 int &action, int &child)
 {
     constexpr int E = 4 * NC;
     const size_t ni = w.nbase + (size_t)node;
@@ -203,14 +199,13 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
     for (int i = 0; i < E; ++i) vm |= (ch[i] >= 0 ? 1u : 0u) << i;
     // compact the visited children: lane prefix over popc(vm)
     int total = 0;
-    SelPtr sc; sc.key = sm.key; sc.lg = sm.lg; sc.n = sm.n; sc.x = sm.x;
+    SelPtr sc = sel_global<NC>(p, warp_slot);
     if (__any_sync(GMZ_FULL, vm != 0)) {
         const int cnt = __popc(vm);
         int inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(GMZ_FULL, inc, o); if (lane >= o) inc += t; }
         total = __shfl_sync(GMZ_FULL, inc, 31);
-        if (total > GMZ_SPARSE_SMEM) sc = sel_global<NC>(p, warp_slot);
         int pos = inc - cnt;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
@@ -313,6 +308,136 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
             const int a = sc.key[k] >> 16;
             if (s > best || (s == best && a < ba)) { best = s; ba = a; bc = sc.key[k] & 0xffff; }
         }
+    }
+    // warp argmax, lowest action wins ties (np.argmax, mcts.py:117)
+    const u64 mk = warp_max_key(f64_key(best));
+    const int a = __reduce_min_sync(GMZ_FULL, f64_key(best) == mk ? ba : 0x7fffffff);
+    const unsigned own = __ballot_sync(GMZ_FULL, f64_key(best) == mk && ba == a);
+    action = a;
+    child = __shfl_sync(GMZ_FULL, bc, __ffs(own) - 1);
+    __syncwarp();
+}
+
+// Fast path of _select_action (mcts.py:106-117) for nodes with <= 32 visited children: lane k owns
+// visited child k in registers (N, W -> q -> sigma -> exp -> score), every lane owns 4*NC dense
+// (unvisited) actions.  Same arithmetic, same order of operations per element as the big variant.
+template <int NC, bool MZ>
+__device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
+                                                int &action, int &child)
+{
+    constexpr int E = 4 * NC;
+    const size_t ni = w.nbase + (size_t)node;
+    const float *lrow = p.logits + ni * (size_t)p.AP;
+    const short *crow = p.child + ni * (size_t)p.AP;
+    float lg[E]; short ch[E];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const float4 t = *reinterpret_cast<const float4 *>(lrow + 128 * j + 4 * lane);
+        const short4 c = *reinterpret_cast<const short4 *>(crow + 128 * j + 4 * lane);
+        lg[4 * j + 0] = t.x; lg[4 * j + 1] = t.y; lg[4 * j + 2] = t.z; lg[4 * j + 3] = t.w;
+        ch[4 * j + 0] = c.x; ch[4 * j + 1] = c.y; ch[4 * j + 2] = c.z; ch[4 * j + 3] = c.w;
+    }
+    unsigned vm = 0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) vm |= (ch[i] >= 0 ? 1u : 0u) << i;
+    int total = 0;
+    if (__any_sync(GMZ_FULL, vm != 0)) {
+        const int cnt = __popc(vm);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(GMZ_FULL, inc, o); if (lane >= o) inc += t; }
+        total = __shfl_sync(GMZ_FULL, inc, 31);
+        if (total > 32) { select_interior_big<NC, MZ>(p, w, node, lane, sm, warp_slot, action, child); return; }
+        int pos = inc - cnt;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            if ((vm >> i) & 1u) {
+                sm.key[pos] = ((128 * (i >> 2) + 4 * lane + (i & 3)) << 16) | (int)ch[i];
+                sm.lg[pos] = lg[i];
+                ++pos;
+            }
+        }
+        __syncwarp();
+    }
+    // sparse: lane k < total owns visited child k
+    const bool sp = lane < total;
+    int key = 0, nn = 0; float slg = 0.f; double W = 0.0, rew = 0.0;
+    if (sp) {
+        key = sm.key[lane]; slg = sm.lg[lane];
+        const size_t ci = w.nbase + (size_t)(key & 0xffff);
+        nn = p.nN[ci]; W = p.nW[ci];
+        if (MZ) rew = p.nR[ci];
+    }
+    const int maxN = __reduce_max_sync(GMZ_FULL, nn), sumN = __reduce_add_sync(GMZ_FULL, nn);
+    const double scale = __dmul_rn(__dadd_rn(p.c_visit, (double)maxN), p.c_scale);
+    const bool rng = w.mm_max > w.mm_min;
+    const double denom = __dadd_rn(__dsub_rn(w.mm_max, w.mm_min), p.delta);
+    const double sig0 = __dmul_rn(scale, mm_norm(0.0, rng, w.mm_min, denom));   // unvisited: q = 0.0
+    double lmx = -INFINITY, xs = -INFINITY;
+    if (sp) {
+        const double val = __ddiv_rn(W, (double)nn);                            // child.get_value()
+        const double q = __dadd_rn(rew, __dmul_rn(p.discount, val));
+        xs = __dadd_rn((double)slg, __dmul_rn(scale, mm_norm(q, rng, w.mm_min, denom)));
+        lmx = xs;
+    }
+    const unsigned dv = w.vb & ~vm;      // valid and unvisited: the dense set
+    double best = -INFINITY; int ba = 0x7fffffff, bc = -1;
+    double inv;
+    if (NC <= 2) {
+        // rolled loops over this lane's E elements staged in shared memory: small code (the loop is
+        // bound by instruction fetch / dependent-issue latency, not by the extra LDS/STS)
+        double *dx = sm.dx + lane;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const double xi = __dadd_rn((double)lg[i], sig0);
+            dx[32 * i] = xi;
+            if ((dv >> i) & 1u) lmx = dmax2(lmx, xi);
+        }
+        const double mx = warp_max_f64(lmx);
+        double ls = 0.0;
+#pragma unroll kExpUnroll
+        for (int i = 0; i < E; ++i) {
+            double e = exp_nonpos(dmin2(__dsub_rn(dx[32 * i], mx), 0.0));
+            e = ((dv >> i) & 1u) ? e : 0.0;
+            dx[32 * i] = e;
+            ls = __dadd_rn(ls, e);
+        }
+        if (sp) { xs = exp_nonpos(__dsub_rn(xs, mx)); ls = __dadd_rn(ls, xs); }
+        inv = __ddiv_rn(1.0, warp_sum_f64(ls));
+        int bi = -1;
+#pragma unroll 2
+        for (int i = 0; i < E; ++i) {
+            const double s = __dmul_rn(dx[32 * i], inv);
+            if (((dv >> i) & 1u) && s > best) { best = s; bi = i; }
+        }
+        if (bi >= 0) ba = 128 * (bi >> 2) + 4 * lane + (bi & 3);
+    } else {
+        double x[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            x[i] = __dadd_rn((double)lg[i], sig0);
+            if ((dv >> i) & 1u) lmx = dmax2(lmx, x[i]);
+        }
+        const double mx = warp_max_f64(lmx);
+        double ls = 0.0;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const double e = exp_nonpos(dmin2(__dsub_rn(x[i], mx), 0.0));
+            x[i] = ((dv >> i) & 1u) ? e : 0.0;
+            ls = __dadd_rn(ls, x[i]);
+        }
+        if (sp) { xs = exp_nonpos(__dsub_rn(xs, mx)); ls = __dadd_rn(ls, xs); }
+        inv = __ddiv_rn(1.0, warp_sum_f64(ls));
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const double s = __dmul_rn(x[i], inv);
+            if (((dv >> i) & 1u) && s > best) { best = s; ba = 128 * (i >> 2) + 4 * lane + (i & 3); }
+        }
+    }
+    if (sp) {
+        const double s = __dsub_rn(__dmul_rn(xs, inv), __ddiv_rn((double)nn, (double)(1 + sumN)));
+        const int a = key >> 16;
+        if (s > best || (s == best && a < ba)) { best = s; ba = a; bc = key & 0xffff; }
     }
     // warp argmax, lowest action wins ties (np.argmax, mcts.py:117)
     const u64 mk = warp_max_key(f64_key(best));
