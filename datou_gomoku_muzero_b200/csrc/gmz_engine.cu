@@ -133,7 +133,7 @@ k_root_expand(Params p, const float *logits, const void *values, int vdtype, con
     if (g >= p.G) return;
     WG w; wg_load(p, g, lane, w);
     if (!w.active) return;
-    wg_valid_bits<NC>(w, lane);
+    wg_valid_bits<NC>(p, w, lane);
     float lg[4 * NC]; double gum[4 * NC];
     load_lane_logits<NC>(logits + (size_t)g * p.A, p.A, lane, lg);
 #pragma unroll
@@ -170,7 +170,7 @@ k_select(Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, 
         }
         return;
     }
-    wg_valid_bits<NC>(w, lane);
+    wg_valid_bits<NC>(p, w, lane);
     __shared__ SelSmem s_sel[WARPS_PER_CTA];
     short *path = p.path + (size_t)g * (p.S + 2);
     u64 P = w.P, M = w.M; int colour = w.to_move;

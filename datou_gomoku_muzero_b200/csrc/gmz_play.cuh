@@ -72,7 +72,7 @@ __device__ __noinline__ void finalize_root(const Params &p, WG &w, int lane, dou
         value = 0.0; action = -1;
         return;
     }
-    wg_valid_bits<NC>(w, lane);
+    wg_valid_bits<NC>(p, w, lane);
     Row<NC> r;
     row_load<NC, MZ>(p, w, 0, lane, r);
     double x[4 * NC];
@@ -98,7 +98,7 @@ __device__ __noinline__ void finalize_root(const Params &p, WG &w, int lane, dou
     if (ties > 1) {
         u64 vw[GMZ_WORDS];
 #pragma unroll
-        for (int k = 0; k < GMZ_WORDS; ++k) vw[k] = shfl_u64(w.V, k);
+        for (int k = 0; k < GMZ_WORDS; ++k) vw[k] = p.gs[w.g].valid[k];
         if (lane == 0) best = pyset_first_max(vw, p.A, nvis, maxn, table);
         best = __shfl_sync(GMZ_FULL, best, 0);
     }
@@ -227,7 +227,7 @@ template <int NC>
 __device__ __noinline__ void play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane);
 
 #ifndef GMZ_PLAY_MIN_CTAS
-#define GMZ_PLAY_MIN_CTAS 5
+#define GMZ_PLAY_MIN_CTAS 6
 #endif
 #define GMZ_PLAY_WARPS 4
 
@@ -306,7 +306,7 @@ k_play_e0(Params p, PlayArgs a)
         WG w; wg_load(p, g, lane, w);
         double value = 0.0; int action = -1;
         if (w.active) {
-            wg_valid_bits<NC>(w, lane);
+            wg_valid_bits<NC>(p, w, lane);
             play_root<NC>(p, a, w, s->noise_ctr, noise_mixed, lane);
             __syncwarp();
             int ev = 0;

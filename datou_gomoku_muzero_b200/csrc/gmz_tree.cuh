@@ -10,11 +10,11 @@ struct WG {
     size_t nbase;          // U  g * S : index of this game's node 0 in the per-node arrays
     double mm_min, mm_max; // U  MinMaxStats
     int sim_count, num_nodes, phase, next_thr, n_surv, n_init, to_move, last_move, active;  // U
-    u64 P, M, V;           // L  lane w < NW holds word w of p1 / m1 / valid
+    u64 P, M;              // L  lane w < NW holds word w of p1 / m1
     unsigned vb;           // L  valid bits of this lane's actions (bit 4*j + t)
     int s_act, s_child, s_n;  // L  lane i < n_init: survivor i
-    double s_g;            // L
-    float s_logit;         // L
+    // (the survivors' gumbel noise / root logits and the valid bitboard stay in GState: they are only
+    //  needed at the <= 5 halvings and at the decision, and registers decide the occupancy here)
 };
 
 __device__ __forceinline__ void wg_load(const Params &p, int g, int lane, WG &w)
@@ -27,17 +27,16 @@ __device__ __forceinline__ void wg_load(const Params &p, int g, int lane, WG &w)
     w.active = s->active;
     w.P = lane < GMZ_WORDS ? s->p1[lane] : 0ull;
     w.M = lane < GMZ_WORDS ? s->m1[lane] : 0ull;
-    w.V = lane < GMZ_WORDS ? s->valid[lane] : 0ull;
     w.s_act = s->surv_act[lane]; w.s_child = s->surv_child[lane]; w.s_n = s->surv_n[lane];
-    w.s_g = s->surv_g[lane]; w.s_logit = s->surv_logit[lane];
 }
 template <int NC>
-__device__ __forceinline__ void wg_valid_bits(WG &w, int lane)
+__device__ __forceinline__ void wg_valid_bits(const Params &p, WG &w, int lane)
 {
+    const u64 V = lane < GMZ_WORDS ? p.gs[w.g].valid[lane] : 0ull;
     unsigned vb = 0;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
-        u64 word = shfl_u64(w.V, 2 * j + (lane >> 4));
+        u64 word = shfl_u64(V, 2 * j + (lane >> 4));
         vb |= (unsigned)((word >> ((lane & 15) * 4)) & 0xFull) << (4 * j);
     }
     w.vb = vb;
@@ -51,7 +50,6 @@ __device__ __forceinline__ void wg_store_search(const Params &p, int lane, const
         s->n_surv = w.n_surv; s->n_init = w.n_init;
     }
     s->surv_act[lane] = (short)w.s_act; s->surv_child[lane] = (short)w.s_child; s->surv_n[lane] = w.s_n;
-    s->surv_g[lane] = w.s_g; s->surv_logit[lane] = w.s_logit;
 }
 
 // GomokuGame.do_move on the lane-distributed bitboards (game.py:20-23): the stone OVERWRITES
@@ -558,7 +556,9 @@ __device__ __forceinline__ void sequential_halving(const Params &p, WG &w, int l
     const bool rng = w.mm_max > w.mm_min;
     const double denom = __dadd_rn(__dsub_rn(w.mm_max, w.mm_min), p.delta);
     const double sig = __dmul_rn(scale, mm_norm(q, rng, w.mm_min, denom));
-    const double score = __dadd_rn(__dadd_rn(w.s_g, (double)w.s_logit), sig);
+    GState *gs = p.gs + w.g;
+    double s_g = gs->surv_g[lane]; float s_logit = gs->surv_logit[lane];
+    const double score = __dadd_rn(__dadd_rn(s_g, (double)s_logit), sig);
     int rank = 0;
     for (int j = 0; j < w.n_surv; ++j) {
         const double sj = __shfl_sync(GMZ_FULL, score, j);
@@ -573,8 +573,9 @@ __device__ __forceinline__ void sequential_halving(const Params &p, WG &w, int l
     w.s_act = __shfl_sync(GMZ_FULL, w.s_act, src);
     w.s_child = __shfl_sync(GMZ_FULL, w.s_child, src);
     w.s_n = __shfl_sync(GMZ_FULL, w.s_n, src);
-    w.s_g = __shfl_sync(GMZ_FULL, w.s_g, src);
-    w.s_logit = __shfl_sync(GMZ_FULL, w.s_logit, src);
+    s_g = __shfl_sync(GMZ_FULL, s_g, src);
+    s_logit = __shfl_sync(GMZ_FULL, s_logit, src);
+    gs->surv_g[lane] = s_g; gs->surv_logit[lane] = s_logit;
     w.n_surv = min(p.m_of_phase[w.phase], w.n_surv);
 }
 
@@ -604,7 +605,10 @@ __device__ __forceinline__ void root_init(const Params &p, WG &w, const float *l
     unsigned rem = w.vb;
 #pragma unroll
     for (int i = 0; i < 4 * NC; ++i) sc[i] = __dadd_rn(gum[i], (double)lg[i]);
-    w.s_act = -1; w.s_child = -1; w.s_n = 0; w.s_g = 0.0; w.s_logit = 0.f;
+    w.s_act = -1; w.s_child = -1; w.s_n = 0;
+    GState *gs = p.gs + w.g;
+    gs->surv_g[lane] = 0.0; gs->surv_logit[lane] = 0.f;
+    __syncwarp();
     int cnt = 0;
     for (int r = 0; r < p.K; ++r) {
         double best = -INFINITY; int ba = -1;
@@ -627,7 +631,7 @@ __device__ __forceinline__ void root_init(const Params &p, WG &w, const float *l
                 if (128 * (i >> 2) + 4 * lane + (i & 3) == ba) { gsel = gum[i]; lsel = lg[i]; rem &= ~(1u << i); }
         }
         gsel = __shfl_sync(GMZ_FULL, gsel, owner); lsel = __shfl_sync(GMZ_FULL, lsel, owner);
-        if (lane == r) { w.s_act = ba; w.s_g = gsel; w.s_logit = lsel; }
+        if (lane == r) { w.s_act = ba; gs->surv_g[r] = gsel; gs->surv_logit[r] = lsel; }
         ++cnt;
     }
     w.n_init = cnt; w.n_surv = cnt;
