@@ -56,6 +56,7 @@ SIGNATURES = {
     "gmz_traj_init": (C.c_int, [_P, C.POINTER(GmzTraj), _P]),
     "gmz_selfplay_e0": (C.c_int, [_P, C.POINTER(GmzTraj), C.c_uint64, C.c_int, C.c_uint64, C.c_int64, C.c_int, _P]),
     "gmz_selfplay_unpark": (C.c_int, [_P, C.POINTER(GmzTraj), _P]),
+    "gmz_selfplay_step": (C.c_int, [_P, C.POINTER(GmzTraj), _P, _P, _P, C.c_int, _P, _P]),
     "gmz_play_counters": (C.c_int, [_P, _P, _P]),
     "gmz_value_targets": (C.c_int, [C.POINTER(GmzTraj), _P, _P, _P, C.c_int, _P, C.c_int, _P, _P]),
     "gmz_build_batch": (C.c_int, [C.POINTER(GmzTraj), C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),

@@ -271,6 +271,65 @@ __global__ void k_fill_gumbel(double *out, size_t n, u64 seed, u64 offset)
     out[i] = gumbel_at(mix64(seed ^ E0_GOLD), offset + i);
 }
 
+// Stepwise self-play move (external evaluator): what k_play_e0 does after its search, as a kernel of
+// its own -- record (policy, value, action) in the game's trajectory slot, do_move, get_game_ended,
+// hand finished games to the host queue and restart them in a fresh slot (workers.py:172-189, 230).
+__global__ void __launch_bounds__(CTA_THREADS)
+k_selfplay_step(Params p, TrajDev t, int use_traj, int restart, const double *policy, const double *value,
+                const int32_t *action, int32_t *out_winner)
+{
+    const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= p.G) return;
+    GState *s = p.gs + g;
+    const int a = action[g];
+    if (s->parked || a < 0 || a >= p.A || s->winner != GMZ_WINNER_NONE) {
+        if (lane == 0 && out_winner) out_winner[g] = s->winner;
+        return;
+    }
+    int slot = -1, tl = 0;
+    if (use_traj) {
+        slot = s->traj_slot; tl = s->traj_len;
+        if (tl == 0) {
+            if (lane < GMZ_WORDS) {
+                t.start_board[((size_t)slot * 2 + 0) * GMZ_WORDS + lane] = s->p1[lane];
+                t.start_board[((size_t)slot * 2 + 1) * GMZ_WORDS + lane] = s->m1[lane];
+            }
+            if (lane == 0) {
+                int32_t *si = t.start_info + (size_t)slot * 4;
+                si[0] = s->to_move; si[1] = s->move_count; si[2] = s->last_move; si[3] = g;
+            }
+        }
+        if (tl < t.max_moves) {
+            double *dst = t.policy + ((size_t)slot * t.max_moves + tl) * (size_t)p.A;
+            for (int c = lane; c < p.A; c += 32) dst[c] = policy[(size_t)g * p.A + c];
+            if (lane == 0) { t.value[(size_t)slot * t.max_moves + tl] = value[g]; t.action[(size_t)slot * t.max_moves + tl] = a; }
+        }
+    }
+    __syncwarp();
+    const int wv = game_do_move(p, s, a, lane);
+    if (lane == 0) {
+        s->noise_ctr += 1; s->traj_len = tl + 1;
+        atomicAdd(&p.ctl->moves_played, 1ull);
+        if (out_winner) out_winner[g] = wv;
+    }
+    if (wv != GMZ_WINNER_NONE) {
+        int ok = 1, nslot = -1;
+        if (lane == 0) {
+            atomicAdd(&p.ctl->games_finished, 1ull);
+            if (use_traj) {
+                const int qi = atomicAdd(t.fin_count, 1);
+                if (qi < t.fin_cap) { int32_t *q = t.fin_queue + (size_t)qi * 4; q[0] = slot; q[1] = g; q[2] = tl + 1; q[3] = wv; }
+                ok = (qi < t.fin_cap) && restart && traj_pop_slot(t, nslot);
+                if (qi >= t.fin_cap) atomicSub(t.fin_count, 1);
+            } else ok = restart;
+        }
+        ok = __shfl_sync(GMZ_FULL, ok, 0); nslot = __shfl_sync(GMZ_FULL, nslot, 0);
+        __syncwarp();
+        if (ok) { game_reset(p, s, lane); if (lane == 0 && use_traj) s->traj_slot = nslot; }
+        else if (lane == 0) s->parked = use_traj ? 1 : 0;
+    }
+}
+
 // parked games (finished, no free trajectory slot at the time): take a slot and restart
 __global__ void __launch_bounds__(CTA_THREADS) k_unpark(Params p, TrajDev t)
 {
@@ -567,6 +626,14 @@ extern "C" int gmz_selfplay_e0(gmz_engine *e, const gmz_traj *traj, uint64_t eva
     int rc = 0;
     DISPATCH_NC(e, rc = launch_play<NC>(e, a, (cudaStream_t)stream));
     return rc;
+}
+extern "C" int gmz_selfplay_step(gmz_engine *e, const gmz_traj *traj, const double *policy, const double *value,
+                                 const int32_t *action, int restart, int32_t *out_winner, gmz_stream stream)
+{
+    if (!e || !action) return fail("gmz_selfplay_step: null argument");
+    if (traj && (check_traj(e, traj) || !policy || !value)) return traj && policy && value ? 1 : fail("gmz_selfplay_step: policy/value required with a trajectory store");
+    k_selfplay_step<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, traj_dev(traj), traj ? 1 : 0, restart ? 1 : 0, policy, value, action, out_winner);
+    return check_launch("k_selfplay_step");
 }
 extern "C" int gmz_selfplay_unpark(gmz_engine *e, const gmz_traj *traj, gmz_stream stream)
 {

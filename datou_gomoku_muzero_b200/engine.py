@@ -196,6 +196,14 @@ class SearchEngine:
                                        self._stream()), "gmz_selfplay_e0")
         self.launches += 1
 
+    def selfplay_step(self, policy, value, action, traj=None, restart=True):
+        """Stepwise-path move bookkeeping: record into the trajectory store, do_move, end check, restart."""
+        check(self.lib.gmz_selfplay_step(self.handle, C.byref(traj.c) if traj is not None else None, _ptr(policy),
+                                         _ptr(value), _ptr(action), int(bool(restart)), _ptr(self.winner), self._stream()),
+              "gmz_selfplay_step")
+        self.launches += 1
+        return self.winner
+
     def play_counters(self):
         """(moves played, games finished) by the persistent kernel since the engine was created."""
         out = torch.zeros(4, dtype=torch.int64, device=self.device)

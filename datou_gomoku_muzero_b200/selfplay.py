@@ -45,15 +45,14 @@ class SelfPlayEngine:
                 e.expand_backup(lg, v)
         return e.finalize(want_visits=False)
 
-    def step(self, restart=True):
-        """One self-play move for all G games (workers.py:168-181) + restart of finished games."""
+    def step(self, restart=True, traj=None):
+        """One self-play move for all G games through the stepwise kernels (any evaluator): search,
+        decision, trajectory record, do_move, end check, restart (workers.py:168-189).  Finished games
+        are harvested from `traj` exactly as with play()."""
         e = self.e
-        _, _, action, _ = self.search()
-        winner = e.game_step(action)
+        policy, value, action, _ = self.search()
+        winner = e.selfplay_step(policy, value, action, traj, restart)
         self.moves_played += e.G
-        if restart:
-            torch.ne(winner, 2, out=self.done_mask)
-            e.reset_games(self.done_mask)
         return winner
 
     def play(self, moves_per_game=1, traj=None, restart=True):

@@ -159,6 +159,12 @@ int gmz_traj_init(gmz_engine *e, const gmz_traj *traj, gmz_stream stream);
 int gmz_selfplay_e0(gmz_engine *e, const gmz_traj *traj, uint64_t eval_seed, int logit_div, uint64_t noise_seed,
                     int64_t total_moves, int restart, gmz_stream stream);
 int gmz_selfplay_unpark(gmz_engine *e, const gmz_traj *traj, gmz_stream stream);
+/* The same move bookkeeping for the stepwise path (any evaluator): after gmz_finalize, record
+ * (policy f64 [G,A], value f64 [G], action int32 [G]) in each game's trajectory slot, do_move,
+ * get_game_ended, queue finished games and restart them (workers.py:172-189, 230).  traj may be
+ * NULL (no recording); out_winner int32 [G] may be NULL. */
+int gmz_selfplay_step(gmz_engine *e, const gmz_traj *traj, const double *policy, const double *value,
+                      const int32_t *action, int restart, int32_t *out_winner, gmz_stream stream);
 /* out (device, uint64 [4]) = moves played, games finished, tickets that found no playable game,
  * tickets whose game produced no move -- all since gmz_create. */
 int gmz_play_counters(gmz_engine *e, uint64_t *out2, gmz_stream stream);

@@ -152,3 +152,48 @@ def test_device_slice_store_matches_reference_slices():
         assert off == len(samples)
     finally:
         config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS = saved
+
+
+def test_stepwise_selfplay_with_external_evaluator_matches_persistent_kernel():
+    """SelfPlayEngine.step() (stepwise kernels + an evaluator callable + gmz_selfplay_step) must play
+    the same games, move for move, as the persistent kernel when the evaluator is E0 and the noise is the
+    same counter-based stream."""
+    import torch
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+    from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
+    N, S, G, seed, nseed = 6, 30, 16, 8, 21
+    A = N * N
+    # reference run: persistent kernel
+    e1 = SearchEngine(G, board_size=N, num_simulations=S)
+    sp1 = SelfPlayEngine(e1, "e0", seed=seed, noise_seed=nseed)
+    t1 = TrajectoryStore(e1, extra_slots=64)
+    fin1 = []
+    for _ in range(5):
+        sp1.play(moves_per_game=8, traj=t1); fin1 += t1.harvest()
+    # stepwise run: evaluator = the stand-alone E0 kernel, noise = same per-game counters
+    e2 = SearchEngine(G, board_size=N, num_simulations=S)
+
+    def evaluator(obs):
+        return e2.e0_eval(obs, seed)
+    sp2 = SelfPlayEngine(e2, evaluator, noise_seed=nseed)
+    t2 = TrajectoryStore(e2, extra_slots=64)
+    counters = np.zeros(G, np.int64)          # searches done per game (the play kernel's noise_ctr)
+    fin2 = []
+    gum = torch.empty((G, A), dtype=torch.float64, device="cuda")
+    for _ in range(40):
+        for g in range(G):
+            e2.fill_gumbel(gum[g], nseed, int((counters[g] * G + g) * A))
+        pol, val, act, _ = sp2.search(gumbel=gum)
+        e2.selfplay_step(pol, val, act, t2, True)
+        counters += 1
+        fin2 += t2.harvest()
+    first1, first2 = {}, {}
+    for r in fin1: first1.setdefault(r["game"], r)
+    for r in fin2: first2.setdefault(r["game"], r)
+    common = sorted(set(first1) & set(first2))
+    assert len(common) >= 8
+    for g in common:
+        a, b = first1[g], first2[g]
+        assert a["length"] == b["length"] and np.array_equal(a["actions"], b["actions"]) and a["winner"] == b["winner"], g
+        assert np.array_equal(a["values"], b["values"]) and np.array_equal(a["policies"], b["policies"]), g
