@@ -112,9 +112,39 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "moves_per_sec": games * args.steps / dt,
         "config": {"workload": "AlphaZero-mode 15x15 Gomoku, 400 sims, E0 fixed evaluator, CPU oracle port", "games": games},
-        "cpu_baseline": {"value": sims, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": sims, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample,
+                         "cpu_model": cpu_model()},
         "e2e": {"value": sims, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def config1_leg():
+    """BASELINE configs[0]: 9x9, N_IN_ROW=5, 100 simulations, ONE self-play worker (single host thread of
+    the CPU port) -- the reference's own CPU-runnable case, timed for context."""
+    from oracle import oracle
+    n, s = 9, 100
+    cfg = oracle.make_config(board_size=n, n_in_row=5, num_simulations=s, num_top_actions=K_TOP, eval_seed=E0_SEED)
+    rs = np.random.RandomState(3)
+    boards = np.zeros((64, n * n), np.int8)
+    pl, lm, mc = np.ones(64, np.int8), np.full(64, -1, np.int32), np.zeros(64, np.int32)
+    oracle.search_batch(cfg, boards, pl, lm, mc, rs.gumbel(0, 1, (64, n * n)), n_threads=1, want_visits=False)
+    t0, k = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 2.0:
+        oracle.search_batch(cfg, boards, pl, lm, mc, rs.gumbel(0, 1, (64, n * n)), n_threads=1, want_visits=False)
+        k += 1
+    dt = time.perf_counter() - t0
+    return {"workload": "9x9, 100 sims, one worker (CPU port, 1 thread, E0)", "sims_per_sec": 64 * k * s / dt,
+            "moves_per_sec": 64 * k / dt}
 
 
 def cpu_baseline_leg(budget_s=10.0):
@@ -131,8 +161,9 @@ def cpu_baseline_leg(budget_s=10.0):
         oracle.search_batch(cfg, boards, players, last, mc, rs.gumbel(0, 1, (games, A)), n_threads=threads, want_visits=False)
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": games * S * n / dt, "unit": "sims/s", "cores": threads, "kind": "port",
-            "sample": f"{n} batches x {games} searches of 15x15/400 sims (E0) on {threads} threads, {dt:.1f} s"}
+    return {"value": games * S * n / dt, "unit": "sims/s", "cores": threads, "kind": "port", "cpu_model": cpu_model(),
+            "sample": f"{n} batches x {games} searches of 15x15/400 sims (E0) on {threads} threads, {dt:.1f} s",
+            "config1": config1_leg()}
 
 
 def net_leg(eng, dev, peaks):

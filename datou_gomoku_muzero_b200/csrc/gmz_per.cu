@@ -71,10 +71,19 @@ k_per_update(double *tree, const long long *tree_idx, const double *prio, int n)
         const int leader = __ffs(grp) - 1;
         double acc = 0.0;
         if (act && lane == leader) acc = __ldcg(tree + key);
-        for (int b = 0; b < 32; ++b) {
-            const long long kb = __shfl_sync(GMZ_FULL, key, b);
-            const double cb = __shfl_sync(GMZ_FULL, ch, b);
-            if (act && lane == leader && kb == key) acc = __dadd_rn(acc, cb);   // self.tree[parent] += change
+        if (__all_sync(GMZ_FULL, grp == (1u << lane))) {
+            // every lane hits a different node (the common case away from the root): one += each
+            if (act) acc = __dadd_rn(acc, ch);
+        } else {
+            // walk only the lanes that share a node with someone, in lane (= batch) order
+            unsigned shared = __ballot_sync(GMZ_FULL, act && grp != (1u << lane));
+            if (act && grp == (1u << lane)) acc = __dadd_rn(acc, ch);
+            while (shared) {
+                const int b = __ffs(shared) - 1; shared &= shared - 1;
+                const long long kb = __shfl_sync(GMZ_FULL, key, b);
+                const double cb = __shfl_sync(GMZ_FULL, ch, b);
+                if (act && lane == leader && kb == key) acc = __dadd_rn(acc, cb);   // self.tree[parent] += change
+            }
         }
         if (act && lane == leader) __stcg(tree + key, acc);
         __syncwarp();
@@ -140,6 +149,22 @@ extern "C" int gmz_per_update(double *tree, int64_t capacity, const int64_t *tre
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return per_fail(cudaGetErrorString(e));
     return 0;
+}
+
+// SumTree.add for a batch (replay_buffer.py:21-25): leaf i goes to ring position (write_ptr + i) % capacity.
+__global__ void k_per_add_idx(long long *idx, long long capacity, long long write_ptr, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) idx[i] = (write_ptr + i) % capacity + capacity - 1;
+}
+extern "C" int gmz_per_add(double *tree, int64_t capacity, int64_t write_ptr, const double *priorities, int n,
+                           int64_t *scratch_idx, gmz_stream stream)
+{
+    if (!tree || !priorities || !scratch_idx) return per_fail("gmz_per_add: null argument");
+    if (n <= 0) return 0;
+    if (capacity < 1 || write_ptr < 0 || write_ptr >= capacity) return per_fail("gmz_per_add: bad capacity / write_ptr");
+    k_per_add_idx<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((long long *)scratch_idx, capacity, write_ptr, n);
+    return gmz_per_update(tree, capacity, scratch_idx, priorities, n, stream);
 }
 
 extern "C" int gmz_per_sample(const double *tree, int64_t capacity, int64_t count, const double *u01, int batch, double beta,

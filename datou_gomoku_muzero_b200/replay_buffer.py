@@ -45,8 +45,10 @@ class SumTree:
 
     def add_many(self, priorities):
         n = len(priorities)
-        idx = (self.write_ptr + np.arange(n)) % self.capacity + self.capacity - 1
-        self.update_many(idx, priorities)
+        pr = torch.as_tensor(np.ascontiguousarray(priorities, dtype=np.float64)).to(self.device)
+        scratch = torch.empty(n, dtype=torch.int64, device=self.device)
+        check(self.lib.gmz_per_add(_ptr(self.tree), self.capacity, self.write_ptr, _ptr(pr), n, _ptr(scratch),
+                                   self._stream()), "gmz_per_add")
         self.write_ptr = (self.write_ptr + n) % self.capacity
         self.count = min(self.capacity, self.count + n)
 

@@ -201,6 +201,11 @@ int gmz_tactics_classify(const int8_t *boards, const int8_t *players, int batch,
 /* update_priorities / add: tree_idx int64 [n], priorities f64 [n], applied in order. */
 int gmz_per_update(double *tree, int64_t capacity, const int64_t *tree_idx, const double *priorities, int n,
                    gmz_stream stream);
+/* add(): n priorities written at ring positions write_ptr, write_ptr+1, ... (mod capacity), applied in
+ * order (replay_buffer.py:21-25); scratch_idx int64 [n] is caller-owned scratch.  The caller advances
+ * write_ptr / count like SumTree.add does. */
+int gmz_per_add(double *tree, int64_t capacity, int64_t write_ptr, const double *priorities, int n,
+                int64_t *scratch_idx, gmz_stream stream);
 /* sample(): u01 f64 [B] uniform draws; outputs tree_idx int64 [B], priority f64 [B],
  * is_weights f32 [B] (already divided by the batch max). */
 int gmz_per_sample(const double *tree, int64_t capacity, int64_t count, const double *u01, int batch, double beta,
