@@ -69,6 +69,7 @@ struct Params {
     int *nN;         // [G*S]      node.visit_count
     double *nW;      // [G*S]      node.value_sum
     double *nR;      // [G*S]      node.reward (MuZero mode only)
+    u64 *nH;         // [G*S]      E0 hidden state of a node (MuZero mode + fixed evaluator only)
     short *path;     // [G][S+2]   node ids root..leaf-parent of the pending simulation
     short *pyset;    // [ceil(G/4)*4][4096] scratch for the CPython-set tie-break (rare path)
     char *sel_overflow;   // [ceil(G/4)*4][128*NC*20 B] select scratch for nodes with > 64 visited children
@@ -182,4 +183,6 @@ __device__ __forceinline__ float e0_logit(u64 h, int a, float logit_div, float i
     const int k = (int)(mix64(h + (u64)(a + 1) * E0_GOLD) >> 58);
     return inv_div != 0.0f ? __fmul_rn((float)(k - 32), inv_div) : __fdiv_rn((float)(k - 32), logit_div);
 }
+__device__ __forceinline__ u64 e0_child_hidden(u64 h_parent, int action) { return mix64(h_parent ^ mix64((u64)(action + 1) + E0_CA)); }
+__device__ __forceinline__ double e0_reward(u64 h) { return (double)((int)((mix64(h ^ E0_CR) >> 40) % 5) - 2) / 16.0; }
 __device__ __forceinline__ double e0_value(u64 h) { return (double)((int)((mix64(h ^ E0_CV) >> 40) % 33) - 16) / 16.0; }

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_game_step(Params p, const int32
 static float pow2_inv(int d) { return (d > 0 && (d & (d - 1)) == 0) ? 1.0f / (float)d : 0.0f; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct Layout { size_t gs, logits, child, nN, nW, nR, path, pyset, selov, ctl, total; };
+struct Layout { size_t gs, logits, child, nN, nW, nR, nH, path, pyset, selov, ctl, total; };
 
 static int validate(const gmz_config *c)
 {
@@ -398,6 +398,7 @@ static Layout make_layout(const gmz_config *c)
     L.nN = o; o = align_up(o + G * S * sizeof(int), 256);
     L.nW = o; o = align_up(o + G * S * sizeof(double), 256);
     L.nR = o; if (c->mode == GMZ_MODE_MUZERO) o = align_up(o + G * S * sizeof(double), 256);
+    L.nH = o; if (c->mode == GMZ_MODE_MUZERO) o = align_up(o + G * S * sizeof(u64), 256);
     L.path = o; o = align_up(o + G * (S + 2) * sizeof(short), 256);
     L.pyset = o; o = align_up(o + ((G + 3) / 4 * 4) * 4096 * sizeof(short), 256);
     L.selov = o; o = align_up(o + ((G + 3) / 4 * 4) * AP * 20, 256);
@@ -448,6 +449,7 @@ extern "C" int gmz_create(const gmz_config *cfg, void *workspace, size_t workspa
     p.gs = (GState *)(base + L.gs); p.logits = (float *)(base + L.logits); p.child = (short *)(base + L.child);
     p.nN = (int *)(base + L.nN); p.nW = (double *)(base + L.nW);
     p.nR = cfg->mode == GMZ_MODE_MUZERO ? (double *)(base + L.nR) : nullptr;
+    p.nH = cfg->mode == GMZ_MODE_MUZERO ? (u64 *)(base + L.nH) : nullptr;
     p.path = (short *)(base + L.path);
     p.pyset = (short *)(base + L.pyset); p.sel_overflow = base + L.selov; p.ctl = (PlayCtl *)(base + L.ctl);
     cudaError_t err = cudaMemsetAsync(base + L.gs, 0, (size_t)p.G * sizeof(GState), (cudaStream_t)stream);
@@ -554,22 +556,27 @@ extern "C" int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint
     return check_launch("k_e0_eval_obs");
 }
 // launch the ticketed play kernel: grid = what fits on the GPU at once (persistent), capped by the game count
-template <int NC>
-static int launch_play(gmz_engine *e, const PlayArgs &a, cudaStream_t st)
+template <int NC, bool MZ>
+static int launch_play_t(gmz_engine *e, const PlayArgs &a, cudaStream_t st)
 {
     static int occ_cache[4] = {0, 0, 0, 0};
     if (!occ_cache[NC]) {
         int occ = 0, dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_play_e0<NC>, 32 * GMZ_PLAY_WARPS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_play_e0<NC, MZ>, 32 * GMZ_PLAY_WARPS, 0);
         occ_cache[NC] = (occ > 0 ? occ : 1) * (sms > 0 ? sms : 148);
     }
     int grid = (e->p.G + GMZ_PLAY_WARPS - 1) / GMZ_PLAY_WARPS;
     if (grid > occ_cache[NC]) grid = occ_cache[NC];
     if (cudaMemsetAsync(&e->p.ctl->next_ticket, 0, 2 * sizeof(unsigned long long), st) != cudaSuccess) return fail("cudaMemsetAsync(ctl)");
-    k_play_e0<NC><<<grid, 32 * GMZ_PLAY_WARPS, 0, st>>>(e->p, a);
+    k_play_e0<NC, MZ><<<grid, 32 * GMZ_PLAY_WARPS, 0, st>>>(e->p, a);
     return check_launch("k_play_e0");
+}
+template <int NC>
+static int launch_play(gmz_engine *e, const PlayArgs &a, cudaStream_t st)
+{
+    return e->p.mode == GMZ_MODE_MUZERO ? launch_play_t<NC, true>(e, a, st) : launch_play_t<NC, false>(e, a, st);
 }
 static TrajDev traj_dev(const gmz_traj *t)
 {
@@ -595,7 +602,6 @@ extern "C" int gmz_search_e0(gmz_engine *e, const double *gumbel, uint64_t seed,
                              int32_t *trace_leaf_action, int32_t *trace_leaf_depth, gmz_stream stream)
 {
     if (!e || !gumbel) return fail("gmz_search_e0: null argument");
-    if (e->p.mode != GMZ_MODE_ALPHAZERO) return fail("gmz_search_e0: AlphaZero mode only");
     PlayArgs a; memset(&a, 0, sizeof(a));
     a.eval_seed = seed; a.logit_div = (float)logit_div; a.inv_div = pow2_inv(logit_div);
     a.total_tickets = e->p.G; a.do_step = 0; a.gumbel_in = gumbel;
@@ -616,7 +622,6 @@ extern "C" int gmz_selfplay_e0(gmz_engine *e, const gmz_traj *traj, uint64_t eva
                                int64_t total_moves, int restart, gmz_stream stream)
 {
     if (!e) return fail("gmz_selfplay_e0: null engine");
-    if (e->p.mode != GMZ_MODE_ALPHAZERO) return fail("gmz_selfplay_e0: AlphaZero mode only");
     if (traj && check_traj(e, traj)) return 1;
     if (total_moves <= 0) return 0;
     PlayArgs a; memset(&a, 0, sizeof(a));

@@ -224,7 +224,7 @@ struct PlayArgs;
 // noise, expand + top-k (mcts.py:203-226).  Out of line: it runs once per 400 simulations, and
 // keeping its registers out of the simulation loop's allocation is worth more than the call.
 template <int NC>
-__device__ __noinline__ void play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane);
+__device__ __noinline__ u64 play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane);
 
 #ifndef GMZ_PLAY_MIN_CTAS
 #define GMZ_PLAY_MIN_CTAS 6
@@ -232,7 +232,7 @@ __device__ __noinline__ void play_root(const Params &p, const PlayArgs &a, WG &w
 #define GMZ_PLAY_WARPS 4
 
 template <int NC>
-__device__ __noinline__ void play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane)
+__device__ __noinline__ u64 play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane)
 {
     const int g = w.g;
     const u64 h = e0_hash_planes(a.eval_seed, w.to_move > 0 ? w.P : w.M, w.to_move > 0 ? w.M : w.P, p.NW, w.last_move);
@@ -245,11 +245,12 @@ __device__ __noinline__ void play_root(const Params &p, const PlayArgs &a, WG &w
         gum[i] = ac < p.A ? (a.gumbel_in ? a.gumbel_in[(size_t)g * p.A + ac] : gumbel_at(noise_mixed, nctr + ac)) : 0.0;
     }
     root_init<NC>(p, w, lg, gum, e0_value(h), lane);
+    return h;
 }
 
 // One search (mcts.py:197-280) -- and in self-play mode one whole move (workers.py:168-189) --
 // per ticket, one game per warp, E0 inlined.
-template <int NC>
+template <int NC, bool MZ>
 __global__ void __launch_bounds__(32 * GMZ_PLAY_WARPS, GMZ_PLAY_MIN_CTAS)
 k_play_e0(Params p, PlayArgs a)
 {
@@ -307,14 +308,19 @@ k_play_e0(Params p, PlayArgs a)
         double value = 0.0; int action = -1;
         if (w.active) {
             wg_valid_bits<NC>(p, w, lane);
-            play_root<NC>(p, a, w, s->noise_ctr, noise_mixed, lane);
+            const u64 h_root = play_root<NC>(p, a, w, s->noise_ctr, noise_mixed, lane);
+            if (MZ && lane == 0) p.nH[w.nbase] = h_root;         // root hidden state = hash of the root observation
             __syncwarp();
             int ev = 0;
             while (w.sim_count < p.S) {
                 u64 P = w.P, M = w.M; int colour = w.to_move;
                 int lp, la;
-                const int depth = descend<NC, false>(p, w, path, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
-                const u64 h = e0_hash_planes(a.eval_seed, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la);
+                const int depth = descend<NC, MZ>(p, w, path, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
+                // AlphaZero mode: evaluate the replayed board (mcts.py:251-253).  MuZero mode: the learned
+                // dynamics, here E0's recurrent half on the parent's hidden state (mcts.py:336-343).
+                const u64 h = MZ ? e0_child_hidden(p.nH[w.nbase + (size_t)lp], la)
+                                 : e0_hash_planes(a.eval_seed, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la);
+                const int reps = MZ ? w.n_surv : 1;            // MuZero: len(selected) identical selections -> that many backups
                 const int nn = w.num_nodes;
                 {   // evaluate + leaf.expand fused: logits go straight into the new node's row
                     float *lrow = p.logits + (w.nbase + (size_t)nn) * (size_t)p.AP;
@@ -330,16 +336,17 @@ k_play_e0(Params p, PlayArgs a)
                 }
                 if (lane == 0) {
                     p.child[(w.nbase + (size_t)lp) * (size_t)p.AP + la] = (short)nn;
+                    if (MZ) p.nH[w.nbase + (size_t)nn] = h;
                     if (a.trace_a) a.trace_a[(size_t)g * p.S + ev] = la;
                     if (a.trace_d) a.trace_d[(size_t)g * p.S + ev] = depth;
                 }
                 w.num_nodes = nn + 1; ++ev;
                 __syncwarp();
-                backup<false>(p, w, path, depth, nn, e0_value(h), 0.0, 1, lane);
-                survivor_visit(w, depth, path, nn, la, 1, lane);
-                w.sim_count += 1;
+                backup<MZ>(p, w, path, depth, nn, e0_value(h), MZ ? e0_reward(h) : 0.0, reps, lane);
+                survivor_visit(w, depth, path, nn, la, reps, lane);
+                w.sim_count += reps;
                 __syncwarp();
-                if (halving_ready(p, w)) sequential_halving<false>(p, w, lane);
+                if (halving_ready(p, w)) sequential_halving<MZ>(p, w, lane);
             }
             wg_store_search(p, lane, w);
             __syncwarp();
@@ -366,7 +373,7 @@ k_play_e0(Params p, PlayArgs a)
             if (a.out_policy) pol = a.out_policy + (size_t)g * p.A;
             if (a.out_visits) vis = a.out_visits + (size_t)g * p.A;
         }
-        finalize_root<NC, false>(p, w, lane, pol, vis, s_nvis[wi], table, value, action);
+        finalize_root<NC, MZ>(p, w, lane, pol, vis, s_nvis[wi], table, value, action);
         if (!a.do_step) {
             if (lane == 0) { if (a.out_value) a.out_value[g] = value; if (a.out_action) a.out_action[g] = action; }
         } else if (action < 0) {

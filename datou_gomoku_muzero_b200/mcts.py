@@ -141,8 +141,6 @@ class _GumbelEngineMCTS(MCTS):
             b["d_" + k].copy_(b["h_" + k], non_blocking=True)
         eng.set_roots(b["d_boards"], b["d_players"], b["d_last"], b["d_mc"])
         if b["evaluator"] == "e0":
-            if self.MODE != "AlphaZero":
-                raise NotImplementedError("the fused E0 search is AlphaZero-mode")
             eng.search_e0(b["d_gumbel"], b["eval_seed"], b["logit_div"])
         else:
             ev = b["evaluator"]

@@ -122,7 +122,9 @@ int gmz_finalize(gmz_engine *e, double *policy, double *value, int32_t *action, 
 int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint64_t seed, int logit_div,
                     float *logits, double *values, gmz_stream stream);
 /* Whole search (root evaluation + S-1 simulations) in ONE persistent kernel
- * with E0 inlined: the tree-only fast path.  gumbel f64 [G,A]; optional int32
+ * with E0 inlined: the tree-only fast path.  In a MuZero-mode engine the in-tree
+ * evaluator is E0's recurrent half (hidden state = 64-bit hash per node, reward
+ * from the hash) and every evaluation receives len(selected) backups.  gumbel f64 [G,A]; optional int32
  * [G,S] traces (leaf action / depth per evaluation).  Follow with gmz_finalize. */
 int gmz_search_e0(gmz_engine *e, const double *gumbel, uint64_t seed, int logit_div,
                   int32_t *trace_leaf_action, int32_t *trace_leaf_depth, gmz_stream stream);

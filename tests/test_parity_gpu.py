@@ -255,3 +255,33 @@ def test_folded_recurrent_inference_matches_module():
     torch.testing.assert_close(lv, v2.reshape(-1), rtol=1e-3, atol=2e-3)
     torch.testing.assert_close(lr, r2.reshape(-1), rtol=1e-3, atol=2e-3)
     torch.testing.assert_close(lh, h2, rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("N,S,G", [(9, 100, 64), (15, 400, 64), (6, 50, 48)])
+def test_muzero_fused_search_matches_oracle(N, S, G):
+    """MuZero mode inside the persistent kernel (E0's recurrent evaluator inlined) vs the oracle."""
+    import torch
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from oracle import oracle
+    A, seed = N * N, 17
+    rs = np.random.RandomState(3 * N + S)
+    boards = np.zeros((G, A), np.int8); players = np.ones(G, np.int8)
+    last = np.full(G, -1, np.int32); mc = np.zeros(G, np.int32)
+    for g in range(G):
+        k = int(rs.randint(0, A - 1)) if g % 4 else A - 1 - (g % 5)
+        p = 1
+        for a in rs.permutation(A)[:k]:
+            boards[g, a] = p; last[g] = a; p = -p
+        players[g] = p; mc[g] = k
+    gumbel = rs.gumbel(0, 1, (G, A))
+    eng = SearchEngine(G, board_size=N, num_simulations=S, mode="MuZero")
+    eng.set_roots(boards, players, last, mc)
+    ta, td = eng.search_e0(torch.from_numpy(gumbel).cuda(), seed, trace=True)
+    pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
+    cfg = oracle.make_config(board_size=N, num_simulations=S, mode=1, eval_seed=seed)
+    opol, oval, oact, ovis = oracle.search_batch(cfg, boards, players, last, mc, gumbel)
+    assert np.array_equal(vis, ovis) and np.array_equal(act, oact) and np.array_equal(val, oval)
+    np.testing.assert_allclose(pol, opol, rtol=RTOL, atol=1e-12)
+    r = oracle.search(cfg, boards[1], players[1], last[1], mc[1], gumbel[1], trace=True)
+    n = r["n_evals"]
+    assert np.array_equal(ta[1].cpu().numpy()[:n], r["leaf_actions"]) and np.array_equal(td[1].cpu().numpy()[:n], r["leaf_depths"])

@@ -19,14 +19,14 @@ def _noise_for_game(eng, g, n_moves, noise_seed):
     return out.cpu().numpy()
 
 
-@pytest.mark.parametrize("N,S,G", [(6, 36, 24), (9, 64, 40)])
-def test_selfplay_games_match_oracle(N, S, G):
+@pytest.mark.parametrize("N,S,G,mode", [(6, 36, 24, "AlphaZero"), (9, 64, 40, "AlphaZero"), (6, 50, 24, "MuZero")])
+def test_selfplay_games_match_oracle(N, S, G, mode):
     from datou_gomoku_muzero_b200.engine import SearchEngine
     from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
     from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
     from oracle import oracle
     A, seed, nseed = N * N, 5, 77
-    eng = SearchEngine(G, board_size=N, num_simulations=S)
+    eng = SearchEngine(G, board_size=N, num_simulations=S, mode=mode)
     sp = SelfPlayEngine(eng, "e0", seed=seed, noise_seed=nseed)
     traj = TrajectoryStore(eng, extra_slots=8)
     finished = []
@@ -36,7 +36,7 @@ def test_selfplay_games_match_oracle(N, S, G):
     moves, nfin = eng.play_counters()
     assert nfin == len(finished) and nfin >= G          # every game ended at least once
     assert moves <= 6 * G * (A // 3) and eng.tickets_idle == 0      # games may park when the 8 spare slots run out
-    cfg = oracle.make_config(board_size=N, num_simulations=S, eval_seed=seed)
+    cfg = oracle.make_config(board_size=N, num_simulations=S, eval_seed=seed, mode=0 if mode == "AlphaZero" else 1)
     first = {}
     for r in finished:                                  # the first game of each index starts at noise counter 0
         first.setdefault(r["game"], r)

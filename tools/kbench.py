@@ -14,10 +14,11 @@ ap.add_argument("--games", type=int, default=4096)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--check", type=int, default=64)
 ap.add_argument("--stepwise", action="store_true")
+ap.add_argument("--mode", default="AlphaZero", choices=["AlphaZero", "MuZero"])
 ap.add_argument("--selfplay", type=int, default=0, help="time the persistent self-play kernel for this many moves per game")
 args = ap.parse_args()
 G = args.games
-eng = SearchEngine(G, board_size=N, num_simulations=S, num_top_actions=K_TOP)
+eng = SearchEngine(G, board_size=N, num_simulations=S, num_top_actions=K_TOP, mode=args.mode)
 roots = staggered_positions(G, 0)
 eng.set_roots(*roots)
 gum = torch.empty((G, A), dtype=torch.float64, device="cuda")
@@ -51,7 +52,8 @@ if args.check:
     from oracle import oracle
     pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
     c = args.check
-    cfg = oracle.make_config(board_size=N, num_simulations=S, num_top_actions=K_TOP, eval_seed=E0_SEED, logit_div=LOGIT_DIV)
+    cfg = oracle.make_config(board_size=N, num_simulations=S, num_top_actions=K_TOP, eval_seed=E0_SEED, logit_div=LOGIT_DIV,
+                             mode=0 if args.mode == "AlphaZero" else 1)
     g = gum.cpu().numpy()
     opol, oval, oact, ovis = oracle.search_batch(cfg, roots[0][:c], roots[1][:c], roots[2][:c], roots[3][:c], g[:c])
     ok = np.array_equal(vis[:c], ovis) and np.array_equal(act[:c], oact)
