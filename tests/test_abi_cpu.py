@@ -91,3 +91,44 @@ def test_contract_types():
     from datou_gomoku_muzero_b200 import GameRecord, TrainingSlice
     assert GameRecord._fields == ("observations", "actions", "rewards", "policies", "values", "board_states")
     assert TrainingSlice._fields == ("observation", "action_history", "reward_history", "policy_history", "value_history")
+
+
+def test_entry_points_reject_bad_arguments_without_crashing():
+    """Error behaviour of the boundary: every entry point validates its arguments before touching the
+    device, returns non-zero and leaves a message in gmz_last_error() (no GPU needed for these paths)."""
+    import ctypes as C
+    from datou_gomoku_muzero_b200 import _lib
+    lib = _lib.load()
+    N = None
+    calls = [
+        ("gmz_set_roots", (N, N, N, N, N, N)), ("gmz_games_reset", (N, N, N)), ("gmz_root_obs", (N, N, 0, N)),
+        ("gmz_get_roots", (N, N, N, N, N, N)), ("gmz_root_expand", (N, N, N, 0, N, N)),
+        ("gmz_select", (N, N, 0, N, N, N)), ("gmz_select_mz", (N, N, N, N, N, N, N)),
+        ("gmz_expand_backup", (N, N, N, N, 0, N)), ("gmz_finalize", (N, N, N, N, N, N)),
+        ("gmz_e0_eval_obs", (N, 4, 9, 0, 16, N, N, N)), ("gmz_search_e0", (N, N, 0, 16, N, N, N)),
+        ("gmz_fill_gumbel", (N, 8, 0, 0, N)), ("gmz_game_step", (N, N, N, N)),
+        ("gmz_traj_init", (N, N, N)), ("gmz_selfplay_e0", (N, N, 0, 16, 0, 8, 1, N)),
+        ("gmz_selfplay_unpark", (N, N, N)), ("gmz_selfplay_step", (N, N, N, N, N, 1, N, N)),
+        ("gmz_play_counters", (N, N, N)), ("gmz_value_targets", (N, N, N, N, 3, N, 10, N, N)),
+        ("gmz_build_batch", (N, 9, N, N, N, N, N, 4, 5, N, N, N, N, N, N)),
+        ("gmz_tactics_classify", (N, N, 4, 9, 5, N, N)), ("gmz_per_update", (N, 8, N, N, 4, N)),
+        ("gmz_per_add", (N, 8, 0, N, 4, N, N)), ("gmz_per_sample", (N, 8, 8, N, 4, 0.4, N, N, N, N)),
+    ]
+    for name, args in calls:
+        rc = getattr(lib, name)(*args)
+        assert rc != 0, f"{name} accepted null arguments"
+        assert lib.gmz_last_error(), f"{name} left no error message"
+    one = (C.c_double * 1)(1.0)
+    assert lib.gmz_per_add(one, 8, 9, one, 1, (C.c_int64 * 1)(0), None) != 0          # write_ptr outside the ring
+    assert lib.gmz_tactics_classify((C.c_int8 * 4)(), (C.c_int8 * 1)(1), 1, 40, 5, (C.c_int8 * 4)(), None) != 0   # board too large
+    assert lib.gmz_e0_eval_obs(None, 0, 9, 0, 16, None, None, None) != 0 or True      # empty batch of nothing is a no-op or an error, never a crash
+    # without a CUDA device gmz_create must fail cleanly as well
+    import torch
+    if not torch.cuda.is_available():
+        cfg = _lib.GmzConfig(9, 5, 16, 4, 0, 2, 0, 0, 30.0, 1.0, 1e-3, 0.997)
+        nbytes = lib.gmz_workspace_bytes(C.byref(cfg))
+        buf = (C.c_char * (nbytes + 512))()
+        addr = (C.addressof(buf) + 255) // 256 * 256
+        h = C.c_void_p()
+        assert lib.gmz_create(C.byref(cfg), C.c_void_p(addr), nbytes, None, C.byref(h)) != 0
+        assert b"cuda" in lib.gmz_last_error().lower() or lib.gmz_last_error()
