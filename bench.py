@@ -92,7 +92,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle
-    threads = oracle.max_threads()
+    threads = host_threads()
     games = args.cpu_games or threads * 8
     cfg = oracle.make_config(board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP,
                              eval_seed=E0_SEED, logit_div=LOGIT_DIV)
@@ -116,6 +116,15 @@ def run_reference(args):
                          "cpu_model": cpu_model()},
         "e2e": {"value": sims, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def host_threads():
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm ignores that:
+    only rank 0 runs it, so it gets the whole box)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 def cpu_model():
@@ -149,7 +158,7 @@ def config1_leg():
 
 def cpu_baseline_leg(budget_s=10.0):
     from oracle import oracle
-    threads = oracle.max_threads()
+    threads = host_threads()
     games = threads * 8
     cfg = oracle.make_config(board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP,
                              eval_seed=E0_SEED, logit_div=LOGIT_DIV)
