@@ -353,12 +353,12 @@ def run_ours(args):
                      "note": "one simulation in flight per game (bit-exact visit counts) => latency/occupancy bound, not HBM bound"},
         "clocks": sampler.summary(),
     }
-    if not args.no_net:
+    if not args.no_net and world == 1:          # single-GPU context measurement
         try:
             out["net"] = net_leg(eng, dev, peaks)
         except Exception as ex:      # the headline (fixed evaluator) stands on its own
             out["net"] = {"error": repr(ex)[:200]}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         out["cpu_baseline"] = cpu_baseline_leg(args.cpu_seconds)
     print(json.dumps(out))
     if world > 1:
