@@ -60,6 +60,8 @@ SIGNATURES = {
     "gmz_play_counters": (C.c_int, [_P, _P, _P]),
     "gmz_value_targets": (C.c_int, [C.POINTER(GmzTraj), _P, _P, _P, C.c_int, _P, C.c_int, _P, _P]),
     "gmz_build_batch": (C.c_int, [C.POINTER(GmzTraj), C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
+    "gmz_build_batch_aug": (C.c_int, [C.POINTER(GmzTraj), C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      _P, _P, _P, _P, _P, _P]),
     "gmz_tactics_classify": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "gmz_per_update": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, _P]),
     "gmz_per_add": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, _P, _P]),

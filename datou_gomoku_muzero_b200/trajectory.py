@@ -127,9 +127,12 @@ class DeviceSliceStore:
             self.traj.release([old])
         return new
 
-    def batch(self, samples):
+    def batch(self, samples, rot_k=0, flip=False):
         """samples: sequence of (slot, t).  Returns device tensors (obs f32 [B,U+1,3,N,N], act i32 [B,U],
-        rew f32 [B,U], pi f64 [B,U+1,A], val f32 [B,U+1])."""
+        rew f32 [B,U], pi f64 [B,U+1,A], val f32 [B,U+1]).  rot_k / flip = the k and flip that
+        calculate_loss draws (loss.py:37-38); the D4 augmentation of loss.py:39-51 is then applied by the
+        gather itself (act comes back augmented; padded entries stay -1, so the reference's `act != -1` mask,
+        loss.py:85, can be taken from the returned tensor)."""
         e = self.e
         B, U, N, A = len(samples), int(config.NUM_UNROLL_STEPS), e.N, e.A
         st = torch.tensor(samples, dtype=torch.int32, device=e.device).reshape(B, 2)
@@ -139,10 +142,11 @@ class DeviceSliceStore:
         rew = torch.empty((B, U), dtype=torch.float32, device=e.device)
         pi = torch.empty((B, U + 1, A), dtype=torch.float64, device=e.device)
         val = torch.empty((B, U + 1), dtype=torch.float32, device=e.device)
-        check(e.lib.gmz_build_batch(C.byref(self.traj.c), N, self.targets.data_ptr(), self.length.data_ptr(),
-                                    self.winner.data_ptr(), s_slot.data_ptr(), s_t.data_ptr(), B, U, obs.data_ptr(),
-                                    act.data_ptr(), rew.data_ptr(), pi.data_ptr(), val.data_ptr(), e._stream()),
-              "gmz_build_batch")
+        check(e.lib.gmz_build_batch_aug(C.byref(self.traj.c), N, self.targets.data_ptr(), self.length.data_ptr(),
+                                        self.winner.data_ptr(), s_slot.data_ptr(), s_t.data_ptr(), B, U, int(rot_k) % 4,
+                                        1 if flip else 0, obs.data_ptr(), act.data_ptr(), rew.data_ptr(), pi.data_ptr(),
+                                        val.data_ptr(), e._stream()),
+              "gmz_build_batch_aug")
         e.launches += 1
         return obs, act, rew, pi, val
 

@@ -189,6 +189,14 @@ int gmz_value_targets(const gmz_traj *traj, const int32_t *slots, const int32_t 
 int gmz_build_batch(const gmz_traj *traj, int board_size, const float *targets, const int32_t *len_by_slot,
                     const int32_t *win_by_slot, const int32_t *sample_slot, const int32_t *sample_t, int batch,
                     int unroll, float *obs, int32_t *act, float *rew, double *pi, float *val, gmz_stream stream);
+/* The same batch with the trainer's D4 augmentation (calculate_loss, loss.py:37-51) applied while
+ * gathering: planes and policies rotated rot_k (0..3) quarter turns as torch.rot90 does, then
+ * flipped left-right if `flip`; actions by the reference's own index formula (loss.py:46-51),
+ * padded entries stay -1. */
+int gmz_build_batch_aug(const gmz_traj *traj, int board_size, const float *targets, const int32_t *len_by_slot,
+                        const int32_t *win_by_slot, const int32_t *sample_slot, const int32_t *sample_t, int batch,
+                        int unroll, int rot_k, int flip, float *obs, int32_t *act, float *rew, double *pi, float *val,
+                        gmz_stream stream);
 
 /* ---- tactics classifier (find_winning_moves_rebuilt, workers.py:49-123) ---- */
 /* boards int8 [B,A], players int8 [B] (the side to move) -> out_cls int8 [B,A]: per empty cell

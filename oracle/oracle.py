@@ -185,6 +185,41 @@ def n_step_returns(rewards, values, discount, n_steps):
     return out
 
 
+def augment_batch(obs, act, pi, k, flip):
+    """The D4 augmentation of calculate_loss (loss.py:37-51) as explicit index maps (small numpy loops).
+    obs [B,U+1,3,N,N] and pi [B,U+1,A] move together: rot90 by k quarter turns (cell (r,c) ->
+    (N-1-c, r) per turn, what torch.rot90 over the last two dims does), then a left-right flip.
+    act [B,U] follows the reference's own formula (loss.py:46-51), which for k = 1, 3 is the OPPOSITE
+    quarter turn of the one applied to the planes -- restated as written, including what it does to
+    the -1 padding (floor division / non-negative remainder, as torch's // and % on integers)."""
+    obs, act, pi = np.asarray(obs), np.asarray(act), np.asarray(pi)
+    N = obs.shape[-1]
+    dst = np.empty(N * N, np.int64)
+    for r in range(N):
+        for c in range(N):
+            i, j = r, c
+            for _ in range(int(k) % 4):
+                i, j = N - 1 - j, i
+            if flip:
+                j = N - 1 - j
+            dst[r * N + c] = i * N + j
+    o = np.empty_like(obs).reshape(obs.shape[:-2] + (N * N,))
+    o[..., dst] = obs.reshape(obs.shape[:-2] + (N * N,))
+    p = np.empty_like(pi)
+    p[..., dst] = pi
+    a = act.astype(np.int64)
+    rows, cols = a // N, a % N
+    if k == 1:
+        rows, cols = cols, N - 1 - rows
+    elif k == 2:
+        rows, cols = N - 1 - rows, N - 1 - cols
+    elif k == 3:
+        rows, cols = N - 1 - cols, rows
+    if flip:
+        cols = N - 1 - cols
+    return o.reshape(obs.shape), (rows * N + cols).astype(act.dtype), p
+
+
 class SumTree:
     """replay_buffer.SumTree restated over the C oracle (replay_buffer.py:4-41)."""
 

@@ -4,7 +4,7 @@ Runs only in the build container (the reference does not travel to the GPU box);
 files it writes next to itself are committed and are what tests/ read.  Usage:
 
     python tests/golden/make_golden.py all          # every group (a few minutes)
-    python tests/golden/make_golden.py search_az | search_mz | selfplay | game | per | tactics | network
+    python tests/golden/make_golden.py search_az | search_mz | selfplay | game | per | tactics | network | augment
 
 Nothing here is copied from the reference: the reference is imported and driven through its
 public interface with (a) the E0 evaluator behind its queue protocol and (b) np.random.seed
@@ -358,6 +358,73 @@ def gen_network():
     print(f"[network] {len(net.state_dict())} tensors, {sum(t.numel() for t in net.parameters())} params", flush=True)
 
 
+def gen_augment():
+    """The D4 augmentation block of calculate_loss (loss.py:37-51) run through the reference itself:
+    np.random.randint / choice are pinned to each (k, flip), F.cross_entropy and the model hooks capture
+    what the reference feeds the networks (augmented observations, policies, actions)."""
+    config, game, mcts = _import_reference(6)
+    import torch
+    import loss as ref_loss
+    config.NUM_UNROLL_STEPS, config.N_STEPS = 5, 5
+    config.DEVICE = torch.device("cpu")
+    sp = np.load(os.path.join(HERE, "selfplay_az_6_36.npz"))
+    pick = np.array([0, 3, 7, 18, 29, 31, 33, 35])                      # includes slices padded at the game's end
+    obs_b, act_b = torch.from_numpy(sp["slice_obs"][pick]), torch.from_numpy(sp["slice_act"][pick])
+    rew_b, pi_b, val_b = (torch.from_numpy(sp[k][pick]) for k in ("slice_rew", "slice_pi", "slice_val"))
+    B, U1, A = pi_b.shape
+    out = dict(obs=obs_b.numpy(), act=act_b.numpy(), rew=rew_b.numpy(), pi=pi_b.numpy(), val=val_b.numpy())
+
+    class Capture:
+        def __init__(self):
+            self.obs, self.acts, self.ce = [], [], []
+            self.projection_net = type("P", (), {"fc2": type("F", (), {"out_features": 4})()})()
+        def train(self): pass
+        def eval(self): pass
+        def initial_inference(self, o):
+            self.obs.append(("last", o.clone())); return None, torch.zeros(o.shape[0], 1), None
+        def representation(self, o):
+            self.obs.append(("repr", o.clone())); return torch.zeros(o.shape[0], 2, 6, 6, requires_grad=True)
+        def prediction(self, h):
+            return torch.zeros(h.shape[0], A), torch.zeros(h.shape[0], 3)
+        def dynamics(self, h, a):
+            self.acts.append(a.clone()); return h.clone(), torch.zeros(h.shape[0], 3)
+        def project(self, h, with_grad=True):
+            return torch.zeros(h.shape[0], 4)
+
+    real_ce, real_randint, real_choice = ref_loss.F.cross_entropy, np.random.randint, np.random.choice
+    for k in range(4):
+        for flip in (False, True):
+            cap = Capture()
+            def fake_ce(inp, target, reduction="none", _cap=cap):
+                _cap.ce.append(target.clone()); return torch.zeros(inp.shape[0])
+            ref_loss.F.cross_entropy = fake_ce
+            np.random.randint = lambda n, _k=k: _k
+            np.random.choice = lambda seq, _f=flip: _f
+            try:
+                try:
+                    ref_loss.calculate_loss(cap, cap, (obs_b, act_b, rew_b, pi_b.float(), val_b), torch.ones(B))
+                except Exception as ex:                                  # everything we need is captured before the
+                    print(f"[augment k={k} flip={flip}] stopped after capture: {type(ex).__name__}: {ex}", flush=True)   # loss tail
+            finally:
+                ref_loss.F.cross_entropy, np.random.randint, np.random.choice = real_ce, real_randint, real_choice
+            tag = f"k{k}f{int(flip)}"
+            obs_aug = np.zeros_like(out["obs"]); pi_aug = np.zeros((B, U1, A), np.float32)
+            act_aug = np.full(out["act"].shape, -99, np.int64)
+            assert cap.obs[0][0] == "last" and cap.obs[1][0] == "repr"
+            obs_aug[:, -1] = cap.obs[0][1].numpy(); obs_aug[:, 0] = cap.obs[1][1].numpy()
+            pol = [t for t in cap.ce if t.dim() == 2 and t.shape[1] == A]    # policy targets: step 0, then each unroll step
+            pi_aug[:, 0] = pol[0].numpy()
+            steps = [s for s in range(U1 - 1) if (out["act"][:, s] != -1).any()]
+            reprs = [o for tag_, o in cap.obs[2:] if tag_ == "repr"]
+            assert len(steps) == len(cap.acts) == len(reprs) == len(pol) - 1
+            for s, a, o, pt in zip(steps, cap.acts, reprs, pol[1:]):
+                m = out["act"][:, s] != -1
+                act_aug[m, s] = a.numpy(); obs_aug[m, s + 1] = o.numpy(); pi_aug[m, s + 1] = pt.numpy()
+            out[f"obs_{tag}"], out[f"pi_{tag}"], out[f"act_{tag}"] = obs_aug, pi_aug, act_aug
+    np.savez_compressed(os.path.join(HERE, "augment_kat.npz"), **out)
+    print(f"[augment] B={B} U={U1 - 1} A={A}: 8 symmetries", flush=True)
+
+
 def _sub(*args):
     subprocess.check_call([sys.executable, os.path.abspath(__file__), *map(str, args)])
 
@@ -368,7 +435,7 @@ if __name__ == "__main__":
         for N in (6, 9, 15):
             _sub("search_az", N); _sub("search_mz", N)
         _sub("selfplay", 6, 36, 11, "az"); _sub("selfplay", 9, 100, 12, "az"); _sub("selfplay", 6, 50, 13, "mz")
-        _sub("game"); _sub("per"); _sub("tactics"); _sub("network")
+        _sub("game"); _sub("per"); _sub("tactics"); _sub("network"); _sub("augment")
     elif cmd in ("search_az", "search_mz"):
         gen_search(cmd[-2:], int(sys.argv[2]))
     elif cmd == "selfplay":
@@ -381,5 +448,7 @@ if __name__ == "__main__":
         gen_tactics()
     elif cmd == "network":
         gen_network()
+    elif cmd == "augment":
+        gen_augment()
     else:
         raise SystemExit(f"unknown group {cmd}")

@@ -139,3 +139,21 @@ def test_selfplay_game_matches_reference(name, mode):
     assert np.array_equal(rew.astype(np.float64), z["rewards"])
     vt = O.n_step_returns(rew.astype(np.float64), g["values"], float(z["discount"]), n_steps)
     assert np.array_equal(vt, z["values_targets"].astype(np.float32)), np.abs(vt - z["values_targets"]).max()
+
+
+def test_augmentation_restatement_matches_reference_loss_path():
+    """O.augment_batch vs the tensors the reference's calculate_loss fed its (capturing) networks for
+    every (k, flip) -- loss.py:37-51, golden made by tests/golden/make_golden.py augment."""
+    g = np.load(os.path.join(GOLDEN_DIR, "augment_kat.npz"))
+    valid = g["act"] != -1
+    for k in range(4):
+        for f in (0, 1):
+            o, a, p = O.augment_batch(g["obs"], g["act"], g["pi"], k, bool(f))
+            tag = f"k{k}f{f}"
+            assert np.array_equal(o, g["obs_" + tag]) and np.array_equal(p.astype(np.float32), g["pi_" + tag])
+            assert np.array_equal(a[valid], g["act_" + tag][valid])
+    # the reference's action formula is the inverse quarter turn of its plane rotation for k = 1, 3
+    N = g["obs"].shape[-1]
+    one = np.zeros((1, 1, 3, N, N), np.float32); one[0, 0, 2, 1, 2] = 1.0
+    o, a, _ = O.augment_batch(one, np.array([[1 * N + 2]], np.int32), np.zeros((1, 1, N * N)), 1, False)
+    assert int(np.argmax(o[0, 0, 2])) != int(a[0, 0]) and int(a[0, 0]) == 2 * N + (N - 1 - 1)

@@ -154,6 +154,49 @@ def test_device_slice_store_matches_reference_slices():
         config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS = saved
 
 
+def test_device_batch_d4_augmentation_matches_reference_loss_path():
+    """gmz_build_batch_aug vs what the reference's calculate_loss feeds its networks (loss.py:37-51,
+    captured in tests/golden/augment_kat.npz) for all 8 symmetries, and vs the numpy restatement."""
+    import torch
+    from datou_gomoku_muzero_b200.config import config
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.trajectory import DeviceSliceStore, TrajectoryStore
+    from oracle import oracle
+    z = np.load(os.path.join(GOLDEN_DIR, "selfplay_az_6_36.npz"))
+    g = np.load(os.path.join(GOLDEN_DIR, "augment_kat.npz"))
+    N, nir, S, K, seed, U, n_steps, version = (int(x) for x in z["params"])
+    pick = [0, 3, 7, 18, 29, 31, 33, 35]
+    saved = (config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS)
+    config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS = float(z["discount"]), n_steps, U
+    try:
+        eng = SearchEngine(4, board_size=N, num_simulations=8)
+        traj = TrajectoryStore(eng, extra_slots=8)
+        store = DeviceSliceStore(traj)
+        T, slot = len(z["actions"]), 5
+        traj.policy[slot, :T] = torch.from_numpy(z["policies"]).cuda()
+        traj.value[slot, :T] = torch.from_numpy(z["search_values"]).cuda()
+        traj.action[slot, :T] = torch.from_numpy(z["actions"]).cuda()
+        traj.start_board[slot].zero_()
+        traj.start_info[slot] = torch.tensor([1, 0, -1, 0], dtype=torch.int32).cuda()
+        store.ingest([dict(slot=slot, game=0, length=T, winner=int(z["winner"]))])
+        samples = [(slot, t) for t in pick]
+        base = [x.cpu().numpy() for x in store.batch(samples)]
+        assert np.array_equal(base[0], g["obs"]) and np.array_equal(base[1], g["act"]) and np.array_equal(base[3], g["pi"])
+        valid = g["act"] != -1
+        for k in range(4):
+            for f in (0, 1):
+                obs, act, rew, pi, val = (x.cpu().numpy() for x in store.batch(samples, rot_k=k, flip=bool(f)))
+                tag = f"k{k}f{f}"
+                assert np.array_equal(obs, g["obs_" + tag]), tag
+                assert np.array_equal(pi.astype(np.float32), g["pi_" + tag]), tag
+                assert np.array_equal(act[valid], g["act_" + tag][valid]) and (act[~valid] == -1).all(), tag
+                o_obs, o_act, o_pi = oracle.augment_batch(g["obs"], g["act"], g["pi"], k, bool(f))
+                assert np.array_equal(obs, o_obs) and np.array_equal(pi, o_pi) and np.array_equal(act[valid], o_act[valid])
+                assert np.array_equal(rew, base[2]) and np.array_equal(val, base[4])          # scalars do not move
+    finally:
+        config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS = saved
+
+
 def test_stepwise_selfplay_with_external_evaluator_matches_persistent_kernel():
     """SelfPlayEngine.step() (stepwise kernels + an evaluator callable + gmz_selfplay_step) must play
     the same games, move for move, as the persistent kernel when the evaluator is E0 and the noise is the

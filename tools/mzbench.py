@@ -13,6 +13,7 @@ from datou_gomoku_muzero_b200.network import FoldedInitialInference, GomokuNetEZ
 ap = argparse.ArgumentParser()
 ap.add_argument("--games", type=int, default=4096)
 ap.add_argument("--searches", type=int, default=2)
+ap.add_argument("--profile", default="", help="write a per-kernel GPU-time table (torch profiler) of one search to this file")
 args = ap.parse_args()
 G = args.games
 torch.manual_seed(0); torch.backends.cudnn.benchmark = True
@@ -42,3 +43,11 @@ print(json.dumps({"config": "MuZero-mode 15x15, 400 sims, %d games, GomokuNetEZ 
                   "ms_per_search": ms, "recurrent_evals_per_search": steps, "sims_per_sec": G * S / (ms * 1e-3),
                   "moves_per_sec": G / (ms * 1e-3), "distinct_evals_per_sec": G * (steps + 1) / (ms * 1e-3),
                   "tensor_tflops": tf, "hidden_pool_gb": mz.pool.numel() * mz.pool.element_size() / 1e9}))
+
+if args.profile:
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        mz.search(gum, max_steps=evals); eng.finalize(want_visits=False)
+        torch.cuda.synchronize()
+    with open(args.profile, "w") as f:
+        f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
