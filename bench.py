@@ -215,6 +215,70 @@ def net_leg(eng, dev, peaks):
                        "flop_per_eval": 1.064e9, "note": "algorithmic conv FLOPs (SURVEY 8d) / measured cuBLAS bf16 burst peak"}}
 
 
+def muzero_leg(dev, peaks, G):
+    """BASELINE configs[2]: MuZero mode, 15x15, 400 simulations (= 100 distinct recurrent evaluations per
+    search), G games, GomokuNetEZ 8x128 bf16 dynamics network in the tree.  Hidden states
+    live in a device pool (one NHWC row per tree node); a simulation step is select -> hidden gather (+ action
+    plane) -> recurrent inference -> hidden scatter -> expand/backup, replayed as one CUDA graph."""
+    import torch
+    from datou_gomoku_muzero_b200.config import Config
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.muzero import FoldedRecurrentInference, MuZeroDeviceSearch, evals_per_search
+    from datou_gomoku_muzero_b200.network import FoldedInitialInference, GomokuNetEZ
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    cfg = Config(BOARD_SIZE=N, ACTION_SPACE_SIZE=A, NUM_RES_BLOCKS=8, NUM_FILTERS=128, HEAD_HIDDEN_DIM=64)
+    net = GomokuNetEZ(cfg).to(dev).eval()
+    fi, fr = FoldedInitialInference(net, torch.bfloat16), FoldedRecurrentInference(net, torch.bfloat16)
+
+    def initial(obs):
+        p, v, h = fi(obs.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+        return p.float().contiguous(), v.reshape(-1).float(), h
+
+    eng = SearchEngine(G, board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP, mode="MuZero", device=dev)
+    eng.set_roots(*staggered_positions(G, 0))
+    evals = evals_per_search(S, K_TOP, K_TOP)
+    mz = MuZeroDeviceSearch(eng, initial, fr, nodes_per_game=evals + 2, graph=True)
+    gum = torch.empty((G, A), dtype=torch.float64, device=dev)
+    eng.fill_gumbel(gum, 4243, 0)
+    mz.search(gum, max_steps=evals); eng.finalize(want_visits=False)          # warm-up: cuDNN plans + graph capture
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); steps = mz.search(gum, max_steps=evals); eng.finalize(want_visits=False); e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    # the pool kernels on their own: bytes moved per launch / time, against the measured HBM peak
+    parent, action, child, _ = eng._mz_out[:4]
+    parent.copy_(mz._root_slot); action.fill_(7); child.copy_(mz._root_slot + 1)
+    hrows = mz.pool[:G].clone()
+    g0, g1, s1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    for _ in range(3):
+        mz._gather(parent, action); mz._scatter(child, hrows)
+    g0.record()
+    for _ in range(20):
+        mz._gather(parent, action)
+    g1.record()
+    for _ in range(20):
+        mz._scatter(child, hrows)
+    s1.record(); torch.cuda.synchronize()
+    gather_ms, scatter_ms = g0.elapsed_time(g1) / 20, g1.elapsed_time(s1) / 20
+    gather_bytes = G * (2 * mz.row_bytes + mz.positions * mz.embed_bytes)
+    scatter_bytes = G * 2 * mz.row_bytes
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf = (1.141e9 * steps + 1.064e9) * G / (ms * 1e-3) / 1e12
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    return {"workload": "MuZero-mode 15x15, 400 sims/move, %d games, GomokuNetEZ 8x128 bf16 dynamics in the tree "
+                        "(BASELINE configs[2])" % G,
+            "sims_per_sec": G * S / (ms * 1e-3), "moves_per_sec": G / (ms * 1e-3), "ms_per_search": ms,
+            "recurrent_evals_per_search": steps, "distinct_evals_per_sec": G * (steps + 1) / (ms * 1e-3),
+            "hidden_pool_gb": mz.pool.numel() * mz.pool.element_size() / 1e9,
+            "tensor": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf},
+            "hidden_gather": {"bound": "hbm", "ms": gather_ms, "achieved": gather_bytes / gather_ms / 1e6, "peak": peak,
+                              "unit": "GB/s", "frac": gather_bytes / gather_ms / 1e6 / peak, "bytes": gather_bytes},
+            "hidden_scatter": {"bound": "hbm", "ms": scatter_ms, "achieved": scatter_bytes / scatter_ms / 1e6, "peak": peak,
+                               "unit": "GB/s", "frac": scatter_bytes / scatter_ms / 1e6 / peak, "bytes": scatter_bytes}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -358,6 +422,11 @@ def run_ours(args):
             out["net"] = net_leg(eng, dev, peaks)
         except Exception as ex:      # the headline (fixed evaluator) stands on its own
             out["net"] = {"error": repr(ex)[:200]}
+    if not args.no_net and world == 1:
+        try:
+            out["muzero"] = muzero_leg(dev, peaks, G)
+        except Exception as ex:
+            out["muzero"] = {"error": repr(ex)[:200]}
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         out["cpu_baseline"] = cpu_baseline_leg(args.cpu_seconds)
     print(json.dumps(out))

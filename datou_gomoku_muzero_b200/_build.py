@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libgmz.so")
-SOURCES = ["gmz_engine.cu", "gmz_per.cu", "gmz_slices.cu", "gmz_tactics.cu"]
+SOURCES = ["gmz_engine.cu", "gmz_per.cu", "gmz_slices.cu", "gmz_tactics.cu", "gmz_hidden.cu"]
 HEADERS = ["gmz_common.cuh", "gmz_tree.cuh", "gmz_play.cuh", os.path.join("..", "..", "include", "gmz.h")]
 # -fmad=false: the search's float64 arithmetic must round once per operation, like the
 # reference's Python floats; an FMA would change visit counts.

@@ -12,7 +12,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .network import GomokuNetEZ, _fold, _support_scalar
+from ._lib import check
+from .network import GomokuNetEZ, _fold, _fold_heads, _support_scalar
 
 _M64 = (1 << 64) - 1
 
@@ -40,55 +41,129 @@ def evals_per_search(num_simulations, num_top_actions, n_survivors):
 class MuZeroDeviceSearch:
     """initial_fn(obs f32 [G,3,N,N]) -> (logits f32 [G,A], values [G], hidden [G, ...])
     recurrent_fn(hidden [G, ...], actions int64 [G]) -> (logits, values, rewards [G], next_hidden [G, ...])
-    Hidden rows may be any dtype / shape; the pool is allocated from the first initial_fn result."""
+    Hidden rows may be any dtype / shape (4-byte multiples); the pool is allocated from the first
+    initial_fn result.  A 4-D hidden state [G,C,N,N] is stored NHWC (one row = N*N cells x C channels), so
+    the gathered batch is a channels_last tensor without a copy.
 
-    def __init__(self, engine, initial_fn, recurrent_fn, nodes_per_game=None):
+    One simulation step = gmz_select_mz -> gmz_hidden_gather -> recurrent_fn -> gmz_hidden_scatter ->
+    gmz_expand_backup, all on the device.  If recurrent_fn has `embed` ([E] action-embedding vector) and
+    `forward_fused(x)` (x = [G, C+E, N, N] channels_last: hidden state and one-hot action embedding already
+    concatenated, network.py:70-73), the gather writes that concatenated input directly.  With `graph=True`
+    the step is captured in a CUDA graph after `graph_warmup` eager steps and replayed from then on."""
+
+    def __init__(self, engine, initial_fn, recurrent_fn, nodes_per_game=None, graph=False, graph_warmup=3):
         if engine.mode != "MuZero":
             raise ValueError("MuZeroDeviceSearch needs an engine created with mode='MuZero'")
         self.e, self.initial_fn, self.recurrent_fn = engine, initial_fn, recurrent_fn
         self.nodes = int(nodes_per_game) if nodes_per_game else engine.S
         self.pool = None
         self.evaluations = 0
+        self.use_graph, self.graph_warmup, self.graph = bool(graph), int(graph_warmup), None
+        self.fused = hasattr(recurrent_fn, "forward_fused") and getattr(recurrent_fn, "embed", None) is not None
+        self._root_slot = (torch.arange(engine.G, dtype=torch.int32, device=engine.device) * engine.S).contiguous()
+
+    # ---- pool layout
+    @staticmethod
+    def _rows(h):
+        """hidden [G, ...] -> [G, row] view in pool order (NHWC for 4-D), copying only if the layout differs."""
+        if h.dim() == 4:
+            return h.permute(0, 2, 3, 1).contiguous().reshape(h.shape[0], -1)
+        return h.contiguous().reshape(h.shape[0], -1)
 
     def _ensure_pool(self, hidden):
-        shape = (self.e.G * self.nodes + 1,) + tuple(hidden.shape[1:])      # +1: dummy row for idle games
-        if self.pool is None or self.pool.shape != shape or self.pool.dtype != hidden.dtype:
-            if hidden.dim() == 4 and hidden.is_contiguous(memory_format=torch.channels_last):
-                self.pool = torch.empty(shape, dtype=hidden.dtype, device=hidden.device).contiguous(
-                    memory_format=torch.channels_last)
-            else:
-                self.pool = torch.empty(shape, dtype=hidden.dtype, device=hidden.device)
-        return self.pool
-
-    def _row(self, slot):
-        """engine slot (g*S + node) -> pool row (g*nodes + node); -1 -> the dummy row."""
         e = self.e
-        s = slot.long()
-        row = (s // e.S) * self.nodes + (s % e.S)
-        return torch.where(s < 0, torch.full_like(row, e.G * self.nodes), row)
+        rows = self._rows(hidden)
+        shape = (e.G * self.nodes, rows.shape[1])
+        if self.pool is None or self.pool.shape != shape or self.pool.dtype != hidden.dtype:
+            self.pool = torch.empty(shape, dtype=hidden.dtype, device=hidden.device)
+            self.hshape = tuple(hidden.shape[1:])
+            self.row_bytes = rows.shape[1] * hidden.element_size()
+            if self.row_bytes % 4:
+                raise ValueError("hidden-state rows must be a multiple of 4 bytes")
+            if hidden.dim() == 4:
+                C_, n1, n2 = self.hshape
+                self.positions, self.pos_bytes = n1 * n2, C_ * hidden.element_size()
+            else:
+                self.positions, self.pos_bytes = 1, self.row_bytes
+            self.embed = None
+            if self.fused and hidden.dim() == 4:
+                self.embed = self.recurrent_fn.embed.detach().to(hidden.dtype).to(hidden.device).contiguous()
+            E = 0 if self.embed is None else self.embed.numel()
+            self.embed_bytes = E * hidden.element_size()
+            per_pos = (self.pos_bytes + self.embed_bytes) // hidden.element_size()
+            self.x = torch.zeros((e.G, self.positions * per_pos), dtype=hidden.dtype, device=hidden.device)
+            self.graph = None
+        return rows
+
+    def _gather(self, slot, action):
+        e = self.e
+        check(e.lib.gmz_hidden_gather(self.pool.data_ptr(), slot.data_ptr(), action.data_ptr(), e.G, e.S, self.nodes,
+                                      self.positions, self.pos_bytes,
+                                      None if self.embed is None else self.embed.data_ptr(), self.embed_bytes,
+                                      self.x.data_ptr(), e._stream()), "gmz_hidden_gather")
+        e.launches += 1
+
+    def _scatter(self, slot, rows):
+        e = self.e
+        if rows.dtype != self.pool.dtype or rows.shape[1] != self.pool.shape[1]:
+            raise ValueError("recurrent_fn returned a hidden state of a different dtype / shape than initial_fn")
+        check(e.lib.gmz_hidden_scatter(self.pool.data_ptr(), slot.data_ptr(), e.G, e.S, self.nodes, self.row_bytes,
+                                       rows.data_ptr(), e._stream()), "gmz_hidden_scatter")
+        e.launches += 1
+
+    def _x_view(self):
+        """The gathered batch in the shape recurrent_fn expects."""
+        e = self.e
+        if len(self.hshape) == 3:
+            C_, n1, n2 = self.hshape
+            E = 0 if self.embed is None else self.embed.numel()
+            return self.x.view(e.G, n1, n2, C_ + E).permute(0, 3, 1, 2)           # channels_last [G, C+E, N, N]
+        return self.x.view((e.G,) + self.hshape)
+
+    def _step(self):
+        e = self.e
+        parent, action, child, depth = e.select_mz()
+        self._gather(parent, action)
+        if self.embed is not None:
+            lg, v, r, h_out = self.recurrent_fn.forward_fused(self._x_view())
+        else:
+            lg, v, r, h_out = self.recurrent_fn(self._x_view(), action.long().clamp_min(0))
+        self._scatter(child, self._rows(h_out))
+        e.expand_backup(lg, v, r)
+
+    def _capture(self):
+        e = self.e
+        n0 = e.launches
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        self._launches_per_step = e.launches - n0
+        e.launches = n0                                   # capture launched nothing
 
     @torch.no_grad()
     def search(self, gumbel, max_steps=None):
         """Runs one search for every game from the engine's current roots; call engine.finalize() after."""
         e = self.e
         lg, v, h = self.initial_fn(e.root_obs())
-        pool = self._ensure_pool(h)
-        base = torch.arange(e.G, device=e.device) * self.nodes
-        pool.index_copy_(0, base, h)
+        self._scatter(self._root_slot, self._ensure_pool(h))
         e.root_expand(lg, v, gumbel)
         steps, limit = 0, int(max_steps) if max_steps else e.S - 1      # at most S-1 evaluations (sim_count starts at 1)
         while steps < limit:
-            parent, action, child, depth = e.select_mz()
-            if steps % 8 == 7 and int(parent.max().item()) < 0:       # every game is done
-                break
             if steps + 2 > self.nodes:          # this step may create node id steps + 1
                 raise RuntimeError("hidden-state pool too small: pass a larger nodes_per_game")
-            h_in = pool.index_select(0, self._row(parent))
-            lg, v, r, h_out = self.recurrent_fn(h_in, action.long().clamp_min(0))
-            pool.index_copy_(0, self._row(child), h_out)
-            e.expand_backup(lg, v, r)
+            if self.use_graph and self.graph is None and steps >= self.graph_warmup:
+                self._capture()
+            if self.graph is not None:
+                self.graph.replay()
+                e.launches += self._launches_per_step
+            else:
+                self._step()
             steps += 1
             self.evaluations += 1
+            if steps % 8 == 0 and steps < limit and int(e._mz_out[0].max().item()) < 0:   # every game is done
+                self.evaluations -= 1           # the last step evaluated nothing
+                steps -= 1
+                break
         return steps
 
 
@@ -179,7 +254,7 @@ class FoldedRecurrentInference:
         self.r1 = (w1.reshape(-1, C, n, n).permute(0, 2, 3, 1).reshape(w1.shape[0], -1).to(dtype).contiguous(),
                    d.reward_fc[0].bias.detach().to(dtype))
         self.r2 = (d.reward_fc[2].weight.detach().to(dtype), d.reward_fc[2].bias.detach().to(dtype))
-        self.pol, self.val = _fold(p.policy_conv, p.policy_bn, dtype), _fold(p.value_conv, p.value_bn, dtype)
+        self.pv = _fold_heads(p, dtype)
         self.policy_fc = (p.policy_fc.weight.detach().to(dtype), p.policy_fc.bias.detach().to(dtype))
         self.value_fc1 = (p.value_fc1.weight.detach().to(dtype), p.value_fc1.bias.detach().to(dtype))
         self.value_fc2 = (p.value_fc2.weight.detach().to(dtype), p.value_fc2.bias.detach().to(dtype))
@@ -195,14 +270,20 @@ class FoldedRecurrentInference:
         B, n = hidden.shape[0], self.n
         plane = F.one_hot(actions, n * n).to(self.dtype).reshape(B, 1, n, n)
         emb = plane * self.embed.reshape(1, -1, 1, 1)                                      # 1x1 conv of a one-hot plane
-        x = torch.cat((hidden, emb), dim=1).contiguous(memory_format=torch.channels_last)
+        return self.forward_fused(torch.cat((hidden, emb), dim=1).contiguous(memory_format=torch.channels_last))
+
+    @torch.no_grad()
+    def forward_fused(self, x):
+        """x [B, C+16, n, n] channels_last: hidden state and action embedding already concatenated
+        (what gmz_hidden_gather writes)."""
+        B = x.shape[0]
         h = self._cr(x, self.stem, 1)
         for c1, c2 in self.blocks:
             h = torch.cudnn_convolution_add_relu(self._cr(h, c1, 1), c2[0], h, 1.0, c2[1], (1, 1), (1, 1), (1, 1), 1)
         flat = h.permute(0, 2, 3, 1).reshape(B, -1)
         rew = _support_scalar(F.linear(F.relu(F.linear(flat, *self.r1)), *self.r2).float(), *self.r_sup)
-        pl = self._cr(h, self.pol, 0).reshape(B, -1)
-        vl = self._cr(h, self.val, 0).reshape(B, -1)
+        pv = self._cr(h, self.pv, 0)
+        pl, vl = pv[:, :2].reshape(B, -1), pv[:, 2].reshape(B, -1)
         logits = F.linear(pl, *self.policy_fc).float()
         value = _support_scalar(F.linear(F.relu(F.linear(vl, *self.value_fc1)), *self.value_fc2).float(), *self.v_sup)
         return logits.contiguous(), value.reshape(-1), rew.reshape(-1), h

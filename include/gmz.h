@@ -171,6 +171,21 @@ int gmz_selfplay_step(gmz_engine *e, const gmz_traj *traj, const double *policy,
  * tickets whose game produced no move -- all since gmz_create. */
 int gmz_play_counters(gmz_engine *e, uint64_t *out2, gmz_stream stream);
 
+/* ---- MuZero-mode hidden-state pool (Node.hidden_state, mcts.py:21, 40-41; queue hops mcts.py:77-85) ---- */
+/* The pool holds one row per tree node, row(g, node) = g*nodes_per_game + node, each row `positions`
+ * cells of pos_bytes (NHWC: board cells x channels).  Slots are what gmz_select_mz emits
+ * (g*sims_per_game + node, or -1 = nothing to do for that game).
+ * gather: x[g] = per cell [ pool row cell | embed if cell == action[g] else zeros ] -- the dynamics
+ *   net's input, hidden state and one-hot action embedding concatenated along channels
+ *   (network.py:70-73).  embed_bytes may be 0 (then embed/action may be NULL).  slot < 0 writes zeros.
+ * scatter: pool[row(slot[g])] = hidden[g] (row_bytes each); slot < 0 is skipped.
+ * Byte sizes and pointers must be multiples of 4; 16-byte multiples take the 128-bit copy path. */
+int gmz_hidden_gather(const void *pool, const int32_t *slot, const int32_t *action, int num_games, int sims_per_game,
+                      int nodes_per_game, int positions, int pos_bytes, const void *embed, int embed_bytes, void *x,
+                      gmz_stream stream);
+int gmz_hidden_scatter(void *pool, const int32_t *slot, int num_games, int sims_per_game, int nodes_per_game,
+                       int row_bytes, const void *hidden, gmz_stream stream);
+
 /* ---- self-play game step --------------------------------------------------- */
 /* game.do_move(action) + game.get_game_ended() on the roots (workers.py:178-181,
  * game.py:20-63): actions int32 [G] (<0 = skip that game); out_winner int32 [G]

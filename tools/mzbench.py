@@ -13,6 +13,7 @@ from datou_gomoku_muzero_b200.network import FoldedInitialInference, GomokuNetEZ
 ap = argparse.ArgumentParser()
 ap.add_argument("--games", type=int, default=4096)
 ap.add_argument("--searches", type=int, default=2)
+ap.add_argument("--graph", type=int, default=1, help="capture the simulation step in a CUDA graph")
 ap.add_argument("--profile", default="", help="write a per-kernel GPU-time table (torch profiler) of one search to this file")
 args = ap.parse_args()
 G = args.games
@@ -28,21 +29,24 @@ def initial(obs):
 eng = SearchEngine(G, board_size=N, num_simulations=S, num_top_actions=K_TOP, mode="MuZero")
 eng.set_roots(*staggered_positions(G, 0))
 evals = evals_per_search(S, K_TOP, K_TOP)
-mz = MuZeroDeviceSearch(eng, initial, fr, nodes_per_game=evals + 2)
+mz = MuZeroDeviceSearch(eng, initial, fr, nodes_per_game=evals + 2, graph=bool(args.graph))
 gum = torch.empty((G, A), dtype=torch.float64, device="cuda"); eng.fill_gumbel(gum, 1, 0)
 mz.search(gum, max_steps=evals); eng.finalize(want_visits=False)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(args.searches):
+marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.searches + 1)]
+marks[0].record()
+for i in range(args.searches):
     steps = mz.search(gum, max_steps=evals); eng.finalize(want_visits=False)
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / args.searches
+    marks[i + 1].record()
+torch.cuda.synchronize()
+per_search = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.searches)]
+ms = sum(per_search) / args.searches
 tf = (1.141e9 * steps + 1.064e9) * G / (ms * 1e-3) / 1e12
 print(json.dumps({"config": "MuZero-mode 15x15, 400 sims, %d games, GomokuNetEZ 8x128 bf16 in-tree dynamics" % G,
                   "ms_per_search": ms, "recurrent_evals_per_search": steps, "sims_per_sec": G * S / (ms * 1e-3),
                   "moves_per_sec": G / (ms * 1e-3), "distinct_evals_per_sec": G * (steps + 1) / (ms * 1e-3),
-                  "tensor_tflops": tf, "hidden_pool_gb": mz.pool.numel() * mz.pool.element_size() / 1e9}))
+                  "tensor_tflops": tf, "ms_each": [round(x, 1) for x in per_search], "graph": bool(args.graph), "hidden_pool_gb": mz.pool.numel() * mz.pool.element_size() / 1e9}))
 
 if args.profile:
     from torch.profiler import ProfilerActivity, profile
