@@ -58,6 +58,7 @@ SIGNATURES = {
     "gmz_selfplay_unpark": (C.c_int, [_P, C.POINTER(GmzTraj), _P]),
     "gmz_selfplay_step": (C.c_int, [_P, C.POINTER(GmzTraj), _P, _P, _P, C.c_int, _P, _P]),
     "gmz_play_counters": (C.c_int, [_P, _P, _P]),
+    "gmz_select_counters": (C.c_int, [_P, _P, _P]),
     "gmz_value_targets": (C.c_int, [C.POINTER(GmzTraj), _P, _P, _P, C.c_int, _P, C.c_int, _P, _P]),
     "gmz_hidden_gather": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "gmz_hidden_scatter": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),

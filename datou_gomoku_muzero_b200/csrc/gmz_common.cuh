@@ -74,6 +74,22 @@ struct Params {
     short *pyset;    // [ceil(G/4)*4][4096] scratch for the CPython-set tie-break (rare path)
     char *sel_overflow;   // [ceil(G/4)*4][128*NC*20 B] select scratch for nodes with > 64 visited children
     struct PlayCtl *ctl;   // play-kernel ticket counter + statistics
+    int4 *nHdr;      // [G*S]      summary of a node's unvisited actions + number of children (see gmz_tree.cuh)
+    int2 *nList;     // [G*S][32]  a node's children in creation order: ((action << 16) | child id, logit bits)
+};
+
+// Device-side control block of the play kernel (+ select statistics).
+struct PlayCtl {
+    unsigned long long next_ticket;        // round-robin game cursor of the current launch
+    unsigned long long moves_started;      // moves handed out in the current launch
+    unsigned long long moves_played;
+    unsigned long long games_finished;
+    unsigned long long tickets_unserved;   // no playable game found (everything busy / parked)
+    unsigned long long tickets_idle;       // game acquired but no move came out of it
+    unsigned long long sel_fallback;       // interior selects the certified path handed to the exact one
+    unsigned long long sel_fast;           // (GMZ_VERIFY_FAST builds) selects decided by the certified path
+    unsigned long long sel_mismatch;       // (GMZ_VERIFY_FAST builds) ... that the exact path decided differently
+    unsigned long long pad[3];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -124,6 +140,27 @@ __device__ __forceinline__ double exp_nonpos(double x)
 #pragma unroll
     for (int i = 5; i < 16; ++i) q = fma(q, r, c_exp[i]);
     return __hiloint2double(__double2hiint(q) + (int)((unsigned)k << 20), __double2loint(q));
+}
+// Order-preserving map float -> u32 and back.
+__device__ __forceinline__ unsigned f32_key(float v)
+{
+    const unsigned b = __float_as_uint(v);
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float f32_unkey(unsigned k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu)); }
+__device__ __forceinline__ float warp_sum_f32(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(GMZ_FULL, v, o));
+    return v;
+}
+// 1/x for x in the float range, to ~1e-15: float reciprocal + two Newton steps (the certified select
+// path only needs ~1e-9; the exact path keeps the correctly rounded division).
+__device__ __forceinline__ double rcp_newton(double x)
+{
+    double r = (double)__frcp_rn((float)x);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
 }
 // xor-butterfly sum: a+b == b+a exactly, so every lane ends with the same bits
 __device__ __forceinline__ double warp_sum_f64(double v)

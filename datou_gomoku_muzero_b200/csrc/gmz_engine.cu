@@ -209,8 +209,10 @@ k_expand_backup(Params p, const float *logits, const void *values, const void *r
     const double value = load_value(values, vdtype, g);
     const double reward = (MZ && rewards) ? load_value(rewards, vdtype, g) : 0.0;
     const int nn = w.num_nodes;
+    wg_valid_bits<NC>(p, w, lane);
     node_write_row<NC>(p, w, nn, lg, lane);
-    if (lane == 0) p.child[(w.nbase + (size_t)lp) * (size_t)p.AP + la] = (short)nn;
+    node_init_hdr<NC>(p, w, nn, lg, lane);
+    node_link<NC>(p, w, lp, la, nn, lane);
     w.num_nodes = nn + 1;
     backup<MZ>(p, w, path, depth, nn, value, reward, reps, lane);
     survivor_visit(w, depth, path, nn, la, reps, lane);
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_game_step(Params p, const int32
 static float pow2_inv(int d) { return (d > 0 && (d & (d - 1)) == 0) ? 1.0f / (float)d : 0.0f; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct Layout { size_t gs, logits, child, nN, nW, nR, nH, path, pyset, selov, ctl, total; };
+struct Layout { size_t gs, logits, child, nN, nW, nR, nH, path, pyset, selov, ctl, hdr, list, total; };
 
 static int validate(const gmz_config *c)
 {
@@ -403,6 +405,8 @@ static Layout make_layout(const gmz_config *c)
     L.pyset = o; o = align_up(o + ((G + 3) / 4 * 4) * 4096 * sizeof(short), 256);
     L.selov = o; o = align_up(o + ((G + 3) / 4 * 4) * AP * 20, 256);
     L.ctl = o; o = align_up(o + sizeof(PlayCtl), 256);
+    L.hdr = o; o = align_up(o + G * S * sizeof(int4), 256);
+    L.list = o; o = align_up(o + G * S * kListCap * sizeof(int2), 256);
     L.total = o;
     return L;
 }
@@ -452,6 +456,7 @@ extern "C" int gmz_create(const gmz_config *cfg, void *workspace, size_t workspa
     p.nH = cfg->mode == GMZ_MODE_MUZERO ? (u64 *)(base + L.nH) : nullptr;
     p.path = (short *)(base + L.path);
     p.pyset = (short *)(base + L.pyset); p.sel_overflow = base + L.selov; p.ctl = (PlayCtl *)(base + L.ctl);
+    p.nHdr = (int4 *)(base + L.hdr); p.nList = (int2 *)(base + L.list);
     cudaError_t err = cudaMemsetAsync(base + L.gs, 0, (size_t)p.G * sizeof(GState), (cudaStream_t)stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(base + L.ctl, 0, sizeof(PlayCtl), (cudaStream_t)stream);
     if (err != cudaSuccess) { free(e); return fail("cudaMemsetAsync: %s", cudaGetErrorString(err)); }
@@ -652,6 +657,13 @@ extern "C" int gmz_play_counters(gmz_engine *e, uint64_t *out2, gmz_stream strea
     if (!e || !out2) return fail("gmz_play_counters: null argument");
     cudaError_t err = cudaMemcpyAsync(out2, &e->p.ctl->moves_played, 4 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     if (err != cudaSuccess) return fail("gmz_play_counters: %s", cudaGetErrorString(err));
+    return 0;
+}
+extern "C" int gmz_select_counters(gmz_engine *e, uint64_t *out3, gmz_stream stream)
+{
+    if (!e || !out3) return fail("gmz_select_counters: null argument");
+    cudaError_t err = cudaMemcpyAsync(out3, &e->p.ctl->sel_fallback, 3 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    if (err != cudaSuccess) return fail("gmz_select_counters: %s", cudaGetErrorString(err));
     return 0;
 }
 extern "C" int gmz_fill_gumbel(double *out, size_t n, uint64_t seed, uint64_t offset, gmz_stream stream)

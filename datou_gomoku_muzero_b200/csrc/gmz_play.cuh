@@ -173,17 +173,6 @@ __device__ __forceinline__ double gumbel_at(u64 seed_mixed, u64 counter)
     return -log(-log(u));
 }
 
-// Device-side control block of the play kernel.
-struct PlayCtl {
-    unsigned long long next_ticket;        // round-robin game cursor of the current launch
-    unsigned long long moves_started;      // moves handed out in the current launch
-    unsigned long long moves_played;
-    unsigned long long games_finished;
-    unsigned long long tickets_unserved;   // no playable game found (everything busy / parked)
-    unsigned long long tickets_idle;       // game acquired but no move came out of it
-    unsigned long long pad[2];
-};
-
 // Caller-owned trajectory storage (gmz_traj in include/gmz.h), device pointers.
 struct TrajDev {
     int n_slots, max_moves, fin_cap, pad;
@@ -323,19 +312,17 @@ k_play_e0(Params p, PlayArgs a)
                 const int reps = MZ ? w.n_surv : 1;            // MuZero: len(selected) identical selections -> that many backups
                 const int nn = w.num_nodes;
                 {   // evaluate + leaf.expand fused: logits go straight into the new node's row
-                    float *lrow = p.logits + (w.nbase + (size_t)nn) * (size_t)p.AP;
-                    short *crow = p.child + (w.nbase + (size_t)nn) * (size_t)p.AP;
+                    float lg[4 * NC];
 #pragma unroll kExpUnroll
                     for (int i = 0; i < 4 * NC; ++i) {      // lightly unrolled: two independent hash chains in flight
                         const int ac = 128 * (i >> 2) + 4 * lane + (i & 3);
-                        lrow[ac] = ac < p.A ? e0_logit(h, ac, a.logit_div, a.inv_div) : 0.0f;
+                        lg[i] = ac < p.A ? e0_logit(h, ac, a.logit_div, a.inv_div) : 0.0f;
                     }
-#pragma unroll
-                    for (int j = 0; j < NC; ++j)
-                        *reinterpret_cast<short4 *>(crow + 128 * j + 4 * lane) = make_short4(-1, -1, -1, -1);
+                    node_write_row<NC>(p, w, nn, lg, lane);
+                    node_init_hdr<NC>(p, w, nn, lg, lane);
                 }
+                node_link<NC>(p, w, lp, la, nn, lane);
                 if (lane == 0) {
-                    p.child[(w.nbase + (size_t)lp) * (size_t)p.AP + la] = (short)nn;
                     if (MZ) p.nH[w.nbase + (size_t)nn] = h;
                     if (a.trace_a) a.trace_a[(size_t)g * p.S + ev] = la;
                     if (a.trace_d) a.trace_d[(size_t)g * p.S + ev] = depth;

@@ -316,12 +316,13 @@ __device__ __noinline__ void select_interior_big(const Params &p, const WG &w, i
     __syncwarp();
 }
 
-// Fast path of _select_action (mcts.py:106-117) for nodes with <= 32 visited children: lane k owns
+// The exact _select_action (mcts.py:106-117) for nodes with <= 32 visited children: lane k owns
 // visited child k in registers (N, W -> q -> sigma -> exp -> score), every lane owns 4*NC dense
 // (unvisited) actions.  Same arithmetic, same order of operations per element as the big variant.
+// Out of line: it only runs when the certified path below cannot decide.
 template <int NC, bool MZ>
-__device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
-                                                int &action, int &child)
+__device__ __noinline__ void select_interior_exact(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
+                                                   int &action, int &child)
 {
     constexpr int E = 4 * NC;
     const size_t ni = w.nbase + (size_t)node;
@@ -444,6 +445,176 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
     action = a;
     child = __shfl_sync(GMZ_FULL, bc, __ffs(own) - 1);
     __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Certified select.  At an interior node every UNVISITED action has q = 0 and N = 0, so its score is
+// just its softmax probability: among the unvisited root-valid actions the winner is always the one
+// with the highest logit (lowest index among equals), whatever sigma and the MinMaxStats are.  Each
+// node therefore carries a 16-byte summary of its unvisited set,
+//     ub  = that best unvisited action,  lub = its logit,
+//     U   = sum over the unvisited valid actions of exp(logit - lub)       (float32, in [1, A])
+// and the list of its children in creation order.  The candidates of a select are then the <= 31
+// visited children plus `ub`: one per lane, no pass over the A logits, and the softmax denominator is
+//     sum_visited exp(x_c - mx) + exp(x_ub - mx) * U.
+// The summary is float32 (relative error ~3e-6 on the probabilities), so the decision is CERTIFIED:
+// it is taken only if the best score clears every other candidate by more than that error, or ties
+// with candidates whose inputs are bit-identical (then the lowest action wins, as np.argmax); otherwise
+// the exact float64 path above decides.  Visit counts stay bit-exact; the summary is rebuilt (one pass
+// over the parent's logits, float32 exp) once per simulation, when a child is added.
+constexpr int kListCap = 32;          // list entries per node (Params::nList)
+constexpr int kFastMaxVisited = 31;   // visited children + the best unvisited action fit one warp
+constexpr double kCertEps = 2e-5;     // > 6x the float32 error bound of a probability
+
+// ub / lub / U / "ambiguous" for the candidate set `cand` (bit i = this lane's action i).  Ambiguous:
+// two different unvisited logits closer than 1e-6 -- float64 rounding of logit + sigma could merge
+// them, so such a node always takes the exact path.
+template <int NC>
+__device__ __forceinline__ void unvisited_summary(const float *lg, unsigned cand, int lane, int &ub, float &lub, float &U, bool &amb)
+{
+    constexpr int E = 4 * NC;
+    float best = -INFINITY; int bi = -1;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        const float v = __fadd_rn(lg[i], 0.0f);                       // -0.0 -> +0.0: equal logits compare equal as keys
+        if (((cand >> i) & 1u) && (bi < 0 || v > best)) { best = v; bi = i; }
+    }
+    const unsigned key = bi >= 0 ? f32_key(best) : 0u;
+    const unsigned mk = __reduce_max_sync(GMZ_FULL, key);
+    const int ba = 128 * (bi >> 2) + 4 * lane + (bi & 3);
+    ub = __reduce_min_sync(GMZ_FULL, (bi >= 0 && key == mk) ? ba : 0x7fffffff);
+    if (ub == 0x7fffffff) { ub = -1; lub = 0.0f; U = 0.0f; amb = false; return; }
+    lub = f32_unkey(mk);
+    float u = 0.0f; bool am = false;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        if ((cand >> i) & 1u) {
+            const float d = __fsub_rn(__fadd_rn(lg[i], 0.0f), lub);   // <= 0
+            u = __fadd_rn(u, __expf(d));
+            am |= (d != 0.0f) && (d > -1e-6f);
+        }
+    }
+    U = warp_sum_f32(u);
+    amb = __any_sync(GMZ_FULL, am);
+}
+
+__device__ __forceinline__ int4 hdr_pack(float U, float lub, int ub, int nvis, int flags)
+{
+    return make_int4(__float_as_int(U), __float_as_int(lub), (ub & 0xffff) | (nvis << 16), flags);
+}
+
+// Header of a freshly expanded node: nothing visited yet.
+template <int NC>
+__device__ __forceinline__ void node_init_hdr(const Params &p, const WG &w, int node, const float *lg, int lane)
+{
+    int ub; float lub, U; bool amb;
+    unvisited_summary<NC>(lg, w.vb, lane, ub, lub, U, amb);
+    if (lane == 0) p.nHdr[w.nbase + (size_t)node] = hdr_pack(U, lub, ub, 0, amb ? 1 : 0);
+}
+
+// node.children[action] = new_node (mcts.py:27-30, 109): the child-row link, and for a non-root parent
+// the list entry + the refreshed summary of what is still unvisited.
+template <int NC>
+__device__ __forceinline__ void node_link(const Params &p, const WG &w, int parent, int action, int new_node, int lane)
+{
+    constexpr int E = 4 * NC;
+    const size_t pi = w.nbase + (size_t)parent;
+    short *crow = p.child + pi * (size_t)p.AP;
+    if (parent == 0) { if (lane == 0) crow[action] = (short)new_node; return; }
+    const float *lrow = p.logits + pi * (size_t)p.AP;
+    float lg[E]; unsigned vm = 0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const float4 t = *reinterpret_cast<const float4 *>(lrow + 128 * j + 4 * lane);
+        const short4 c = *reinterpret_cast<const short4 *>(crow + 128 * j + 4 * lane);
+        lg[4 * j + 0] = t.x; lg[4 * j + 1] = t.y; lg[4 * j + 2] = t.z; lg[4 * j + 3] = t.w;
+        vm |= ((c.x >= 0 ? 1u : 0u) | (c.y >= 0 ? 2u : 0u) | (c.z >= 0 ? 4u : 0u) | (c.w >= 0 ? 8u : 0u)) << (4 * j);
+    }
+    const int4 h = p.nHdr[pi];
+    const int owner = (action & 127) >> 2, idx = 4 * (action >> 7) + (action & 3);
+    float la = 0.0f;
+    if (lane == owner) {
+#pragma unroll
+        for (int i = 0; i < E; ++i) if (i == idx) la = lg[i];
+        vm |= 1u << idx;
+    }
+    la = __shfl_sync(GMZ_FULL, la, owner);
+    __syncwarp();
+    const int nvis = (h.z >> 16) + 1;
+    if (lane == 0) {
+        crow[action] = (short)new_node;
+        if (nvis <= kListCap) p.nList[pi * kListCap + (nvis - 1)] = make_int2((action << 16) | new_node, __float_as_int(la));
+    }
+    int ub; float lub, U; bool amb;
+    unvisited_summary<NC>(lg, w.vb & ~vm, lane, ub, lub, U, amb);
+    if (lane == 0) p.nHdr[pi] = hdr_pack(U, lub, ub, min(nvis, 32767), (amb || nvis > kFastMaxVisited) ? 1 : 0);
+}
+
+template <int NC, bool MZ>
+__device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
+                                                int &action, int &child)
+{
+    const size_t ni = w.nbase + (size_t)node;
+    const int4 h = p.nHdr[ni];
+    if (h.w == 0) {
+        const int nvis = h.z >> 16, ub = (int)(short)(h.z & 0xffff);
+        if (nvis == 0) { action = ub; child = -1; return; }            // nothing visited: the highest logit wins outright
+        const bool vis = lane < nvis, un = lane == nvis && ub >= 0, cand = vis || un;
+        int key = (ub << 16) | 0xffff, nn = 0; float slg = __int_as_float(h.y); double W = 0.0, rew = 0.0;
+        if (vis) {
+            const int2 e = p.nList[ni * kListCap + lane];
+            key = e.x; slg = __int_as_float(e.y);
+            const size_t ci = w.nbase + (size_t)(key & 0xffff);
+            nn = p.nN[ci]; W = p.nW[ci];
+            if (MZ) rew = p.nR[ci];
+        }
+        const int maxN = __reduce_max_sync(GMZ_FULL, nn), sumN = __reduce_add_sync(GMZ_FULL, nn);
+        const double scale = (p.c_visit + (double)maxN) * p.c_scale;
+        const bool rng = w.mm_max > w.mm_min;
+        const double rden = rng ? rcp_newton((w.mm_max - w.mm_min) + p.delta) : 0.0;
+        double xs = -INFINITY;
+        if (cand) {
+            const double q = vis ? rew + p.discount * (W * rcp_newton((double)nn)) : 0.0;
+            double nrm = (q - w.mm_min) * rden;
+            nrm = rng ? fmin(fmax(nrm, 0.0), 1.0) : 0.0;
+            xs = (double)slg + scale * nrm;
+        }
+        const double mx = warp_max_f64(xs);
+        const float ef = cand ? __expf((float)(xs - mx)) : 0.0f;
+        const float sum = warp_sum_f32(un ? __fmul_rn(ef, __int_as_float(h.x)) : ef);
+        const float pf = __fmul_rn(ef, __frcp_rn(sum));
+        const double s = (double)pf - (double)nn * rcp_newton((double)(1 + sumN));
+        const u64 k64 = cand ? f64_key(s) : 0ull;
+        const u64 mk = warp_max_key(k64);
+        const int a = __reduce_min_sync(GMZ_FULL, (cand && k64 == mk) ? (key >> 16) : 0x7fffffff);
+        const int bl = __ffs(__ballot_sync(GMZ_FULL, cand && k64 == mk && (key >> 16) == a)) - 1;
+        const double sb = f64_unkey(mk);
+        const float pb = __shfl_sync(GMZ_FULL, pf, bl);
+        bool near = cand && lane != bl && !(sb - s > kCertEps * (double)(pb + pf));
+        if (__any_sync(GMZ_FULL, near)) {      // a near-tie is fine only between bit-identical inputs (a true tie)
+            const int nb = __shfl_sync(GMZ_FULL, nn, bl);
+            const float lb = __shfl_sync(GMZ_FULL, slg, bl);
+            const double Wb = __shfl_sync(GMZ_FULL, W, bl), rb = __shfl_sync(GMZ_FULL, rew, bl);
+            near = near && !(nn == nb && nn > 0 && slg == lb && W == Wb && rew == rb);
+            near = __any_sync(GMZ_FULL, near);
+        } else near = false;
+        if (!near) {
+            const int wkey = __shfl_sync(GMZ_FULL, key, bl);
+            action = a; child = (wkey & 0xffff) == 0xffff ? -1 : (wkey & 0xffff);
+#ifdef GMZ_VERIFY_FAST
+            int ea, ec;
+            select_interior_exact<NC, MZ>(p, w, node, lane, sm, warp_slot, ea, ec);
+            if (lane == 0) {
+                atomicAdd(&p.ctl->sel_fast, 1ull);
+                if (ea != action || ec != child) atomicAdd(&p.ctl->sel_mismatch, 1ull);
+            }
+            action = ea; child = ec;
+#endif
+            return;
+        }
+        if (lane == 0) atomicAdd(&p.ctl->sel_fallback, 1ull);
+    }
+    select_interior_exact<NC, MZ>(p, w, node, lane, sm, warp_slot, action, child);
 }
 
 // _select_leaf (mcts.py:88-104): root = first least-visited survivor (strict <, list order),

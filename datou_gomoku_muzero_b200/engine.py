@@ -212,6 +212,13 @@ class SearchEngine:
         self.tickets_unserved, self.tickets_idle = int(unserved), int(idle)
         return int(m), int(f)
 
+    def select_counters(self):
+        """(fallbacks, certified, mismatches): interior selects handed to the exact path since the engine was
+        created; the last two are only counted by -DGMZ_VERIFY_FAST builds of the library."""
+        out = torch.zeros(3, dtype=torch.int64, device=self.device)
+        check(self.lib.gmz_select_counters(self.handle, _ptr(out), self._stream()), "gmz_select_counters")
+        return tuple(int(x) for x in out.cpu().tolist())
+
     def fill_gumbel(self, out, seed, offset=0):
         check(self.lib.gmz_fill_gumbel(_ptr(out), out.numel(), C.c_uint64(seed & (2**64 - 1)),
                                        C.c_uint64(offset), self._stream()), "gmz_fill_gumbel")

@@ -170,6 +170,11 @@ int gmz_selfplay_step(gmz_engine *e, const gmz_traj *traj, const double *policy,
 /* out (device, uint64 [4]) = moves played, games finished, tickets that found no playable game,
  * tickets whose game produced no move -- all since gmz_create. */
 int gmz_play_counters(gmz_engine *e, uint64_t *out2, gmz_stream stream);
+/* out (device, uint64 [3]) = interior selections (_select_action, mcts.py:106-117) that the certified
+ * float32 candidate path could not decide and handed to the exact float64 path; and, in builds with
+ * -DGMZ_VERIFY_FAST only (every certified decision re-derived by the exact path), the number of
+ * certified decisions and how many of them the exact path contradicted (must be 0). */
+int gmz_select_counters(gmz_engine *e, uint64_t *out3, gmz_stream stream);
 
 /* ---- MuZero-mode hidden-state pool (Node.hidden_state, mcts.py:21, 40-41; queue hops mcts.py:77-85) ---- */
 /* The pool holds one row per tree node, row(g, node) = g*nodes_per_game + node, each row `positions`

@@ -35,7 +35,7 @@ def test_config_validation_without_gpu():
     lib = _lib.load()
     ok = _lib.GmzConfig(15, 5, 400, 16, 0, 4096, 0, 0, 30.0, 1.0, 1e-3, 0.997)
     nbytes = lib.gmz_workspace_bytes(ctypes.byref(ok))
-    assert 2.4e9 < nbytes < 3.0e9          # 4096 games x 400 nodes x (1 KiB logits + 512 B children + headers)
+    assert 2.8e9 < nbytes < 3.3e9          # 4096 games x 400 nodes x (1 KiB logits + 512 B children + 256 B child list + headers)
     for bad in (_lib.GmzConfig(20, 5, 400, 16, 0, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997),      # board too large
                 _lib.GmzConfig(15, 5, 0, 16, 0, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997),        # no simulations
                 _lib.GmzConfig(15, 5, 400, 33, 0, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997),      # too many top actions
@@ -109,7 +109,7 @@ def test_entry_points_reject_bad_arguments_without_crashing():
         ("gmz_fill_gumbel", (N, 8, 0, 0, N)), ("gmz_game_step", (N, N, N, N)),
         ("gmz_traj_init", (N, N, N)), ("gmz_selfplay_e0", (N, N, 0, 16, 0, 8, 1, N)),
         ("gmz_selfplay_unpark", (N, N, N)), ("gmz_selfplay_step", (N, N, N, N, N, 1, N, N)),
-        ("gmz_play_counters", (N, N, N)), ("gmz_value_targets", (N, N, N, N, 3, N, 10, N, N)),
+        ("gmz_play_counters", (N, N, N)), ("gmz_select_counters", (N, N, N)), ("gmz_value_targets", (N, N, N, N, 3, N, 10, N, N)),
         ("gmz_build_batch", (N, 9, N, N, N, N, N, 4, 5, N, N, N, N, N, N)),
         ("gmz_build_batch_aug", (N, 9, N, N, N, N, N, 4, 5, 1, 1, N, N, N, N, N, N)),
         ("gmz_hidden_gather", (N, N, N, 4, 20, 4, 36, 256, N, 0, N, N)), ("gmz_hidden_scatter", (N, N, 4, 20, 4, 9216, N, N)),

@@ -41,4 +41,5 @@ for b in range(args.batches):
     print(f"batch {b}: seed {seed} logit_div {div}: cumulative {tot} searches, visit mismatches {bad_vis}, move {bad_act}, value {bad_val}", flush=True)
 print(json.dumps({"searches": tot, "simulations": tot * S, "config": "15x15, 400 sims, K=16, random positions 0..224 stones, logit_div in {16,4,2}",
                   "visit_count_mismatches": bad_vis, "move_mismatches": bad_act, "value_bit_mismatches": bad_val,
-                  "max_abs_policy_diff": worst_pol, "seconds": time.time() - t0}))
+                  "max_abs_policy_diff": worst_pol, "seconds": time.time() - t0,
+                  "select_counters": dict(zip(("fallback_to_exact", "certified", "certified_but_exact_differs"), eng.select_counters()))}))
