@@ -117,7 +117,7 @@ __device__ __forceinline__ void load_lane_logits(const float *src, int A, int la
 #pragma unroll
     for (int i = 0; i < 4 * NC; ++i) {
         const int a = 128 * (i >> 2) + 4 * lane + (i & 3);
-        lg[i] = a < A ? src[a] : 0.0f;
+        lg[i] = a < A ? __fadd_rn(src[a], 0.0f) : 0.0f;      // -0.0 -> +0.0: equal logits have equal bits (unvisited_summary)
     }
 }
 __device__ __forceinline__ double load_value(const void *v, int dtype, int g)
@@ -148,7 +148,7 @@ k_root_expand(Params p, const float *logits, const void *values, int vdtype, con
 
 template <int NC, bool MZ, typename T>
 __global__ void __launch_bounds__(CTA_THREADS)
-k_select(Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, int32_t *out_depth, int32_t *out_reps)
+k_select(const __grid_constant__ Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, int32_t *out_depth, int32_t *out_reps)
 {
     // AZ: out_a = leaf action (trace).  MZ: out_a = parent slot, out_b = action, out_c = child slot.
     const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -194,7 +194,7 @@ k_select(Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, 
 
 template <int NC, bool MZ>
 __global__ void __launch_bounds__(CTA_THREADS)
-k_expand_backup(Params p, const float *logits, const void *values, const void *rewards, int vdtype)
+k_expand_backup(const __grid_constant__ Params p, const float *logits, const void *values, const void *rewards, int vdtype)
 {
     const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (g >= p.G) return;
@@ -225,7 +225,7 @@ k_expand_backup(Params p, const float *logits, const void *values, const void *r
 
 template <int NC, bool MZ>
 __global__ void __launch_bounds__(CTA_THREADS)
-k_finalize(Params p, double *policy, double *value, int32_t *action, int32_t *visits)
+k_finalize(const __grid_constant__ Params p, double *policy, double *value, int32_t *action, int32_t *visits)
 {
     __shared__ short s_nvis[WARPS_PER_CTA][128 * NC];
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_CTA + wi;

@@ -241,7 +241,7 @@ __device__ __noinline__ u64 play_root(const Params &p, const PlayArgs &a, WG &w,
 // per ticket, one game per warp, E0 inlined.
 template <int NC, bool MZ>
 __global__ void __launch_bounds__(32 * GMZ_PLAY_WARPS, GMZ_PLAY_MIN_CTAS)
-k_play_e0(Params p, PlayArgs a)
+k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
 {
     __shared__ SelSmem s_sel[GMZ_PLAY_WARPS];
     __shared__ short s_nvis[GMZ_PLAY_WARPS][128 * NC];
@@ -297,7 +297,8 @@ k_play_e0(Params p, PlayArgs a)
         double value = 0.0; int action = -1;
         if (w.active) {
             wg_valid_bits<NC>(p, w, lane);
-            const u64 h_root = play_root<NC>(p, a, w, s->noise_ctr, noise_mixed, lane);
+            u64 h_root;
+            { WG t = w; h_root = play_root<NC>(p, a, t, s->noise_ctr, noise_mixed, lane); w = t; }   // by copy: w stays in registers
             if (MZ && lane == 0) p.nH[w.nbase] = h_root;         // root hidden state = hash of the root observation
             __syncwarp();
             int ev = 0;
@@ -360,7 +361,7 @@ k_play_e0(Params p, PlayArgs a)
             if (a.out_policy) pol = a.out_policy + (size_t)g * p.A;
             if (a.out_visits) vis = a.out_visits + (size_t)g * p.A;
         }
-        finalize_root<NC, MZ>(p, w, lane, pol, vis, s_nvis[wi], table, value, action);
+        { WG t = w; finalize_root<NC, MZ>(p, t, lane, pol, vis, s_nvis[wi], table, value, action); }
         if (!a.do_step) {
             if (lane == 0) { if (a.out_value) a.out_value[g] = value; if (a.out_action) a.out_action[g] = action; }
         } else if (action < 0) {

@@ -171,15 +171,26 @@ __device__ __forceinline__ SelPtr sel_global(const Params &p, int warp_slot)
     return s;
 }
 
+// What the out-of-line exact select needs of the game, passed BY VALUE: a reference to the caller's WG
+// would pin the whole register-resident game view in local memory.
+struct SelCtx { size_t nbase; double mm_min, mm_max; unsigned vb; };
+__device__ __forceinline__ SelCtx sel_ctx(const WG &w) { SelCtx c; c.nbase = w.nbase; c.mm_min = w.mm_min; c.mm_max = w.mm_max; c.vb = w.vb; return c; }
+__device__ __forceinline__ int sel_pack(int action, int child) { return (action << 16) | (child & 0xffff); }
+__device__ __forceinline__ void sel_unpack(int packed, int &action, int &child)
+{
+    action = packed >> 16;
+    child = (packed & 0xffff) == 0xffff ? -1 : (packed & 0xffff);
+}
+
 // _select_action at an interior node (mcts.py:106-117):
 // argmax_a  softmax(logits + sigma)[a] - N(a) / (1 + sum_b N(b))   over the ROOT-valid actions.
 // Most of a node's A children are unvisited (q = 0, N = 0, same sigma): those are scored in a
 // branch-free dense pass from the row alone.  The few visited children are compacted into
 // `sc` (one per lane) and scored in a sparse pass that gathers their N / W.
 template <int NC, bool MZ>
-__device__ __noinline__ void select_interior_big(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
-                                                 int &action, int &child)
+__device__ __noinline__ int select_interior_big(const Params &p, const SelCtx w, int node, int lane, SelSmem &sm, int warp_slot)
 {
+    int action, child;
     constexpr int E = 4 * NC;
     const size_t ni = w.nbase + (size_t)node;
     const float *lrow = p.logits + ni * (size_t)p.AP;
@@ -314,6 +325,7 @@ __device__ __noinline__ void select_interior_big(const Params &p, const WG &w, i
     action = a;
     child = __shfl_sync(GMZ_FULL, bc, __ffs(own) - 1);
     __syncwarp();
+    return sel_pack(action, child);
 }
 
 // The exact _select_action (mcts.py:106-117) for nodes with <= 32 visited children: lane k owns
@@ -321,9 +333,9 @@ __device__ __noinline__ void select_interior_big(const Params &p, const WG &w, i
 // (unvisited) actions.  Same arithmetic, same order of operations per element as the big variant.
 // Out of line: it only runs when the certified path below cannot decide.
 template <int NC, bool MZ>
-__device__ __noinline__ void select_interior_exact(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
-                                                   int &action, int &child)
+__device__ __noinline__ int select_interior_exact(const Params &p, const SelCtx w, int node, int lane, SelSmem &sm, int warp_slot)
 {
+    int action, child;
     constexpr int E = 4 * NC;
     const size_t ni = w.nbase + (size_t)node;
     const float *lrow = p.logits + ni * (size_t)p.AP;
@@ -346,7 +358,7 @@ __device__ __noinline__ void select_interior_exact(const Params &p, const WG &w,
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(GMZ_FULL, inc, o); if (lane >= o) inc += t; }
         total = __shfl_sync(GMZ_FULL, inc, 31);
-        if (total > 32) { select_interior_big<NC, MZ>(p, w, node, lane, sm, warp_slot, action, child); return; }
+        if (total > 32) return select_interior_big<NC, MZ>(p, w, node, lane, sm, warp_slot);
         int pos = inc - cnt;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
@@ -445,6 +457,7 @@ __device__ __noinline__ void select_interior_exact(const Params &p, const WG &w,
     action = a;
     child = __shfl_sync(GMZ_FULL, bc, __ffs(own) - 1);
     __syncwarp();
+    return sel_pack(action, child);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -463,6 +476,7 @@ __device__ __noinline__ void select_interior_exact(const Params &p, const WG &w,
 // the exact float64 path above decides.  Visit counts stay bit-exact; the summary is rebuilt (one pass
 // over the parent's logits, float32 exp) once per simulation, when a child is added.
 constexpr int kListCap = 32;          // list entries per node (Params::nList)
+constexpr int kListSpec = 8;          // entries loaded speculatively with the header
 constexpr int kFastMaxVisited = 31;   // visited children + the best unvisited action fit one warp
 constexpr double kCertEps = 2e-5;     // > 6x the float32 error bound of a probability
 
@@ -473,26 +487,23 @@ template <int NC>
 __device__ __forceinline__ void unvisited_summary(const float *lg, unsigned cand, int lane, int &ub, float &lub, float &U, bool &amb)
 {
     constexpr int E = 4 * NC;
-    float best = -INFINITY; int bi = -1;
+    // rows never hold -0.0 (canonicalised when they are written), so equal logits have equal bits
+    float v[E], best = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < E; ++i) {
-        const float v = __fadd_rn(lg[i], 0.0f);                       // -0.0 -> +0.0: equal logits compare equal as keys
-        if (((cand >> i) & 1u) && (bi < 0 || v > best)) { best = v; bi = i; }
-    }
-    const unsigned key = bi >= 0 ? f32_key(best) : 0u;
-    const unsigned mk = __reduce_max_sync(GMZ_FULL, key);
-    const int ba = 128 * (bi >> 2) + 4 * lane + (bi & 3);
-    ub = __reduce_min_sync(GMZ_FULL, (bi >= 0 && key == mk) ? ba : 0x7fffffff);
-    if (ub == 0x7fffffff) { ub = -1; lub = 0.0f; U = 0.0f; amb = false; return; }
+    for (int i = 0; i < E; ++i) { v[i] = ((cand >> i) & 1u) ? lg[i] : -INFINITY; best = fmaxf(best, v[i]); }
+    const unsigned mk = __reduce_max_sync(GMZ_FULL, f32_key(best));
     lub = f32_unkey(mk);
+    int bi = E;
+#pragma unroll
+    for (int i = E - 1; i >= 0; --i) bi = (v[i] == lub) ? i : bi;
+    ub = __reduce_min_sync(GMZ_FULL, (bi < E && cand != 0u) ? 128 * (bi >> 2) + 4 * lane + (bi & 3) : 0x7fffffff);
+    if (ub == 0x7fffffff) { ub = -1; lub = 0.0f; U = 0.0f; amb = false; return; }
     float u = 0.0f; bool am = false;
 #pragma unroll
     for (int i = 0; i < E; ++i) {
-        if ((cand >> i) & 1u) {
-            const float d = __fsub_rn(__fadd_rn(lg[i], 0.0f), lub);   // <= 0
-            u = __fadd_rn(u, __expf(d));
-            am |= (d != 0.0f) && (d > -1e-6f);
-        }
+        const float d = __fsub_rn(v[i], lub);                          // <= 0, -inf for non-candidates (exp -> 0)
+        u = __fadd_rn(u, __expf(d));
+        am |= (d < 0.0f) && (d > -1e-6f);
     }
     U = warp_sum_f32(u);
     amb = __any_sync(GMZ_FULL, am);
@@ -556,13 +567,16 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
 {
     const size_t ni = w.nbase + (size_t)node;
     const int4 h = p.nHdr[ni];
+    // the first 8 list entries (two sectors) are fetched alongside the header: 5 of 6 nodes have <= 8 children
+    int2 e = make_int2(0, 0);
+    if (lane < kListSpec) e = p.nList[ni * kListCap + lane];
     if (h.w == 0) {
         const int nvis = h.z >> 16, ub = (int)(short)(h.z & 0xffff);
         if (nvis == 0) { action = ub; child = -1; return; }            // nothing visited: the highest logit wins outright
         const bool vis = lane < nvis, un = lane == nvis && ub >= 0, cand = vis || un;
         int key = (ub << 16) | 0xffff, nn = 0; float slg = __int_as_float(h.y); double W = 0.0, rew = 0.0;
         if (vis) {
-            const int2 e = p.nList[ni * kListCap + lane];
+            if (lane >= kListSpec) e = p.nList[ni * kListCap + lane];
             key = e.x; slg = __int_as_float(e.y);
             const size_t ci = w.nbase + (size_t)(key & 0xffff);
             nn = p.nN[ci]; W = p.nW[ci];
@@ -603,7 +617,7 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
             action = a; child = (wkey & 0xffff) == 0xffff ? -1 : (wkey & 0xffff);
 #ifdef GMZ_VERIFY_FAST
             int ea, ec;
-            select_interior_exact<NC, MZ>(p, w, node, lane, sm, warp_slot, ea, ec);
+            sel_unpack(select_interior_exact<NC, MZ>(p, sel_ctx(w), node, lane, sm, warp_slot), ea, ec);
             if (lane == 0) {
                 atomicAdd(&p.ctl->sel_fast, 1ull);
                 if (ea != action || ec != child) atomicAdd(&p.ctl->sel_mismatch, 1ull);
@@ -614,7 +628,7 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         }
         if (lane == 0) atomicAdd(&p.ctl->sel_fallback, 1ull);
     }
-    select_interior_exact<NC, MZ>(p, w, node, lane, sm, warp_slot, action, child);
+    sel_unpack(select_interior_exact<NC, MZ>(p, sel_ctx(w), node, lane, sm, warp_slot), action, child);
 }
 
 // _select_leaf (mcts.py:88-104): root = first least-visited survivor (strict <, list order),
