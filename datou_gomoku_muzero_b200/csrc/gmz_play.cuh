@@ -306,6 +306,7 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                 u64 P = w.P, M = w.M; int colour = w.to_move;
                 int lp, la;
                 const int depth = descend<NC, MZ>(p, w, path, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
+                prefetch_parent_rows<NC>(p, w, lp, lane);
                 // AlphaZero mode: evaluate the replayed board (mcts.py:251-253).  MuZero mode: the learned
                 // dynamics, here E0's recurrent half on the parent's hidden state (mcts.py:336-343).
                 const u64 h = MZ ? e0_child_hidden(p.nH[w.nbase + (size_t)lp], la)

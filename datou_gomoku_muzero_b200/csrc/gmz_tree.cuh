@@ -563,7 +563,7 @@ __device__ __forceinline__ void node_link(const Params &p, const WG &w, int pare
 
 template <int NC, bool MZ>
 __device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
-                                                int &action, int &child)
+                                                bool rng, double rden, int &action, int &child)
 {
     const size_t ni = w.nbase + (size_t)node;
     const int4 h = p.nHdr[ni];
@@ -584,8 +584,6 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         }
         const int maxN = __reduce_max_sync(GMZ_FULL, nn), sumN = __reduce_add_sync(GMZ_FULL, nn);
         const double scale = (p.c_visit + (double)maxN) * p.c_scale;
-        const bool rng = w.mm_max > w.mm_min;
-        const double rden = rng ? rcp_newton((w.mm_max - w.mm_min) + p.delta) : 0.0;
         double xs = -INFINITY;
         if (cand) {
             const double q = vis ? rew + p.discount * (W * rcp_newton((double)nn)) : 0.0;
@@ -645,15 +643,30 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, short *path
     int parent = 0, depth = 1;
     if (lane == 0) path[0] = 0;
     if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
+    // MinMaxStats only change in the backup: 1 / (max - min + delta) is the same at every level of this descent
+    const bool rng = w.mm_max > w.mm_min;
+    const double rden = rng ? rcp_newton((w.mm_max - w.mm_min) + p.delta) : 0.0;
     while (node >= 0) {
         if (lane == 0) path[depth] = (short)node;
         int c;
-        select_interior<NC, MZ>(p, w, node, lane, sc, warp_slot, a, c);
+        select_interior<NC, MZ>(p, w, node, lane, sc, warp_slot, rng, rden, a, c);
         if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
         parent = node; node = c; ++depth;
     }
     leaf_parent = parent; leaf_action = a;
     return depth;
+}
+
+// The leaf's parent is refreshed (node_link) after the evaluation: start pulling its logits / child rows
+// into L1 now, so that the refresh does not pay the memory round trip.
+template <int NC>
+__device__ __forceinline__ void prefetch_parent_rows(const Params &p, const WG &w, int parent, int lane)
+{
+    if (parent == 0) return;
+    const size_t pi = (w.nbase + (size_t)parent) * (size_t)(128 * NC);          // row index * AP
+    const char *a = lane < 4 * NC ? (const char *)(p.logits + pi) + 128 * lane   // 4*NC lines of logits, 2*NC of child ids
+                                  : (const char *)(p.child + pi) + 128 * (lane - 4 * NC);
+    if (lane < 6 * NC) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
 }
 
 // leaf.expand (mcts.py:24-25, 260): write the new node's row (logits, no children) and link it.
@@ -680,6 +693,7 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const short *path
 {
     double v = dclip1(value);
     double qmin = INFINITY, qmax = -INFINITY;
+
     for (int hi = depth; hi >= 0; hi -= 32) {
         const int pos = hi - lane;
         const bool act = pos >= 0;
@@ -708,8 +722,10 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const short *path
             if (MZ && is_new) p.nR[ni] = R;
         }
     }
-    qmin = warp_min_f64(qmin); qmax = warp_max_f64(qmax);
-    w.mm_min = dmin2(w.mm_min, qmin); w.mm_max = dmax2(w.mm_max, qmax);
+    if (__any_sync(GMZ_FULL, qmin < w.mm_min || qmax > w.mm_max)) {      // rare once the range has settled
+        qmin = warp_min_f64(qmin); qmax = warp_max_f64(qmax);
+        w.mm_min = dmin2(w.mm_min, qmin); w.mm_max = dmax2(w.mm_max, qmax);
+    }
 }
 
 // _ready_for_next_gumbel_phase (mcts.py:166-181), tables precomputed on the host.
