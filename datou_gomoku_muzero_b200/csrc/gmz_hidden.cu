@@ -19,7 +19,7 @@ static int hd_fail(const char *m) { return gmz_set_error_(m); }
 
 namespace {
 
-constexpr int kThreads = 256, kUnroll = 4;
+constexpr int kThreads = 256, kUnroll = 8;
 
 // engine slot g*S + node -> pool row g*nodes + node
 __device__ __forceinline__ long long pool_row(int slot, int S, int nodes) { return (long long)(slot / S) * nodes + (slot % S); }
@@ -31,11 +31,14 @@ template <> __device__ __forceinline__ unsigned vzero<unsigned>() { return 0u; }
 
 // x row = A positions of (vin + ve) vectors; pool row = A positions of vin vectors.  V = the widest
 // vector (16, 8 or 4 bytes) every size and pointer is a multiple of.
-template <typename V>
+// CVIN / CVE: compile-time vector counts per position for the common shapes (the division by their sum
+// then costs a multiply-high), 0 = take the run-time values.
+template <typename V, int CVIN, int CVE>
 __global__ void __launch_bounds__(kThreads)
 k_hidden_gather(const V *__restrict__ pool, const int32_t *__restrict__ slot, const int32_t *__restrict__ action,
-                int S, int nodes, int A, int vin, int ve, const V *__restrict__ embed, V *__restrict__ x)
+                int S, int nodes, int A, int vin_rt, int ve_rt, const V *__restrict__ embed, V *__restrict__ x)
 {
+    const int vin = CVIN ? CVIN : vin_rt, ve = CVIN ? CVE : ve_rt;
     const int g = blockIdx.y, s = slot[g], a = ve ? action[g] : -1;
     const int vo = vin + ve, total = A * vo;
     const V *src = pool + (s >= 0 ? pool_row(s, S, nodes) : 0) * (long long)A * vin;
@@ -90,7 +93,12 @@ static void launch_gather(const void *pool, const int32_t *slot, const int32_t *
     const int vin = pos_bytes / (int)sizeof(V), ve = embed_bytes / (int)sizeof(V);
     const long long total = (long long)A * (vin + ve);
     dim3 grid((unsigned)((total + kThreads * kUnroll - 1) / (kThreads * kUnroll)), (unsigned)G);
-    k_hidden_gather<V><<<grid, kThreads, 0, st>>>((const V *)pool, slot, action, S, nodes, A, vin, ve, (const V *)embed, (V *)x);
+    if (sizeof(V) == 16 && vin == 16 && ve == 2)        // 128 bf16 channels + 16-channel action embedding (GomokuNetEZ)
+        k_hidden_gather<V, 16, 2><<<grid, kThreads, 0, st>>>((const V *)pool, slot, action, S, nodes, A, vin, ve, (const V *)embed, (V *)x);
+    else if (sizeof(V) == 16 && vin == 16 && ve == 0)
+        k_hidden_gather<V, 16, 0><<<grid, kThreads, 0, st>>>((const V *)pool, slot, action, S, nodes, A, vin, ve, (const V *)embed, (V *)x);
+    else
+        k_hidden_gather<V, 0, 0><<<grid, kThreads, 0, st>>>((const V *)pool, slot, action, S, nodes, A, vin, ve, (const V *)embed, (V *)x);
 }
 
 template <typename V>
