@@ -53,6 +53,10 @@ def staggered_positions(G, rank, rs=None):
     return boards, players, last, mc
 
 
+WORKLOAD = ("AlphaZero-mode 15x15 Gomoku self-play, 400 sims/move, 4096 concurrent games per GPU "
+            "(BASELINE configs[1]), E0 fixed deterministic evaluator")
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -62,7 +66,39 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
 
+    def _nvml(self):
+        """Fast path: NVML in-process (a sample every few ms); None if NVML cannot be used."""
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            return pynvml, h
+        except Exception:
+            return None
+
     def run(self):
+        nv = self._nvml()
+        bits = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+        while not self.stop_flag and nv is not None:
+            try:
+                pynvml, h = nv
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append([str(sm), str(mx), str(pw)] + [("Active" if r & b else "Not Active") for b, _ in bits])
+            except Exception:
+                nv = None
+                break
+            time.sleep(0.005)
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
@@ -71,7 +107,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
@@ -111,7 +147,10 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "moves_per_sec": games * args.steps / dt,
-        "config": {"workload": "AlphaZero-mode 15x15 Gomoku, 400 sims, E0 fixed evaluator, CPU oracle port", "games": games},
+        "config": {"workload": WORKLOAD, "games_per_gpu": args.games, "board": N, "num_simulations": S, "num_top_actions": K_TOP,
+                   "roots": "staggered synthetic mid-game positions (0..159 stones)",
+                   "step": "bounded sample of the workload: one 400-simulation search for each of %d games per step, "
+                           "CPU port of the reference search (oracle/gmz_oracle.c, OpenMP over games)" % games},
         "cpu_baseline": {"value": sims, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample,
                          "cpu_model": cpu_model()},
         "e2e": {"value": sims, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -291,7 +330,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created: send it to stderr,
+        # stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     G = args.games
 
     eng = SearchEngine(G, board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP, device=dev)
@@ -396,8 +447,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "moves_per_sec": moves_total / (elapsed_ms * 1e-3),
-        "config": {"workload": "AlphaZero-mode 15x15 Gomoku self-play, 400 sims/move, 4096 concurrent games per GPU "
-                               "(BASELINE configs[1]), E0 fixed deterministic evaluator inlined in the search kernel",
+        "config": {"workload": WORKLOAD,
                    "games_per_gpu": G, "board": N, "num_simulations": S, "num_top_actions": K_TOP,
                    "roots": "staggered synthetic mid-game positions (0..159 stones), finished games restarted in-kernel",
                    "step": "G self-play moves; the K timed steps run as one persistent ticketed launch of K*G moves",
