@@ -16,19 +16,26 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 
-def _stale() -> bool:
-    if not os.path.exists(SO):
+# The same library with every certified select decision re-derived by the exact float64 path and the
+# disagreements counted (gmz_select_counters): loaded only by tests/test_certified_select_gpu.py and
+# tools/soak_parity.py through GMZ_LIB, never by the package itself.
+SO_VERIFY = os.path.join(HERE, "libgmz_verify.so")
+
+
+def _stale(so=SO) -> bool:
+    if not os.path.exists(so):
         return True
-    t = os.path.getmtime(SO)
+    t = os.path.getmtime(so)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, verify: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not force and not _stale():
-        return SO
+    so = SO_VERIFY if verify else SO
+    if not force and not _stale(so):
+        return so
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", SO, *srcs]
+    cmd = [nvcc, *NVCC_FLAGS, *(["-DGMZ_VERIFY_FAST"] if verify else []), *(["-Xptxas", "-v"] if verbose else []), "-o", so, *srcs]
     subprocess.check_call(cmd)
-    return SO
+    return so
