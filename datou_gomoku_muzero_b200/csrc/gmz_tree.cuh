@@ -581,12 +581,6 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
             const size_t ci = w.nbase + (size_t)(key & 0xffff);
             nn = p.nN[ci]; W = p.nW[ci];
             if (MZ) rew = p.nR[ci];
-#ifndef GMZ_NO_CHILD_PREFETCH
-            // one of these children is the next node of the descent: pull its header and the first
-            // sector of its list towards L1 while this level is being scored
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.nHdr + ci));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.nList + ci * kListCap));
-#endif
         }
         const int maxN = __reduce_max_sync(GMZ_FULL, nn), sumN = __reduce_add_sync(GMZ_FULL, nn);
         const double scale = (p.c_visit + (double)maxN) * p.c_scale;
