@@ -11,8 +11,10 @@ from .engine import SearchEngine
 
 
 class SelfPlayEngine:
-    """evaluator: "e0" (fixed deterministic evaluator, fused persistent-kernel search) or a callable
-    `f(obs f32 [G,3,N,N]) -> (logits f32 [G,A], values f32/f64 [G])` run on the device (stepwise path)."""
+    """evaluator: "e0" (fixed deterministic evaluator, fused persistent-kernel search), a callable
+    `f(obs f32 [G,3,N,N]) -> (logits f32 [G,A], values f32/f64 [G])` run on the device (stepwise path), or --
+    for an engine in MuZero mode -- a pair `(initial_fn, recurrent_fn)` / a `muzero.MuZeroDeviceSearch`
+    (learned dynamics in the tree, hidden states in the device pool; MuZeroMCTS.search, mcts.py:288-362)."""
 
     def __init__(self, engine: SearchEngine, evaluator="e0", seed=0, logit_div=16, noise_seed=0):
         self.e = engine
@@ -24,6 +26,15 @@ class SelfPlayEngine:
         self.moves_played = 0
         self.games_finished = 0
         self.done_mask = torch.zeros(G, dtype=torch.uint8, device=engine.device)
+        self.mz = None
+        if evaluator != "e0" and engine.mode == "MuZero":
+            from .muzero import MuZeroDeviceSearch
+            if isinstance(evaluator, MuZeroDeviceSearch):
+                self.mz = evaluator
+            elif isinstance(evaluator, (tuple, list)) and len(evaluator) == 2:
+                self.mz = MuZeroDeviceSearch(engine, evaluator[0], evaluator[1])
+            else:
+                raise ValueError("a MuZero-mode engine needs evaluator='e0', (initial_fn, recurrent_fn) or a MuZeroDeviceSearch")
         engine.reset_games()
 
     def search(self, gumbel=None):
@@ -35,6 +46,8 @@ class SelfPlayEngine:
             gumbel = self.gumbel
         if self.evaluator == "e0":
             e.search_e0(gumbel, self.seed, self.logit_div)
+        elif self.mz is not None:
+            self.mz.search(gumbel)
         else:
             obs = e.root_obs()
             lg, v = self.evaluator(obs)

@@ -240,3 +240,47 @@ def test_stepwise_selfplay_with_external_evaluator_matches_persistent_kernel():
         a, b = first1[g], first2[g]
         assert a["length"] == b["length"] and np.array_equal(a["actions"], b["actions"]) and a["winner"] == b["winner"], g
         assert np.array_equal(a["values"], b["values"]) and np.array_equal(a["policies"], b["policies"]), g
+
+
+def test_muzero_stepwise_selfplay_matches_persistent_kernel():
+    """MuZero mode: SelfPlayEngine with (initial_fn, recurrent_fn) = E0 as torch ops (hidden states through
+    the device pool kernels) plays the same games as the persistent MuZero-mode kernel."""
+    import torch
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.muzero import TorchE0
+    from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+    from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
+    N, S, G, seed, nseed = 6, 40, 12, 9, 33
+    A = N * N
+    e1 = SearchEngine(G, board_size=N, num_simulations=S, mode="MuZero")
+    sp1 = SelfPlayEngine(e1, "e0", seed=seed, noise_seed=nseed)
+    t1 = TrajectoryStore(e1, extra_slots=64)
+    fin1 = []
+    for _ in range(5):
+        sp1.play(moves_per_game=8, traj=t1); fin1 += t1.harvest()
+    e2 = SearchEngine(G, board_size=N, num_simulations=S, mode="MuZero")
+    e0 = TorchE0(N, seed=seed)
+    sp2 = SelfPlayEngine(e2, (e0.initial, e0.recurrent), noise_seed=nseed)
+    assert sp2.mz is not None
+    t2 = TrajectoryStore(e2, extra_slots=64)
+    counters = np.zeros(G, np.int64)
+    fin2 = []
+    gum = torch.empty((G, A), dtype=torch.float64, device="cuda")
+    for _ in range(40):
+        for g in range(G):
+            e2.fill_gumbel(gum[g], nseed, int((counters[g] * G + g) * A))
+        pol, val, act, _ = sp2.search(gumbel=gum)
+        e2.selfplay_step(pol, val, act, t2, True)
+        counters += 1
+        fin2 += t2.harvest()
+    first1, first2 = {}, {}
+    for r in fin1: first1.setdefault(r["game"], r)
+    for r in fin2: first2.setdefault(r["game"], r)
+    common = sorted(set(first1) & set(first2))
+    assert len(common) >= 6
+    for g in common:
+        a, b = first1[g], first2[g]
+        assert a["length"] == b["length"] and np.array_equal(a["actions"], b["actions"]) and a["winner"] == b["winner"], g
+        assert np.array_equal(a["values"], b["values"]) and np.array_equal(a["policies"], b["policies"]), g
+    with pytest.raises(ValueError):
+        SelfPlayEngine(e2, lambda obs: None)
