@@ -156,9 +156,15 @@ __device__ __forceinline__ float warp_sum_f32(float v)
 }
 // 1/x for x in the float range, to ~1e-15: float reciprocal + two Newton steps (the certified select
 // path only needs ~1e-9; the exact path keeps the correctly rounded division).
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ double rcp_newton(double x)
 {
-    double r = (double)__frcp_rn((float)x);
+    double r = (double)rcp_approx((float)x);                 // ~2^-23, squared twice below
     r = fma(r, fma(-x, r, 1.0), r);
     return fma(r, fma(-x, r, 1.0), r);
 }

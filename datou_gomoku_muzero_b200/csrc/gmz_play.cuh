@@ -324,8 +324,8 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                     node_init_hdr<NC>(p, w, nn, lg, lane);
                 }
                 node_link<NC>(p, w, lp, la, nn, lane);
-                if (lane == 0) {
-                    if (MZ) p.nH[w.nbase + (size_t)nn] = h;
+                if (MZ && lane == 0) p.nH[w.nbase + (size_t)nn] = h;
+                if ((a.trace_a != nullptr || a.trace_d != nullptr) && lane == 0) {      // parity tests only
                     if (a.trace_a) a.trace_a[(size_t)g * p.S + ev] = la;
                     if (a.trace_d) a.trace_d[(size_t)g * p.S + ev] = depth;
                 }

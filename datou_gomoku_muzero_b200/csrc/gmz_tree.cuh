@@ -56,10 +56,10 @@ __device__ __forceinline__ void wg_store_search(const Params &p, int lane, const
 // whatever is on the cell (the reference's in-tree replay has no legality check).
 __device__ __forceinline__ void bb_do_move(u64 &P, u64 &M, int colour, int a, int lane)
 {
-    if (lane == (a >> 6)) {
-        const u64 b = 1ull << (a & 63);
-        if (colour > 0) { P |= b; M &= ~b; } else { M |= b; P &= ~b; }
-    }
+    const u64 b = lane == (a >> 6) ? 1ull << (a & 63) : 0ull;     // branch-free: every lane runs the same few LOP3
+    const u64 bp = colour > 0 ? b : 0ull, bm = b ^ bp;
+    P = (P | bp) & ~bm;
+    M = (M | bm) & ~bp;
 }
 
 // utils.MinMaxStats.normalize (utils.py:16-25) with the range test hoisted.
@@ -563,20 +563,21 @@ __device__ __forceinline__ void node_link(const Params &p, const WG &w, int pare
 
 template <int NC, bool MZ>
 __device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
-                                                bool rng, double rden, int &action, int &child)
+                                                double mn, double rden, int &action, int &child)
 {
     const size_t ni = w.nbase + (size_t)node;
     const int4 h = p.nHdr[ni];
     // the first 8 list entries (two sectors) are fetched alongside the header: 5 of 6 nodes have <= 8 children
+    const int2 *le = p.nList + ni * kListCap + lane;
     int2 e = make_int2(0, 0);
-    if (lane < kListSpec) e = p.nList[ni * kListCap + lane];
+    if (lane < kListSpec) e = *le;
     if (h.w == 0) {
         const int nvis = h.z >> 16, ub = (int)(short)(h.z & 0xffff);
         if (nvis == 0) { action = ub; child = -1; return; }            // nothing visited: the highest logit wins outright
         const bool vis = lane < nvis, un = lane == nvis && ub >= 0, cand = vis || un;
         int key = (ub << 16) | 0xffff, nn = 0; float slg = __int_as_float(h.y); double W = 0.0, rew = 0.0;
         if (vis) {
-            if (lane >= kListSpec) e = p.nList[ni * kListCap + lane];
+            if (lane >= kListSpec) e = *le;
             key = e.x; slg = __int_as_float(e.y);
             const size_t ci = w.nbase + (size_t)(key & 0xffff);
             nn = p.nN[ci]; W = p.nW[ci];
@@ -587,14 +588,15 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         double xs = -INFINITY;
         if (cand) {
             const double q = vis ? rew + p.discount * (W * rcp_newton((double)nn)) : 0.0;
-            double nrm = (q - w.mm_min) * rden;
-            nrm = rng ? fmin(fmax(nrm, 0.0), 1.0) : 0.0;
+            double nrm = (q - mn) * rden;                       // (mn, rden) = (0, 0) while max <= min: normalize() is 0 then
+            const int hi = __double2hiint(nrm);                  // clamp to [0, 1] on the high word
+            nrm = hi < 0 ? 0.0 : (hi >= 0x3ff00000 ? 1.0 : nrm);
             xs = (double)slg + scale * nrm;
         }
         const double mx = warp_max_f64(xs);
         const float ef = cand ? __expf((float)(xs - mx)) : 0.0f;
         const float sum = warp_sum_f32(un ? __fmul_rn(ef, __int_as_float(h.x)) : ef);
-        const float pf = __fmul_rn(ef, __frcp_rn(sum));
+        const float pf = __fmul_rn(ef, rcp_approx(sum));
         const double s = (double)pf - (double)nn * rcp_newton((double)(1 + sumN));
         const u64 k64 = cand ? f64_key(s) : 0ull;
         const u64 mk = warp_max_key(k64);
@@ -645,11 +647,11 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, short *path
     if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
     // MinMaxStats only change in the backup: 1 / (max - min + delta) is the same at every level of this descent
     const bool rng = w.mm_max > w.mm_min;
-    const double rden = rng ? rcp_newton((w.mm_max - w.mm_min) + p.delta) : 0.0;
+    const double rden = rng ? rcp_newton((w.mm_max - w.mm_min) + p.delta) : 0.0, mn = rng ? w.mm_min : 0.0;
     while (node >= 0) {
         if (lane == 0) path[depth] = (short)node;
         int c;
-        select_interior<NC, MZ>(p, w, node, lane, sc, warp_slot, rng, rden, a, c);
+        select_interior<NC, MZ>(p, w, node, lane, sc, warp_slot, mn, rden, a, c);
         if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
         parent = node; node = c; ++depth;
     }
