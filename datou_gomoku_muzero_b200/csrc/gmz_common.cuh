@@ -162,6 +162,13 @@ __device__ __forceinline__ float rcp_approx(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// exp(x) for x <= 0 to ~2^-22 relative: one multiply and MUFU.EX2 (results below 2^-126 flush to 0)
+__device__ __forceinline__ float exp_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmul_rn(x, 1.4426950408889634f)));
+    return r;
+}
 __device__ __forceinline__ double rcp_newton(double x)
 {
     double r = (double)rcp_approx((float)x);                 // ~2^-23, squared twice below

@@ -593,8 +593,9 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
             nrm = hi < 0 ? 0.0 : (hi >= 0x3ff00000 ? 1.0 : nrm);
             xs = (double)slg + scale * nrm;
         }
-        const double mx = warp_max_f64(xs);
-        const float ef = cand ? __expf((float)(xs - mx)) : 0.0f;
+        // any common shift near the maximum will do on this path: take it in float32 (one REDUX)
+        const double mx = (double)f32_unkey(__reduce_max_sync(GMZ_FULL, f32_key(cand ? (float)xs : -INFINITY)));
+        const float ef = cand ? exp_approx((float)(xs - mx)) : 0.0f;
         const float sum = warp_sum_f32(un ? __fmul_rn(ef, __int_as_float(h.x)) : ef);
         const float pf = __fmul_rn(ef, rcp_approx(sum));
         const double s = (double)pf - (double)nn * rcp_newton((double)(1 + sumN));
@@ -695,6 +696,7 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const short *path
 {
     double v = dclip1(value);
     double qmin = INFINITY, qmax = -INFINITY;
+    const bool noclip = p.discount <= 1.0 && p.discount >= -1.0;
 
     for (int hi = depth; hi >= 0; hi -= 32) {
         const int pos = hi - lane;
@@ -707,10 +709,17 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const short *path
         if (act && is_new && MZ) R = reward;
         double myv = 0.0;
         const int cnt = min(32, hi + 1);
-        for (int l = 0; l < cnt; ++l) {
-            const double Rl = MZ ? __shfl_sync(GMZ_FULL, R, l) : 0.0;
-            if (lane == l) myv = v;
-            v = dclip1(__dadd_rn(Rl, __dmul_rn(p.discount, v)));   // value = node.reward + DISCOUNT * value; clip
+        if (!MZ && noclip) {            // no rewards, |discount| <= 1: after the first clip |v| can only shrink
+            for (int l = 0; l < cnt; ++l) {
+                if (lane == l) myv = v;
+                v = __dadd_rn(0.0, __dmul_rn(p.discount, v));
+            }
+        } else {
+            for (int l = 0; l < cnt; ++l) {
+                const double Rl = MZ ? __shfl_sync(GMZ_FULL, R, l) : 0.0;
+                if (lane == l) myv = v;
+                v = dclip1(__dadd_rn(Rl, __dmul_rn(p.discount, v)));   // value = node.reward + DISCOUNT * value; clip
+            }
         }
         if (act) {
             for (int r = 0; r < reps; ++r) {
