@@ -175,8 +175,10 @@ k_select(const __grid_constant__ Params p, T *leaf_obs, int32_t *out_a, int32_t 
     short *path = p.path + (size_t)g * (p.S + 2);
     u64 P = w.P, M = w.M; int colour = w.to_move;
     int lp, la;
-    const int depth = descend<NC, MZ>(p, w, path, s_sel[threadIdx.x >> 5], blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane,
+    int mypath;
+    const int depth = descend<NC, MZ>(p, w, path, mypath, s_sel[threadIdx.x >> 5], blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane,
                                       lp, la, P, M, colour);
+    if (lane < min(depth, 32)) path[lane] = (short)mypath;      // hand the path to k_expand_backup
     if (!MZ && leaf_obs)   // colour is now the player to move at the leaf; last move = la
         obs_write<NC, T>(leaf_obs + (size_t)g * 3 * p.A, p.A, colour > 0 ? P : M, colour > 0 ? M : P, la, lane);
     if (lane == 0) {
@@ -214,8 +216,9 @@ k_expand_backup(const __grid_constant__ Params p, const float *logits, const voi
     node_init_hdr<NC>(p, w, nn, lg, lane);
     node_link<NC>(p, w, lp, la, nn, lane);
     w.num_nodes = nn + 1;
-    backup<MZ>(p, w, path, depth, nn, value, reward, reps, lane);
-    survivor_visit(w, depth, path, nn, la, reps, lane);
+    const int mypath = lane < min(depth, 32) ? (int)path[lane] : 0;
+    backup<MZ>(p, w, path, mypath, depth, nn, value, reward, reps, lane);
+    survivor_visit(w, depth, mypath, nn, la, reps, lane);
     w.sim_count += reps;
     __syncwarp();
     if (halving_ready(p, w)) sequential_halving<MZ>(p, w, lane);

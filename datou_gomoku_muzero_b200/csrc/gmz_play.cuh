@@ -305,7 +305,8 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
             while (w.sim_count < p.S) {
                 u64 P = w.P, M = w.M; int colour = w.to_move;
                 int lp, la;
-                const int depth = descend<NC, MZ>(p, w, path, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
+                int mypath;
+                const int depth = descend<NC, MZ>(p, w, path, mypath, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
                 prefetch_parent_rows<NC>(p, w, lp, lane);
                 // AlphaZero mode: evaluate the replayed board (mcts.py:251-253).  MuZero mode: the learned
                 // dynamics, here E0's recurrent half on the parent's hidden state (mcts.py:336-343).
@@ -331,8 +332,8 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                 }
                 w.num_nodes = nn + 1; ++ev;
                 __syncwarp();
-                backup<MZ>(p, w, path, depth, nn, e0_value(h), MZ ? e0_reward(h) : 0.0, reps, lane);
-                survivor_visit(w, depth, path, nn, la, reps, lane);
+                backup<MZ>(p, w, path, mypath, depth, nn, e0_value(h), MZ ? e0_reward(h) : 0.0, reps, lane);
+                survivor_visit(w, depth, mypath, nn, la, reps, lane);
                 w.sim_count += reps;
                 __syncwarp();
                 if (halving_ready(p, w)) sequential_halving<MZ>(p, w, lane);

@@ -483,7 +483,10 @@ constexpr double kCertEps = 2e-5;     // > 6x the float32 error bound of a proba
 // ub / lub / U / "ambiguous" for the candidate set `cand` (bit i = this lane's action i).  Ambiguous:
 // two different unvisited logits closer than 1e-6 -- float64 rounding of logit + sigma could merge
 // them, so such a node always takes the exact path.
-template <int NC>
+// WITH_U = false: a freshly expanded node.  Its U is never read -- the first select at the node has no
+// visited child and returns `ub` outright, and adding that child rebuilds the summary -- so only ub / lub /
+// amb are computed.
+template <int NC, bool WITH_U>
 __device__ __forceinline__ void unvisited_summary(const float *lg, unsigned cand, int lane, int &ub, float &lub, float &U, bool &amb)
 {
     constexpr int E = 4 * NC;
@@ -519,7 +522,7 @@ template <int NC>
 __device__ __forceinline__ void node_init_hdr(const Params &p, const WG &w, int node, const float *lg, int lane)
 {
     int ub; float lub, U; bool amb;
-    unvisited_summary<NC>(lg, w.vb, lane, ub, lub, U, amb);
+    unvisited_summary<NC, false>(lg, w.vb, lane, ub, lub, U, amb);
     if (lane == 0) p.nHdr[w.nbase + (size_t)node] = hdr_pack(U, lub, ub, 0, amb ? 1 : 0);
 }
 
@@ -557,7 +560,7 @@ __device__ __forceinline__ void node_link(const Params &p, const WG &w, int pare
         if (nvis <= kListCap) p.nList[pi * kListCap + (nvis - 1)] = make_int2((action << 16) | new_node, __float_as_int(la));
     }
     int ub; float lub, U; bool amb;
-    unvisited_summary<NC>(lg, w.vb & ~vm, lane, ub, lub, U, amb);
+    unvisited_summary<NC, true>(lg, w.vb & ~vm, lane, ub, lub, U, amb);
     if (lane == 0) p.nHdr[pi] = hdr_pack(U, lub, ub, min(nvis, 32767), (amb || nvis > kFastMaxVisited) ? 1 : 0);
 }
 
@@ -636,7 +639,7 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
 // then interior selection until an unexpanded child is reached.  In AlphaZero mode the path
 // is replayed on the bitboards while descending (mcts.py:236-248).  Returns depth (edges).
 template <int NC, bool MZ>
-__device__ __forceinline__ int descend(const Params &p, const WG &w, short *path, SelSmem &sc, int warp_slot, int lane,
+__device__ __forceinline__ int descend(const Params &p, const WG &w, short *path, int &mypath, SelSmem &sc, int warp_slot, int lane,
                                        int &leaf_parent, int &leaf_action, u64 &P, u64 &M, int &colour)
 {
     const unsigned key = lane < w.n_surv ? (((unsigned)w.s_n << 5) | (unsigned)lane) : 0xffffffffu;
@@ -644,13 +647,16 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, short *path
     int a = __shfl_sync(GMZ_FULL, w.s_act, bl);
     int node = __shfl_sync(GMZ_FULL, w.s_child, bl);
     int parent = 0, depth = 1;
-    if (lane == 0) path[0] = 0;
+    // the path root..leaf-parent lives in registers: lane d holds the node at depth d (depths >= 32 -- never seen
+    // at 400 simulations -- spill to the global `path`)
+    mypath = 0;
     if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
     // MinMaxStats only change in the backup: 1 / (max - min + delta) is the same at every level of this descent
     const bool rng = w.mm_max > w.mm_min;
     const double rden = rng ? rcp_newton((w.mm_max - w.mm_min) + p.delta) : 0.0, mn = rng ? w.mm_min : 0.0;
     while (node >= 0) {
-        if (lane == 0) path[depth] = (short)node;
+        if (depth < 32) mypath = lane == depth ? node : mypath;
+        else if (lane == 0) path[depth] = (short)node;
         int c;
         select_interior<NC, MZ>(p, w, node, lane, sc, warp_slot, mn, rden, a, c);
         if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
@@ -691,7 +697,7 @@ __device__ __forceinline__ void node_write_row(const Params &p, const WG &w, int
 // `depth` is the new node.  Lane l of a 32-wide segment owns position hi - l.  Also maintains
 // the survivor visit counts and the MinMaxStats (min/max are order-independent).
 template <bool MZ>
-__device__ __forceinline__ void backup(const Params &p, WG &w, const short *path, int depth, int new_node,
+__device__ __forceinline__ void backup(const Params &p, WG &w, const short *path, int mypath, int depth, int new_node,
                                        double value, double reward, int reps, int lane)
 {
     double v = dclip1(value);
@@ -702,7 +708,8 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const short *path
         const int pos = hi - lane;
         const bool act = pos >= 0;
         const bool is_new = pos == depth;
-        const int node = act ? (is_new ? new_node : (int)path[pos]) : 0;
+        const int pn = __shfl_sync(GMZ_FULL, mypath, pos & 31);
+        const int node = act ? (is_new ? new_node : (pos < 32 ? pn : (int)path[pos])) : 0;
         const size_t ni = w.nbase + (size_t)node;
         int n = 0; double W = 0.0, R = 0.0;
         if (act && !is_new) { n = p.nN[ni]; W = p.nW[ni]; if (MZ) R = p.nR[ni]; }
@@ -793,11 +800,12 @@ __device__ __forceinline__ void sequential_halving(const Params &p, WG &w, int l
 
 // After a backup through root child `first_node` (depth-1 node on the path): bump the
 // survivor's visit count (and record the child id if it was just created).
-__device__ __forceinline__ void survivor_visit(WG &w, int depth, const short *path, int new_node, int leaf_action, int reps, int lane)
+__device__ __forceinline__ void survivor_visit(WG &w, int depth, int mypath, int new_node, int leaf_action, int reps, int lane)
 {
+    const int first = __shfl_sync(GMZ_FULL, mypath, 1);        // every lane takes part: no shuffle behind a short-circuit
     bool hit;
     if (depth == 1) hit = lane < w.n_surv && w.s_act == leaf_action;
-    else hit = lane < w.n_surv && w.s_child == (int)path[1];
+    else hit = lane < w.n_surv && w.s_child == first;
     if (hit) { w.s_n += reps; if (depth == 1) w.s_child = new_node; }
 }
 

@@ -285,3 +285,39 @@ def test_muzero_fused_search_matches_oracle(N, S, G):
     r = oracle.search(cfg, boards[1], players[1], last[1], mc[1], gumbel[1], trace=True)
     n = r["n_evals"]
     assert np.array_equal(ta[1].cpu().numpy()[:n], r["leaf_actions"]) and np.array_equal(td[1].cpu().numpy()[:n], r["leaf_depths"])
+
+
+@pytest.mark.parametrize("mode", ["AlphaZero", "MuZero"])
+def test_deep_paths_match_oracle(mode):
+    """Peaked logits (logit_div = 2) grow chains deeper than one warp (> 32 edges): the descent path then
+    spills from registers to the global path buffer.  Fused and stepwise kernels vs the oracle, with the
+    per-simulation (leaf action, depth) traces."""
+    import torch
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from oracle import oracle
+    N, S, G, seed, div = 9, 300, 12, 5, 2
+    A = N * N
+    rs = np.random.RandomState(4)
+    boards = np.zeros((G, A), np.int8); players = np.ones(G, np.int8)
+    last = np.full(G, -1, np.int32); mc = np.zeros(G, np.int32)
+    gumbel = rs.gumbel(0, 1, (G, A))
+    m = 0 if mode == "AlphaZero" else 1
+    cfg = oracle.make_config(board_size=N, num_simulations=S, eval_seed=seed, logit_div=div, mode=m)
+    opol, oval, oact, ovis = oracle.search_batch(cfg, boards, players, last, mc, gumbel)
+    refs = [oracle.search(cfg, boards[g], 1, -1, 0, gumbel[g], trace=True) for g in range(G)]
+    if mode == "AlphaZero":          # (MuZero mode backs every leaf up k times: its trees stay shallow)
+        assert max(int(r["leaf_depths"][:r["n_evals"]].max()) for r in refs) > 40
+    eng = SearchEngine(G, board_size=N, num_simulations=S, mode=mode)
+    runs = [("fused", lambda: eng.search_e0(torch.from_numpy(gumbel).cuda(), seed, div, trace=True))]
+    if mode == "AlphaZero":
+        runs.append(("stepwise", lambda: eng.search_stepwise_e0(torch.from_numpy(gumbel).cuda(), seed, div, trace=True)))
+    for name, run in runs:
+        eng.set_roots(boards, players, last, mc)
+        ta, td = run()
+        pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
+        assert np.array_equal(vis, ovis) and np.array_equal(act, oact) and np.array_equal(val, oval), name
+        if ta is not None:
+            for g in range(G):
+                n = refs[g]["n_evals"]
+                assert np.array_equal(ta[g].cpu().numpy()[:n], refs[g]["leaf_actions"]), (name, g)
+                assert np.array_equal(td[g].cpu().numpy()[:n], refs[g]["leaf_depths"]), (name, g)
