@@ -316,10 +316,20 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                 const int nn = w.num_nodes;
                 {   // evaluate + leaf.expand fused: logits go straight into the new node's row
                     float lg[4 * NC];
+                    const u64 zb = h + (u64)(4 * lane + 1) * E0_GOLD;       // h + (a + 1) * G for this lane's first action
+                    if (a.inv_div != 0.0f) {                                 // logit_div a power of two: exact reciprocal
 #pragma unroll kExpUnroll
-                    for (int i = 0; i < 4 * NC; ++i) {      // lightly unrolled: two independent hash chains in flight
-                        const int ac = 128 * (i >> 2) + 4 * lane + (i & 3);
-                        lg[i] = ac < p.A ? e0_logit(h, ac, a.logit_div, a.inv_div) : 0.0f;
+                        for (int i = 0; i < 4 * NC; ++i) {  // lightly unrolled: two independent hash chains in flight
+                            const int off = 128 * (i >> 2) + (i & 3);
+                            const int k = (int)(mix64(zb + (u64)off * E0_GOLD) >> 58);
+                            lg[i] = off + 4 * lane < p.A ? __fmul_rn((float)(k - 32), a.inv_div) : 0.0f;
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int i = 0; i < 4 * NC; ++i) {
+                            const int ac = 128 * (i >> 2) + 4 * lane + (i & 3);
+                            lg[i] = ac < p.A ? e0_logit(h, ac, a.logit_div, a.inv_div) : 0.0f;
+                        }
                     }
                     node_write_row<NC>(p, w, nn, lg, lane);
                     node_init_hdr<NC>(p, w, nn, lg, lane);

@@ -505,10 +505,10 @@ __device__ __forceinline__ void unvisited_summary(const float *lg, unsigned cand
 #pragma unroll
     for (int i = 0; i < E; ++i) {
         const float d = __fsub_rn(v[i], lub);                          // <= 0, -inf for non-candidates (exp -> 0)
-        u = __fadd_rn(u, __expf(d));
+        if (WITH_U) u = __fadd_rn(u, exp_approx(d));
         am |= (d < 0.0f) && (d > -1e-6f);
     }
-    U = warp_sum_f32(u);
+    U = WITH_U ? warp_sum_f32(u) : 0.0f;
     amb = __any_sync(GMZ_FULL, am);
 }
 
@@ -546,13 +546,16 @@ __device__ __forceinline__ void node_link(const Params &p, const WG &w, int pare
     }
     const int4 h = p.nHdr[pi];
     const int owner = (action & 127) >> 2, idx = 4 * (action >> 7) + (action & 3);
-    float la = 0.0f;
-    if (lane == owner) {
+    if (lane == owner) vm |= 1u << idx;
+    float la = __int_as_float(h.y);                       // the new child is normally the summary's best unvisited action
+    if (action != (int)(short)(h.z & 0xffff)) {           // (not when the exact path broke a near-tie differently)
+        la = 0.0f;
+        if (lane == owner) {
 #pragma unroll
-        for (int i = 0; i < E; ++i) if (i == idx) la = lg[i];
-        vm |= 1u << idx;
+            for (int i = 0; i < E; ++i) if (i == idx) la = lg[i];
+        }
+        la = __shfl_sync(GMZ_FULL, la, owner);
     }
-    la = __shfl_sync(GMZ_FULL, la, owner);
     __syncwarp();
     const int nvis = (h.z >> 16) + 1;
     if (lane == 0) {
