@@ -214,6 +214,14 @@ def cpu_baseline_leg(budget_s=10.0):
             "config1": config1_leg()}
 
 
+def own_bytes_per_sim(d, n_vis=3.2):
+    """Bytes one simulation of THIS kernel has to move: per interior select a 16 B header,
+    n_vis list entries (8 B) and n_vis child (N, W) pairs (12 B); the new node's logits + child rows written;
+    the parent's logits + child rows read once for its refreshed summary, header and list entry written; the
+    backup's read-modify-write of (N, W) along the path."""
+    return (d - 1) * (16 + 20 * n_vis) + (4 * A + 2 * A + 16) + (4 * A + 2 * A + 16 + 16 + 8 + 2) + 24 * (d + 1)
+
+
 def net_leg(eng, dev, peaks):
     """Same workload with the REAL network as evaluator (E1): GomokuNetEZ 8 blocks x 128 filters,
     random init (torch.manual_seed(0)), bf16, BatchNorm folded, cuDNN fused conv ops, CUDA graph;
@@ -464,16 +472,24 @@ def run_ours(args):
                      "frac": achieved / peak, "traffic": traffic, "kernel_ms_per_step": kernel_ms,
                      "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(mean_depth),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                     "note": "one simulation in flight per game (bit-exact visit counts) => latency/occupancy bound, not HBM bound"},
+                     "own_bytes_per_sim": own_bytes_per_sim(mean_depth),
+                     "own_frac": own_bytes_per_sim(mean_depth) * (moves_done / args.steps) * (S - 1) / (kernel_ms * 1e-3) / 1e9 / peak,
+                     "note": "achieved/frac use SURVEY 8d's bytes per simulation, i.e. the reference algorithm's dense row reads; the "
+                             "certified select does not make those reads (own_bytes_per_sim = what this kernel must move, own_frac = "
+                             "its share of the HBM peak; measured DRAM traffic in `traffic`): the kernel is latency/issue bound"},
         "clocks": sampler.summary(),
     }
     if not args.no_net and world == 1:          # single-GPU context measurement
         try:
+            torch.cuda.empty_cache()
             out["net"] = net_leg(eng, dev, peaks)
         except Exception as ex:      # the headline (fixed evaluator) stands on its own
             out["net"] = {"error": repr(ex)[:200]}
     if not args.no_net and world == 1:
         try:
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()      # cuDNN autotuning sizes its workspace by what the caching allocator has released
             out["muzero"] = muzero_leg(dev, peaks, G)
         except Exception as ex:
             out["muzero"] = {"error": repr(ex)[:200]}
