@@ -218,7 +218,9 @@ __device__ __noinline__ u64 play_root(const Params &p, const PlayArgs &a, WG &w,
 #ifndef GMZ_PLAY_MIN_CTAS
 #define GMZ_PLAY_MIN_CTAS 6
 #endif
+#ifndef GMZ_PLAY_WARPS
 #define GMZ_PLAY_WARPS 4
+#endif
 
 template <int NC>
 __device__ __noinline__ u64 play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane)

@@ -11,10 +11,14 @@ from oracle import oracle
 ap = argparse.ArgumentParser()
 ap.add_argument("--batches", type=int, default=25)
 ap.add_argument("--games", type=int, default=4096)
+ap.add_argument("--board", type=int, default=15)
+ap.add_argument("--sims", type=int, default=400)
+ap.add_argument("--top", type=int, default=16)
+ap.add_argument("--mode", default="AlphaZero", choices=["AlphaZero", "MuZero"])
 args = ap.parse_args()
-N, S, K, G = 15, 400, 16, args.games
+N, S, K, G = args.board, args.sims, args.top, args.games
 A = N * N
-eng = SearchEngine(G, board_size=N, num_simulations=S, num_top_actions=K)
+eng = SearchEngine(G, board_size=N, num_simulations=S, num_top_actions=K, mode=args.mode)
 rs = np.random.RandomState(2026)
 tot = bad_vis = bad_act = bad_val = 0
 worst_pol = 0.0
@@ -33,13 +37,14 @@ for b in range(args.batches):
     eng.set_roots(boards, players, last, mc)
     eng.search_e0(torch.from_numpy(gum).cuda(), seed, div)
     pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
-    cfg = oracle.make_config(board_size=N, num_simulations=S, num_top_actions=K, eval_seed=seed, logit_div=div)
+    cfg = oracle.make_config(board_size=N, num_simulations=S, num_top_actions=K, eval_seed=seed, logit_div=div,
+                             mode=0 if args.mode == "AlphaZero" else 1)
     opol, oval, oact, ovis = oracle.search_batch(cfg, boards, players, last, mc, gum)
     tot += G
     bad_vis += int((vis != ovis).any(axis=1).sum()); bad_act += int((act != oact).sum()); bad_val += int((val != oval).sum())
     worst_pol = max(worst_pol, float(np.abs(pol - opol).max()))
     print(f"batch {b}: seed {seed} logit_div {div}: cumulative {tot} searches, visit mismatches {bad_vis}, move {bad_act}, value {bad_val}", flush=True)
-print(json.dumps({"searches": tot, "simulations": tot * S, "config": "15x15, 400 sims, K=16, random positions 0..224 stones, logit_div in {16,4,2}",
+print(json.dumps({"searches": tot, "simulations": tot * S, "config": f"{N}x{N}, {S} sims, K={K}, {args.mode} mode, random positions 0..{A - 1} stones, logit_div in {{16,4,2}}",
                   "visit_count_mismatches": bad_vis, "move_mismatches": bad_act, "value_bit_mismatches": bad_val,
                   "max_abs_policy_diff": worst_pol, "seconds": time.time() - t0,
                   "select_counters": dict(zip(("fallback_to_exact", "certified", "certified_but_exact_differs"), eng.select_counters()))}))
