@@ -326,6 +326,38 @@ def muzero_leg(dev, peaks, G):
                                "unit": "GB/s", "frac": scatter_bytes / scatter_ms / 1e6 / peak, "bytes": scatter_bytes}}
 
 
+def weight_broadcast_leg(dev, rank, world):
+    """BASELINE configs[3]: the trainer rank publishes GomokuNetEZ's weights to every self-play rank
+    (`model_update_queue` in the reference, workers.py:587-593) as one NCCL broadcast of a flat buffer."""
+    import torch
+    import torch.distributed as dist
+    from datou_gomoku_muzero_b200.config import Config
+    from datou_gomoku_muzero_b200.network import GomokuNetEZ
+    from datou_gomoku_muzero_b200.parallel import FlatWeights
+    torch.manual_seed(100 + rank)                       # every rank starts from DIFFERENT weights
+    cfg = Config(BOARD_SIZE=N, ACTION_SPACE_SIZE=A, NUM_RES_BLOCKS=8, NUM_FILTERS=128, HEAD_HIDDEN_DIM=64)
+    net = GomokuNetEZ(cfg).to(dev)
+    fw = FlatWeights(net)                               # parameters become views into one flat buffer per dtype
+    nbytes = fw.nbytes
+    for _ in range(2):
+        fw.broadcast(src=0)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fw.broadcast(src=0)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    chk = torch.stack([p.detach().double().sum() for p in net.parameters()]).sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return {"what": "GomokuNetEZ 8x128 parameters + buffers living in one flat buffer per dtype (parallel.FlatWeights), "
+                    "in-place NCCL broadcast from rank 0",
+            "bytes": int(nbytes), "ms": float(t.item()), "gb_per_s": nbytes / (float(t.item()) * 1e-3) / 1e9,
+            "ranks_identical_after": bool(lo.item() == hi.item())}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -431,6 +463,7 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    bcast = weight_broadcast_leg(dev, rank, world) if world > 1 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -479,6 +512,8 @@ def run_ours(args):
                              "its share of the HBM peak; measured DRAM traffic in `traffic`): the kernel is latency/issue bound"},
         "clocks": sampler.summary(),
     }
+    if bcast is not None:
+        out["weight_broadcast"] = bcast
     if not args.no_net and world == 1:          # single-GPU context measurement
         try:
             torch.cuda.empty_cache()

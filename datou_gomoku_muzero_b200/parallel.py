@@ -45,6 +45,40 @@ def broadcast_weights(module: torch.nn.Module, src: int = 0, group=None):
     return module
 
 
+class FlatWeights:
+    """A module's parameters and buffers re-homed as views into ONE flat tensor per dtype, so that publishing
+    the weights (`model_update_queue`, workers.py:587-593) is a single in-place broadcast per dtype with no
+    packing or unpacking kernels -- the link, not ~300 small copies, sets the time.  The module keeps working
+    as before (its tensors now alias the flat buffers); every rank must wrap an identically shaped module."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.module = module
+        groups = {}
+        for t in list(module.parameters()) + list(module.buffers()):
+            groups.setdefault((t.dtype, t.device), []).append(t)
+        self.flats = []
+        for (dtype, device), ts in groups.items():
+            flat = torch.empty(sum(t.numel() for t in ts), dtype=dtype, device=device)
+            off = 0
+            for t in ts:
+                n = t.numel()
+                view = flat[off:off + n].view(t.shape)
+                with torch.no_grad():
+                    view.copy_(t)
+                t.data = view                     # parameter / buffer now aliases the flat storage
+                off += n
+            self.flats.append(flat)
+
+    @property
+    def nbytes(self):
+        return sum(f.numel() * f.element_size() for f in self.flats)
+
+    def broadcast(self, src: int = 0, group=None):
+        for f in self.flats:
+            dist.broadcast(f, src=src, group=group)
+        return self.module
+
+
 def max_over_ranks(value: float, device=None, group=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)

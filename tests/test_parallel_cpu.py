@@ -26,6 +26,19 @@ def _worker(rank, world, port, q):
     before = torch.cat([p.reshape(-1) for p in net.parameters()]).clone()
     parallel.broadcast_weights(net, src=0)
     after = torch.cat([p.reshape(-1) for p in net.parameters()])
+    # the same through the persistent flat buffer: perturb rank 1, publish again, forward still works
+    fw = parallel.FlatWeights(net)
+    if rank == 1:
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(1.0)
+    fw.broadcast(src=0)
+    flat_after = torch.cat([p.reshape(-1) for p in net.parameters()])
+    assert torch.equal(flat_after, after) and all(p.data_ptr() >= f.data_ptr() for p in net.parameters() for f in fw.flats[:1])
+    net.eval()
+    with torch.no_grad():
+        out = net.initial_inference(torch.zeros(2, 3, 6, 6))
+    assert out[0].shape == (2, 36) and torch.isfinite(out[0]).all()
     lo, hi = parallel.shard_games(9, world, rank)
     recs = [dict(game=g, length=3 + g, winner=1, actions=np.arange(3 + g)) for g in range(lo, hi)]
     got = parallel.gather_finished_games(recs, dst=0)
