@@ -142,10 +142,10 @@ __device__ __forceinline__ double row_softmax(const Params &p, const WG &w, cons
     return __ddiv_rn(1.0, sum);
 }
 
-// Per-warp scratch for the visited children of the node being scored.  Nodes almost always have
-// <= 32 visited children: then child k is handed to lane k through 256 bytes of shared memory and
-// scored in registers.  The rare bigger node takes select_interior_big, which loops over this
-// warp's slice of a global overflow area (Params::sel_overflow).
+// Per-warp scratch of the EXACT select (select_interior_exact / _big; the certified path below needs no
+// shared memory).  Nodes almost always have <= 32 visited children: then child k is handed to lane k through
+// 256 bytes of shared memory and scored in registers.  The rare bigger node takes select_interior_big,
+// which loops over this warp's slice of a global overflow area (Params::sel_overflow).
 // Shared memory is kept small on purpose: it is carved out of the same 228 KB as the L1 cache
 // that serves the node-header gathers.
 #ifndef GMZ_EXP_UNROLL
@@ -154,7 +154,7 @@ __device__ __forceinline__ double row_softmax(const Params &p, const WG &w, cons
 constexpr int kExpUnroll = GMZ_EXP_UNROLL;
 struct SelSmem {
     double dx[256];                // dense pass: element i of lane l at [32*i + l] (NC <= 2; NC = 3 keeps registers)
-    int key[32];                   // visited child k -> (action << 16) | child node id   (fast path: <= 32 children)
+    int key[32];                   // visited child k -> (action << 16) | child node id   (<= 32 children)
     float lg[32];                  // logit of that action
 };
 // Working pointers for one select call (shared or global, chosen per node).
@@ -182,7 +182,7 @@ __device__ __forceinline__ void sel_unpack(int packed, int &action, int &child)
     child = (packed & 0xffff) == 0xffff ? -1 : (packed & 0xffff);
 }
 
-// _select_action at an interior node (mcts.py:106-117):
+// The exact _select_action at an interior node (mcts.py:106-117):
 // argmax_a  softmax(logits + sigma)[a] - N(a) / (1 + sum_b N(b))   over the ROOT-valid actions.
 // Most of a node's A children are unvisited (q = 0, N = 0, same sigma): those are scored in a
 // branch-free dense pass from the row alone.  The few visited children are compacted into
