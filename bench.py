@@ -415,7 +415,15 @@ def run_ours(args):
     m0, f0 = eng.play_counters()
     barrier()
     ev0.record()
-    sp.play(moves_per_game=args.steps, traj=traj)
+    # trajectory slots are recycled by the host between launches and a game ends about every 85 moves, so a
+    # long run is cut into launches of <= 48 steps with a (policy-free) harvest in between -- inside the timing
+    remaining = args.steps
+    while remaining > 0:
+        n = min(48, remaining)
+        sp.play(moves_per_game=n, traj=traj)
+        remaining -= n
+        if remaining > 0:
+            traj.harvest(copy_policies=False)
     ev1.record()
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
@@ -491,7 +499,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD,
                    "games_per_gpu": G, "board": N, "num_simulations": S, "num_top_actions": K_TOP,
                    "roots": "staggered synthetic mid-game positions (0..159 stones), finished games restarted in-kernel",
-                   "step": "G self-play moves; the K timed steps run as one persistent ticketed launch of K*G moves",
+                   "step": "G self-play moves; the K timed steps run as one persistent ticketed launch of K*G moves (K <= 48; longer runs: one launch per 48 steps)",
                    "l2": "node pools (2.6 GB per GPU) exceed the 126 MB L2; no explicit flush",
                    "mean_leaf_depth": mean_depth},
         "e2e": {"value": sims_per_step * e2e_steps / e2e_s, "unit": "sims/s",
