@@ -554,7 +554,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-net", action="store_true", help="skip the real-network (E1) leg")
-    ap.add_argument("--e2e-depth", type=int, default=4, help="host batches in flight in the end-to-end leg")
+    ap.add_argument("--e2e-depth", type=int, default=6, help="host batches in flight in the end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
