@@ -43,27 +43,30 @@ class GomokuGame:
         self.current_player = -self.current_player
         self.move_count += 1
 
-    def _run(self, r, c, dr, dc, colour):
-        k, n = 0, self.board_size
-        for i in range(1, self.n_in_row + 2):           # at most n_in_row + 1 stones each way
-            rr, cc = r + i * dr, c + i * dc
-            if 0 <= rr < n and 0 <= cc < n and self.board[rr, cc] == colour:
-                k += 1
-            else:
-                break
-        return k
+    def _longest_through(self, r, c, colour):
+        """Length of the run of `colour` through (r, c) in each of the 4 directions, looking at most
+        n_in_row + 1 cells each way (game.py:41-55) -- one fancy-indexed window per direction."""
+        n, reach = self.board_size, self.n_in_row + 1
+        k = np.arange(-reach, reach + 1)
+        best = 0
+        for dr, dc in _DIRS:
+            rr, cc = r + k * dr, c + k * dc
+            inside = (rr >= 0) & (rr < n) & (cc >= 0) & (cc < n)
+            same = np.zeros(k.size, dtype=bool)
+            same[inside] = self.board[rr[inside], cc[inside]] == colour
+            gaps_before = np.flatnonzero(~same[:reach])
+            gaps_after = np.flatnonzero(~same[reach + 1:])
+            lo = gaps_before[-1] + 1 if gaps_before.size else 0
+            hi = reach + 1 + (gaps_after[0] if gaps_after.size else reach)
+            best = max(best, int(hi - lo))
+        return best
 
     def check_win(self, move=None):
-        if move is None:
-            if self.last_move is None:
-                return False
-            move = self.last_move
-        r, c = move
-        colour = self.board[r, c]
-        if colour == 0:
+        where = self.last_move if move is None else move
+        if where is None:
             return False
-        return any(1 + self._run(r, c, dr, dc, colour) + self._run(r, c, -dr, -dc, colour) >= self.n_in_row
-                   for dr, dc in _DIRS)
+        colour = self.board[where[0], where[1]]
+        return bool(colour != 0 and self._longest_through(where[0], where[1], colour) >= self.n_in_row)
 
     def get_game_ended(self):
         if self.check_win():
