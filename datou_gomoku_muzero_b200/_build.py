@@ -4,16 +4,20 @@ from __future__ import annotations
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libgmz.so")
 SOURCES = ["gmz_engine.cu", "gmz_per.cu", "gmz_slices.cu", "gmz_tactics.cu", "gmz_hidden.cu"]
-HEADERS = ["gmz_common.cuh", "gmz_tree.cuh", "gmz_play.cuh", os.path.join("..", "..", "include", "gmz.h")]
-# -fmad=false: the search's float64 arithmetic must round once per operation, like the
-# reference's Python floats; an FMA would change visit counts.
+# the persistent play kernel: one object per (MuZero mode, float32 accumulation), built in parallel
+PLAY_SOURCE = "gmz_play_inst.cu"
+PLAY_VARIANTS = [(0, 0), (0, 1), (1, 0), (1, 1)]
+HEADERS = ["gmz_common.cuh", "gmz_tree.cuh", "gmz_play.cuh", "gmz_internal.h", os.path.join("..", "..", "include", "gmz.h")]
+# -fmad=false: the search's float64 / float32 arithmetic must round once per operation, like the
+# reference's Python floats / NumPy scalars; an FMA would change visit counts.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
-              "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
+              "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 # The same library with every certified select decision re-derived by the exact float64 path and the
@@ -26,7 +30,7 @@ def _stale(so=SO) -> bool:
     if not os.path.exists(so):
         return True
     t = os.path.getmtime(so)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + [PLAY_SOURCE] + HEADERS]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
@@ -35,7 +39,17 @@ def build(force: bool = False, verbose: bool = False, verify: bool = False) -> s
     so = SO_VERIFY if verify else SO
     if not force and not _stale(so):
         return so
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc, *NVCC_FLAGS, *(["-DGMZ_VERIFY_FAST"] if verify else []), *(["-Xptxas", "-v"] if verbose else []), "-o", so, *srcs]
-    subprocess.check_call(cmd)
+    objdir = os.path.join(HERE, "build", "verify" if verify else "release")
+    os.makedirs(objdir, exist_ok=True)
+    common = [nvcc, *NVCC_FLAGS, *(["-DGMZ_VERIFY_FAST"] if verify else []), *(["-Xptxas", "-v"] if verbose else [])]
+    jobs = []
+    for s in SOURCES:
+        jobs.append((common + ["-c", os.path.join(CSRC, s), "-o", os.path.join(objdir, s[:-3] + ".o")]))
+    for mz, f32 in PLAY_VARIANTS:
+        jobs.append(common + [f"-DGMZ_PLAY_MZ={mz}", f"-DGMZ_PLAY_F32={f32}", "-c", os.path.join(CSRC, PLAY_SOURCE),
+                              "-o", os.path.join(objdir, f"gmz_play_mz{mz}_f{f32}.o")])
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        list(ex.map(subprocess.check_call, jobs))
+    objs = [j[-1] for j in jobs]
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", so, *objs])
     return so

@@ -10,13 +10,14 @@ SO = os.environ.get("GMZ_LIB") or os.path.join(HERE, "libgmz.so")   # GMZ_LIB: d
 
 GMZ_MODE_ALPHAZERO, GMZ_MODE_MUZERO = 0, 1
 GMZ_F32, GMZ_F64, GMZ_BF16 = 0, 1, 2
+GMZ_ACCUM_F64, GMZ_ACCUM_F32 = 0, 1
 GMZ_WINNER_NONE = 2
 
 
 class GmzConfig(C.Structure):
     _fields_ = [("board_size", C.c_int32), ("n_in_row", C.c_int32), ("num_simulations", C.c_int32),
                 ("num_top_actions", C.c_int32), ("mode", C.c_int32), ("num_games", C.c_int32),
-                ("max_moves", C.c_int32), ("reserved", C.c_int32),
+                ("max_moves", C.c_int32), ("accum_dtype", C.c_int32),
                 ("c_visit", C.c_double), ("c_scale", C.c_double), ("minmax_delta", C.c_double),
                 ("discount", C.c_double)]
 

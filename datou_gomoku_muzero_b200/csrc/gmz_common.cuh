@@ -63,6 +63,8 @@ struct Params {
     int m_of_phase[GMZ_MAX_PHASES];      // current_num_top_actions after p halvings (mcts.py:168-169)
     int extra_of_phase[GMZ_MAX_PHASES];  // int(extra_visit) of phase p            (mcts.py:173-180)
     double c_visit, c_scale, delta, discount;
+    float discf, deltaf;                 // float32(DISCOUNT), float32(VALUE_MINMAX_DELTA): float32 accumulation mode
+    int f32acc, pad0;                    // gmz_config.accum_dtype == GMZ_F32
     GState *gs;
     float *logits;   // [G*S][AP]  node.policy_logits
     short *child;    // [G*S][AP]  node.children -> node index, -1 = absent
@@ -205,11 +207,21 @@ __device__ __forceinline__ void warp_argmax_highidx(double &s, int &a)
 __device__ __forceinline__ u64 shfl_u64(u64 v, int src) { return __shfl_sync(GMZ_FULL, v, src); }
 
 // ---------------------------------------------------------------------------------------------
-// E0, the fixed deterministic evaluator: splitmix64-style hashing of the observation.
+// E0, the fixed deterministic evaluator (device twin of tests/golden/e0_py.py):
+//   h0 = mix64(seed ^ GOLD)
+//   h  = mix64( XOR_w [ mix64((own_w ^ h0) + (2w+1) GOLD) ^ mix64((opp_w ^ h0) + (2w+2) GOLD) ] + (last+1) CV )
+//   x_a = 32-bit hash of (lo32(h) ^ hi32(h)) + (a+1) * 0x9E3779B1   (two multiplies, high bits used)
+//   quantised (logit_div > 0): logit = ((x_a >> 26) - 32) / logit_div,  value = ((h >> 40) % 33 - 16) / 16,
+//                              reward = (((h >> 16) & 0xFFFFFF) % 5 - 2) / 16
+//   dense (logit_div = 0):     logit = ((x_a >> 8) - 2^23) 2^-21,  value = ((h >> 40) - 2^23) 2^-23,
+//                              reward = (((h >> 16) & 0xFFFFFF) - 2^23) 2^-25
+//   MuZero mode: h_child = mix64(h_parent + (a+1) CA)
+// The per-word terms are XOR-combined, so lane w hashes word w and a REDUX finishes the board hash: two
+// dependent mix64 per evaluation instead of 2*NW + 2.
 #define E0_GOLD 0x9E3779B97F4A7C15ULL
 #define E0_CV 0xD1B54A32D192ED03ULL
 #define E0_CA 0x8CB92BA72F3D8DD7ULL
-#define E0_CR 0xA24BAED4963EE407ULL
+#define E0_GOLD32 0x9E3779B1u
 
 __host__ __device__ __forceinline__ u64 mix64(u64 z)
 {
@@ -218,21 +230,61 @@ __host__ __device__ __forceinline__ u64 mix64(u64 z)
     z ^= z >> 31;
     return z;
 }
+// How E0's integers become numbers (host-prepared, passed by value to the kernels).
+struct E0Spec {
+    u64 h0;            // mix64(seed ^ GOLD)
+    int lshift, lbias; // k = (x >> lshift) - lbias
+    float lmul, ldiv;  // logit = lmul != 0 ? k * lmul : k / ldiv   (lmul = exact reciprocal of a power-of-two divisor)
+    int dense;         // 0: quantised value / reward, 1: dense 24-bit value / reward
+    int pad;
+};
+static inline E0Spec e0_spec(u64 seed, int logit_div)
+{
+    E0Spec s;
+    s.h0 = mix64(seed ^ E0_GOLD); s.pad = 0;
+    if (logit_div > 0) {
+        s.lshift = 26; s.lbias = 32; s.dense = 0; s.ldiv = (float)logit_div;
+        s.lmul = (logit_div & (logit_div - 1)) == 0 ? 1.0f / (float)logit_div : 0.0f;
+    } else { s.lshift = 8; s.lbias = 1 << 23; s.dense = 1; s.ldiv = 1.0f; s.lmul = 4.76837158203125e-07f; /* 2^-21 */ }
+    return s;
+}
+__device__ __forceinline__ u64 warp_xor_u64(u64 v)
+{
+    const unsigned lo = __reduce_xor_sync(GMZ_FULL, (unsigned)v), hi = __reduce_xor_sync(GMZ_FULL, (unsigned)(v >> 32));
+    return ((u64)hi << 32) | lo;
+}
 // own_w / opp_w: lane w holds word w of the plane.  All lanes return the same hash.
-__device__ __forceinline__ u64 e0_hash_planes(u64 seed, u64 own_w, u64 opp_w, int nw, int last)
+__device__ __forceinline__ u64 e0_hash_planes(u64 h0, u64 own_w, u64 opp_w, int nw, int last, int lane)
 {
-    u64 h = mix64(seed ^ E0_GOLD);
-    for (int w = 0; w < nw; ++w) h = mix64(h ^ shfl_u64(own_w, w));
-    for (int w = 0; w < nw; ++w) h = mix64(h ^ shfl_u64(opp_w, w));
-    return mix64(h ^ (u64)(long long)(last + 1));
+    u64 t = 0;
+    if (lane < nw)
+        t = mix64((own_w ^ h0) + (u64)(2 * lane + 1) * E0_GOLD) ^ mix64((opp_w ^ h0) + (u64)(2 * lane + 2) * E0_GOLD);
+    return mix64(warp_xor_u64(t) + (u64)(long long)(last + 1) * E0_CV);
 }
-// logit = (k - 32) / logit_div; when logit_div is a power of two (inv_div != 0) the product with
-// the exact reciprocal is the same float, without the division sequence.
-__device__ __forceinline__ float e0_logit(u64 h, int a, float logit_div, float inv_div)
+__device__ __forceinline__ unsigned e0_seed32(u64 h) { return (unsigned)h ^ (unsigned)(h >> 32); }
+__device__ __forceinline__ unsigned e0_action_hash(unsigned x)      // x = seed32 + (a + 1) * E0_GOLD32
 {
-    const int k = (int)(mix64(h + (u64)(a + 1) * E0_GOLD) >> 58);
-    return inv_div != 0.0f ? __fmul_rn((float)(k - 32), inv_div) : __fdiv_rn((float)(k - 32), logit_div);
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    return x;
 }
-__device__ __forceinline__ u64 e0_child_hidden(u64 h_parent, int action) { return mix64(h_parent ^ mix64((u64)(action + 1) + E0_CA)); }
-__device__ __forceinline__ double e0_reward(u64 h) { return (double)((int)((mix64(h ^ E0_CR) >> 40) % 5) - 2) / 16.0; }
-__device__ __forceinline__ double e0_value(u64 h) { return (double)((int)((mix64(h ^ E0_CV) >> 40) % 33) - 16) / 16.0; }
+__device__ __forceinline__ float e0_logit_of(unsigned x, const E0Spec &e)
+{
+    const float k = (float)((int)(x >> e.lshift) - e.lbias);
+    return e.lmul != 0.0f ? __fmul_rn(k, e.lmul) : __fdiv_rn(k, e.ldiv);
+}
+__device__ __forceinline__ float e0_logit(u64 h, int a, const E0Spec &e)
+{
+    return e0_logit_of(e0_action_hash(e0_seed32(h) + (unsigned)(a + 1) * E0_GOLD32), e);
+}
+__device__ __forceinline__ u64 e0_child_hidden(u64 h_parent, int action) { return mix64(h_parent + (u64)(action + 1) * E0_CA); }
+__device__ __forceinline__ double e0_value(u64 h, int dense)
+{
+    const int vk = (int)((h >> 40) & 0xFFFFFFull);
+    return dense ? (double)(vk - (1 << 23)) * 1.1920928955078125e-07 : (double)(vk % 33 - 16) * 0.0625;
+}
+__device__ __forceinline__ double e0_reward(u64 h, int dense)
+{
+    const int rk = (int)((h >> 16) & 0xFFFFFFull);
+    return dense ? (double)(rk - (1 << 23)) * 2.98023223876953125e-08 : (double)(rk % 5 - 2) * 0.0625;
+}

@@ -5,7 +5,11 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../../include/gmz.h"
+#include <atomic>
+#include <mutex>
+#include <unordered_set>
+
+#include "gmz_internal.h"
 #include "gmz_tree.cuh"
 #include "gmz_play.cuh"
 
@@ -13,26 +17,33 @@
 #define CTA_THREADS (32 * WARPS_PER_CTA)
 
 static thread_local char g_err[512] = "";
-static int fail(const char *fmt, const char *a = "")
+int gmz_fail(const char *fmt, const char *a)
 {
     snprintf(g_err, sizeof(g_err), fmt, a);
     return 1;
 }
 extern "C" void gmz_set_error_(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
-static int check_launch(const char *what)
+int gmz_check_launch(const char *what)
 {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e)); return 1; }
     return 0;
 }
+#define fail gmz_fail
+#define check_launch gmz_check_launch
 
-struct gmz_engine {
-    gmz_config cfg;
-    Params p;
-    int NC;
-    size_t bytes;
-    void *workspace;
-};
+// Live engine handles.  Threading contract (as the reference's engines, SURVEY 8b: "one engine per process,
+// single-threaded, not re-entrant"): calls on DIFFERENT engines may run concurrently from different host
+// threads; calls on ONE engine must be serialised by the caller.  gmz_destroy on a handle that is not (or no
+// longer) live is a no-op returning 0; every other entry point rejects such a handle.
+static std::mutex g_live_mu;
+static std::unordered_set<const gmz_engine *> g_live;
+static bool engine_live(const gmz_engine *e)
+{
+    if (!e) return false;
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    return g_live.count(e) != 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // root positions
@@ -146,7 +157,7 @@ k_root_expand(Params p, const float *logits, const void *values, int vdtype, con
     if (lane == 0) p.gs[g].leaf_depth = 0;
 }
 
-template <int NC, bool MZ, typename T>
+template <int NC, bool MZ, bool F32, typename T>
 __global__ void __launch_bounds__(CTA_THREADS)
 k_select(const __grid_constant__ Params p, T *leaf_obs, int32_t *out_a, int32_t *out_b, int32_t *out_c, int32_t *out_depth, int32_t *out_reps)
 {
@@ -176,7 +187,7 @@ k_select(const __grid_constant__ Params p, T *leaf_obs, int32_t *out_a, int32_t 
     u64 P = w.P, M = w.M; int colour = w.to_move;
     int lp, la;
     int mypath;
-    const int depth = descend<NC, MZ>(p, w, path, mypath, s_sel[threadIdx.x >> 5], blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane,
+    const int depth = descend<NC, MZ, F32>(p, w, path, mypath, s_sel[threadIdx.x >> 5], blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane,
                                       lp, la, P, M, colour);
     if (lane < min(depth, 32)) path[lane] = (short)mypath;      // hand the path to k_expand_backup
     if (!MZ && leaf_obs)   // colour is now the player to move at the leaf; last move = la
@@ -194,7 +205,7 @@ k_select(const __grid_constant__ Params p, T *leaf_obs, int32_t *out_a, int32_t 
     }
 }
 
-template <int NC, bool MZ>
+template <int NC, bool MZ, bool F32>
 __global__ void __launch_bounds__(CTA_THREADS)
 k_expand_backup(const __grid_constant__ Params p, const float *logits, const void *values, const void *rewards, int vdtype)
 {
@@ -217,16 +228,16 @@ k_expand_backup(const __grid_constant__ Params p, const float *logits, const voi
     node_link<NC>(p, w, lp, la, nn, lane);
     w.num_nodes = nn + 1;
     const int mypath = lane < min(depth, 32) ? (int)path[lane] : 0;
-    backup<MZ>(p, w, path, mypath, depth, nn, value, reward, reps, lane);
+    backup<MZ, F32>(p, w, path, mypath, depth, nn, value, reward, reps, lane);
     survivor_visit(w, depth, mypath, nn, la, reps, lane);
     w.sim_count += reps;
     __syncwarp();
-    if (halving_ready(p, w)) sequential_halving<MZ>(p, w, lane);
+    if (halving_ready(p, w)) sequential_halving<MZ, F32>(p, w, lane);
     wg_store_search(p, lane, w);
     if (lane == 0) p.gs[g].leaf_depth = 0;
 }
 
-template <int NC, bool MZ>
+template <int NC, bool MZ, bool F32>
 __global__ void __launch_bounds__(CTA_THREADS)
 k_finalize(const __grid_constant__ Params p, double *policy, double *value, int32_t *action, int32_t *visits)
 {
@@ -235,7 +246,7 @@ k_finalize(const __grid_constant__ Params p, double *policy, double *value, int3
     if (g >= p.G) return;
     WG w; wg_load(p, g, lane, w);
     double v; int a;
-    finalize_root<NC, MZ>(p, w, lane, policy ? policy + (size_t)g * p.A : nullptr, visits ? visits + (size_t)g * p.A : nullptr,
+    finalize_root<NC, MZ, F32>(p, w, lane, policy ? policy + (size_t)g * p.A : nullptr, visits ? visits + (size_t)g * p.A : nullptr,
                           s_nvis[wi], p.pyset + ((size_t)blockIdx.x * WARPS_PER_CTA + wi) * 4096, v, a);
     if (lane == 0) { if (value) value[g] = v; if (action) action[g] = a; }
 }
@@ -244,7 +255,7 @@ k_finalize(const __grid_constant__ Params p, double *policy, double *value, int3
 // E0 evaluator kernels
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CTA_THREADS)
-k_e0_eval_obs(const float *obs, int B, int N, u64 seed, float logit_div, float inv_div, float *logits, double *values)
+k_e0_eval_obs(const float *obs, int B, int N, E0Spec e0, float *logits, double *values)
 {
     const int lane = threadIdx.x & 31, b = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -263,9 +274,9 @@ k_e0_eval_obs(const float *obs, int B, int N, u64 seed, float logit_div, float i
         }
         if (lane == w) { own = ow; opp = pw; }
     }
-    const u64 h = e0_hash_planes(seed, own, opp, nw, last);
-    for (int a = lane; a < A; a += 32) logits[(size_t)b * A + a] = e0_logit(h, a, logit_div, inv_div);
-    if (lane == 0) values[b] = e0_value(h);
+    const u64 h = e0_hash_planes(e0.h0, own, opp, nw, last, lane);
+    for (int a = lane; a < A; a += 32) logits[(size_t)b * A + a] = e0_logit(h, a, e0);
+    if (lane == 0) values[b] = e0_value(h, e0.dense);
 }
 
 // Gumbel(0,1) = -log(-log(u)), u from a counter-based splitmix64 stream, 53-bit mantissa in (0,1).
@@ -375,8 +386,6 @@ __global__ void __launch_bounds__(CTA_THREADS) k_game_step(Params p, const int32
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-// exact reciprocal of a power-of-two divisor, else 0 (kernel then divides)
-static float pow2_inv(int d) { return (d > 0 && (d & (d - 1)) == 0) ? 1.0f / (float)d : 0.0f; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Layout { size_t gs, logits, child, nN, nW, nR, nH, path, pyset, selov, ctl, hdr, list, total; };
@@ -388,8 +397,10 @@ static int validate(const gmz_config *c)
     if (c->num_simulations < 1 || c->num_simulations > 32767) return fail("num_simulations out of range (1..32767)");
     if (c->num_top_actions < 1 || c->num_top_actions > GMZ_MAX_TOP_ACTIONS) return fail("num_top_actions out of range (1..32)");
     if (c->mode != GMZ_MODE_ALPHAZERO && c->mode != GMZ_MODE_MUZERO) return fail("unknown mode");
+    if (c->accum_dtype != GMZ_ACCUM_F64 && c->accum_dtype != GMZ_ACCUM_F32) return fail("unknown accum_dtype");
     if (c->num_games < 1) return fail("num_games must be >= 1");
     if (c->n_in_row < 1 || c->n_in_row > 14) return fail("n_in_row out of range (1..14)");
+    if (c->max_moves < 0) return fail("max_moves must be >= 0");
     return 0;
 }
 static Layout make_layout(const gmz_config *c)
@@ -431,12 +442,15 @@ extern "C" int gmz_create(const gmz_config *cfg, void *workspace, size_t workspa
     if (!workspace || workspace_bytes < L.total) return fail("workspace too small");
     if ((uintptr_t)workspace % 256) return fail("workspace must be 256-byte aligned");
     gmz_engine *e = (gmz_engine *)calloc(1, sizeof(gmz_engine));
-    e->cfg = *cfg; e->workspace = workspace; e->bytes = L.total;
+    if (!e) return fail("out of host memory");
+    e->magic = GMZ_ENGINE_MAGIC; e->cfg = *cfg; e->workspace = workspace; e->bytes = L.total;
+    cudaGetDevice(&e->device);
     Params &p = e->p;
     p.G = cfg->num_games; p.N = cfg->board_size; p.A = p.N * p.N; p.S = cfg->num_simulations; p.K = cfg->num_top_actions;
     p.NW = (p.A + 63) / 64; e->NC = (p.A + 127) / 128; p.AP = 128 * e->NC; p.mode = cfg->mode;
     p.n_in_row = cfg->n_in_row; p.max_moves = cfg->max_moves > 0 ? cfg->max_moves : p.A;
     p.c_visit = cfg->c_visit; p.c_scale = cfg->c_scale; p.delta = cfg->minmax_delta; p.discount = cfg->discount;
+    p.discf = (float)cfg->discount; p.deltaf = (float)cfg->minmax_delta; p.f32acc = cfg->accum_dtype == GMZ_ACCUM_F32; p.pad0 = 0;
     // sequential-halving schedule (mcts.py:158-181), same double arithmetic as the reference
     {
         const int n = p.S, m = p.K;
@@ -463,43 +477,67 @@ extern "C" int gmz_create(const gmz_config *cfg, void *workspace, size_t workspa
     cudaError_t err = cudaMemsetAsync(base + L.gs, 0, (size_t)p.G * sizeof(GState), (cudaStream_t)stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(base + L.ctl, 0, sizeof(PlayCtl), (cudaStream_t)stream);
     if (err != cudaSuccess) { free(e); return fail("cudaMemsetAsync: %s", cudaGetErrorString(err)); }
+    { std::lock_guard<std::mutex> lk(g_live_mu); g_live.insert(e); }
     *out = e;
     return 0;
 }
 
-extern "C" int gmz_destroy(gmz_engine *e) { free(e); return 0; }
+// Idempotent: destroying a handle that is not live (already destroyed, or never created) does nothing.
+extern "C" int gmz_destroy(gmz_engine *e)
+{
+    if (!e) return 0;
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        if (!g_live.erase(e)) return 0;
+    }
+    e->magic = 0;
+    free(e);
+    return 0;
+}
 
 #define GRID(e) dim3(((e)->p.G + WARPS_PER_CTA - 1) / WARPS_PER_CTA), dim3(CTA_THREADS)
+#define LIVE(e, name) do { if (!engine_live(e)) return fail("%s: invalid or destroyed engine handle", name); } while (0)
 #define DISPATCH_NC(e, ...)                                      \
     switch ((e)->NC) {                                           \
         case 1: { constexpr int NC = 1; __VA_ARGS__; } break;    \
         case 2: { constexpr int NC = 2; __VA_ARGS__; } break;    \
         default: { constexpr int NC = 3; __VA_ARGS__; } break;   \
     }
+// NC x (MuZero mode) x (float32 accumulation)
+#define DISPATCH_ALL(e, ...)                                                                      \
+    do {                                                                                          \
+        const int mz_ = (e)->p.mode == GMZ_MODE_MUZERO, f_ = (e)->p.f32acc;                       \
+        if (mz_ && f_) { constexpr bool MZ = true, F32 = true; DISPATCH_NC(e, __VA_ARGS__) }      \
+        else if (mz_) { constexpr bool MZ = true, F32 = false; DISPATCH_NC(e, __VA_ARGS__) }      \
+        else if (f_) { constexpr bool MZ = false, F32 = true; DISPATCH_NC(e, __VA_ARGS__) }       \
+        else { constexpr bool MZ = false, F32 = false; DISPATCH_NC(e, __VA_ARGS__) }              \
+    } while (0)
 
 extern "C" int gmz_set_roots(gmz_engine *e, const int8_t *boards, const int8_t *players, const int32_t *last_moves,
                              const int32_t *move_counts, gmz_stream stream)
 {
-    if (!e || !boards || !players || !last_moves || !move_counts) return fail("gmz_set_roots: null argument");
+    LIVE(e, "gmz_set_roots");
+    if (!boards || !players || !last_moves || !move_counts) return fail("gmz_set_roots: null argument");
     k_set_roots<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, boards, players, last_moves, move_counts);
     return check_launch("k_set_roots");
 }
 extern "C" int gmz_games_reset(gmz_engine *e, const uint8_t *mask, gmz_stream stream)
 {
-    if (!e) return fail("gmz_games_reset: null engine");
+    LIVE(e, "gmz_games_reset");
     k_games_reset<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, mask);
     return check_launch("k_games_reset");
 }
 extern "C" int gmz_get_roots(gmz_engine *e, int8_t *boards, int8_t *players, int32_t *last_moves, int32_t *move_counts,
                              gmz_stream stream)
 {
-    if (!e) return fail("gmz_get_roots: null engine");
+    LIVE(e, "gmz_get_roots");
     k_get_roots<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, boards, players, last_moves, move_counts);
     return check_launch("k_get_roots");
 }
 extern "C" int gmz_root_obs(gmz_engine *e, void *obs, int obs_dtype, gmz_stream stream)
 {
-    if (!e || !obs) return fail("gmz_root_obs: null argument");
+    LIVE(e, "gmz_root_obs");
+    if (!obs) return fail("gmz_root_obs: null argument");
     if (obs_dtype != GMZ_F32) return fail("gmz_root_obs: only GMZ_F32 observations are supported");
     DISPATCH_NC(e, k_root_obs<NC, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)obs));
     return check_launch("k_root_obs");
@@ -507,7 +545,8 @@ extern "C" int gmz_root_obs(gmz_engine *e, void *obs, int obs_dtype, gmz_stream 
 extern "C" int gmz_root_expand(gmz_engine *e, const float *logits, const void *values, int value_dtype,
                                const double *gumbel, gmz_stream stream)
 {
-    if (!e || !logits || !values || !gumbel) return fail("gmz_root_expand: null argument");
+    LIVE(e, "gmz_root_expand");
+    if (!logits || !values || !gumbel) return fail("gmz_root_expand: null argument");
     if (value_dtype != GMZ_F32 && value_dtype != GMZ_F64) return fail("gmz_root_expand: bad value dtype");
     DISPATCH_NC(e, k_root_expand<NC><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, logits, values, value_dtype, gumbel));
     return check_launch("k_root_expand");
@@ -515,42 +554,45 @@ extern "C" int gmz_root_expand(gmz_engine *e, const float *logits, const void *v
 extern "C" int gmz_select(gmz_engine *e, void *leaf_obs, int obs_dtype, int32_t *out_leaf_action, int32_t *out_leaf_depth,
                           gmz_stream stream)
 {
-    if (!e) return fail("gmz_select: null engine");
+    LIVE(e, "gmz_select");
     if (e->p.mode != GMZ_MODE_ALPHAZERO) return fail("gmz_select: engine is in MuZero mode, use gmz_select_mz");
     if (obs_dtype != GMZ_F32) return fail("gmz_select: only GMZ_F32 observations are supported");
-    DISPATCH_NC(e, k_select<NC, false, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)leaf_obs, out_leaf_action,
-                                                                                     nullptr, nullptr, out_leaf_depth, nullptr));
+    if (e->p.f32acc) {
+        DISPATCH_NC(e, k_select<NC, false, true, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)leaf_obs, out_leaf_action,
+                                                                                            nullptr, nullptr, out_leaf_depth, nullptr));
+    } else {
+        DISPATCH_NC(e, k_select<NC, false, false, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)leaf_obs, out_leaf_action,
+                                                                                             nullptr, nullptr, out_leaf_depth, nullptr));
+    }
     return check_launch("k_select");
 }
 extern "C" int gmz_select_mz(gmz_engine *e, int32_t *out_parent_slot, int32_t *out_action, int32_t *out_child_slot,
                              int32_t *out_leaf_depth, int32_t *out_reps, gmz_stream stream)
 {
-    if (!e) return fail("gmz_select_mz: null engine");
+    LIVE(e, "gmz_select_mz");
     if (e->p.mode != GMZ_MODE_MUZERO) return fail("gmz_select_mz: engine is in AlphaZero mode, use gmz_select");
-    DISPATCH_NC(e, k_select<NC, true, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, nullptr, out_parent_slot, out_action,
-                                                                                    out_child_slot, out_leaf_depth, out_reps));
+    if (e->p.f32acc) {
+        DISPATCH_NC(e, k_select<NC, true, true, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, nullptr, out_parent_slot, out_action,
+                                                                                           out_child_slot, out_leaf_depth, out_reps));
+    } else {
+        DISPATCH_NC(e, k_select<NC, true, false, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, nullptr, out_parent_slot, out_action,
+                                                                                            out_child_slot, out_leaf_depth, out_reps));
+    }
     return check_launch("k_select_mz");
 }
 extern "C" int gmz_expand_backup(gmz_engine *e, const float *logits, const void *values, const void *rewards,
                                  int value_dtype, gmz_stream stream)
 {
-    if (!e || !logits || !values) return fail("gmz_expand_backup: null argument");
+    LIVE(e, "gmz_expand_backup");
+    if (!logits || !values) return fail("gmz_expand_backup: null argument");
     if (value_dtype != GMZ_F32 && value_dtype != GMZ_F64) return fail("gmz_expand_backup: bad value dtype");
-    if (e->p.mode == GMZ_MODE_MUZERO) {
-        DISPATCH_NC(e, k_expand_backup<NC, true><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, logits, values, rewards, value_dtype));
-    } else {
-        DISPATCH_NC(e, k_expand_backup<NC, false><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, logits, values, rewards, value_dtype));
-    }
+    DISPATCH_ALL(e, k_expand_backup<NC, MZ, F32><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, logits, values, rewards, value_dtype));
     return check_launch("k_expand_backup");
 }
 extern "C" int gmz_finalize(gmz_engine *e, double *policy, double *value, int32_t *action, int32_t *visits, gmz_stream stream)
 {
-    if (!e) return fail("gmz_finalize: null engine");
-    if (e->p.mode == GMZ_MODE_MUZERO) {
-        DISPATCH_NC(e, k_finalize<NC, true><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, policy, value, action, visits));
-    } else {
-        DISPATCH_NC(e, k_finalize<NC, false><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, policy, value, action, visits));
-    }
+    LIVE(e, "gmz_finalize");
+    DISPATCH_ALL(e, k_finalize<NC, MZ, F32><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, policy, value, action, visits));
     return check_launch("k_finalize");
 }
 extern "C" int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint64_t seed, int logit_div,
@@ -559,32 +601,16 @@ extern "C" int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint
     if (!obs || !logits || !values) return fail("gmz_e0_eval_obs: null argument");
     if (batch <= 0) return 0;
     if (board_size < 1 || board_size > GMZ_MAX_BOARD) return fail("gmz_e0_eval_obs: board_size out of range");
+    if (logit_div < 0) return fail("gmz_e0_eval_obs: logit_div must be >= 0 (0 = dense logits)");
     k_e0_eval_obs<<<(batch + WARPS_PER_CTA - 1) / WARPS_PER_CTA, CTA_THREADS, 0, (cudaStream_t)stream>>>(
-        obs, batch, board_size, (u64)seed, (float)logit_div, pow2_inv(logit_div), logits, values);
+        obs, batch, board_size, e0_spec((u64)seed, logit_div), logits, values);
     return check_launch("k_e0_eval_obs");
 }
-// launch the ticketed play kernel: grid = what fits on the GPU at once (persistent), capped by the game count
-template <int NC, bool MZ>
-static int launch_play_t(gmz_engine *e, const PlayArgs &a, cudaStream_t st)
-{
-    static int occ_cache[4] = {0, 0, 0, 0};
-    if (!occ_cache[NC]) {
-        int occ = 0, dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_play_e0<NC, MZ>, 32 * GMZ_PLAY_WARPS, 0);
-        occ_cache[NC] = (occ > 0 ? occ : 1) * (sms > 0 ? sms : 148);
-    }
-    int grid = (e->p.G + GMZ_PLAY_WARPS - 1) / GMZ_PLAY_WARPS;
-    if (grid > occ_cache[NC]) grid = occ_cache[NC];
-    if (cudaMemsetAsync(&e->p.ctl->next_ticket, 0, 2 * sizeof(unsigned long long), st) != cudaSuccess) return fail("cudaMemsetAsync(ctl)");
-    k_play_e0<NC, MZ><<<grid, 32 * GMZ_PLAY_WARPS, 0, st>>>(e->p, a);
-    return check_launch("k_play_e0");
-}
-template <int NC>
 static int launch_play(gmz_engine *e, const PlayArgs &a, cudaStream_t st)
 {
-    return e->p.mode == GMZ_MODE_MUZERO ? launch_play_t<NC, true>(e, a, st) : launch_play_t<NC, false>(e, a, st);
+    const bool mz = e->p.mode == GMZ_MODE_MUZERO, f = e->p.f32acc != 0;
+    if (mz) return f ? gmz_launch_play_mz1_f1(e, a, st) : gmz_launch_play_mz1_f0(e, a, st);
+    return f ? gmz_launch_play_mz0_f1(e, a, st) : gmz_launch_play_mz0_f0(e, a, st);
 }
 static TrajDev traj_dev(const gmz_traj *t)
 {
@@ -609,18 +635,19 @@ static int check_traj(const gmz_engine *e, const gmz_traj *t)
 extern "C" int gmz_search_e0(gmz_engine *e, const double *gumbel, uint64_t seed, int logit_div,
                              int32_t *trace_leaf_action, int32_t *trace_leaf_depth, gmz_stream stream)
 {
-    if (!e || !gumbel) return fail("gmz_search_e0: null argument");
+    LIVE(e, "gmz_search_e0");
+    if (!gumbel) return fail("gmz_search_e0: null argument");
+    if (logit_div < 0) return fail("gmz_search_e0: logit_div must be >= 0 (0 = dense logits)");
     PlayArgs a; memset(&a, 0, sizeof(a));
-    a.eval_seed = seed; a.logit_div = (float)logit_div; a.inv_div = pow2_inv(logit_div);
+    a.e0 = e0_spec((u64)seed, logit_div);
     a.total_tickets = e->p.G; a.do_step = 0; a.gumbel_in = gumbel;
     a.trace_a = trace_leaf_action; a.trace_d = trace_leaf_depth;
-    int rc = 0;
-    DISPATCH_NC(e, rc = launch_play<NC>(e, a, (cudaStream_t)stream));
-    return rc;
+    return launch_play(e, a, (cudaStream_t)stream);
 }
 extern "C" int gmz_traj_init(gmz_engine *e, const gmz_traj *traj, gmz_stream stream)
 {
-    if (!e || !traj) return fail("gmz_traj_init: null argument");
+    LIVE(e, "gmz_traj_init");
+    if (!traj) return fail("gmz_traj_init: null argument");
     if (check_traj(e, traj)) return 1;
     const int n = traj->n_slots > e->p.G ? traj->n_slots : e->p.G;
     k_traj_init<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(e->p, traj_dev(traj));
@@ -629,42 +656,45 @@ extern "C" int gmz_traj_init(gmz_engine *e, const gmz_traj *traj, gmz_stream str
 extern "C" int gmz_selfplay_e0(gmz_engine *e, const gmz_traj *traj, uint64_t eval_seed, int logit_div, uint64_t noise_seed,
                                int64_t total_moves, int restart, gmz_stream stream)
 {
-    if (!e) return fail("gmz_selfplay_e0: null engine");
+    LIVE(e, "gmz_selfplay_e0");
     if (traj && check_traj(e, traj)) return 1;
+    if (logit_div < 0) return fail("gmz_selfplay_e0: logit_div must be >= 0 (0 = dense logits)");
     if (total_moves <= 0) return 0;
     PlayArgs a; memset(&a, 0, sizeof(a));
-    a.eval_seed = eval_seed; a.noise_seed = noise_seed; a.logit_div = (float)logit_div; a.inv_div = pow2_inv(logit_div);
+    a.e0 = e0_spec((u64)eval_seed, logit_div); a.noise_seed = noise_seed;
     a.total_tickets = total_moves; a.do_step = 1; a.restart = restart ? 1 : 0; a.use_traj = traj ? 1 : 0;
     a.traj = traj_dev(traj);
-    int rc = 0;
-    DISPATCH_NC(e, rc = launch_play<NC>(e, a, (cudaStream_t)stream));
-    return rc;
+    return launch_play(e, a, (cudaStream_t)stream);
 }
 extern "C" int gmz_selfplay_step(gmz_engine *e, const gmz_traj *traj, const double *policy, const double *value,
                                  const int32_t *action, int restart, int32_t *out_winner, gmz_stream stream)
 {
-    if (!e || !action) return fail("gmz_selfplay_step: null argument");
+    LIVE(e, "gmz_selfplay_step");
+    if (!action) return fail("gmz_selfplay_step: null argument");
     if (traj && (check_traj(e, traj) || !policy || !value)) return traj && policy && value ? 1 : fail("gmz_selfplay_step: policy/value required with a trajectory store");
     k_selfplay_step<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, traj_dev(traj), traj ? 1 : 0, restart ? 1 : 0, policy, value, action, out_winner);
     return check_launch("k_selfplay_step");
 }
 extern "C" int gmz_selfplay_unpark(gmz_engine *e, const gmz_traj *traj, gmz_stream stream)
 {
-    if (!e || !traj) return fail("gmz_selfplay_unpark: null argument");
+    LIVE(e, "gmz_selfplay_unpark");
+    if (!traj) return fail("gmz_selfplay_unpark: null argument");
     if (check_traj(e, traj)) return 1;
     k_unpark<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, traj_dev(traj));
     return check_launch("k_unpark");
 }
 extern "C" int gmz_play_counters(gmz_engine *e, uint64_t *out2, gmz_stream stream)
 {
-    if (!e || !out2) return fail("gmz_play_counters: null argument");
+    LIVE(e, "gmz_play_counters");
+    if (!out2) return fail("gmz_play_counters: null argument");
     cudaError_t err = cudaMemcpyAsync(out2, &e->p.ctl->moves_played, 4 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     if (err != cudaSuccess) return fail("gmz_play_counters: %s", cudaGetErrorString(err));
     return 0;
 }
 extern "C" int gmz_select_counters(gmz_engine *e, uint64_t *out3, gmz_stream stream)
 {
-    if (!e || !out3) return fail("gmz_select_counters: null argument");
+    LIVE(e, "gmz_select_counters");
+    if (!out3) return fail("gmz_select_counters: null argument");
     cudaError_t err = cudaMemcpyAsync(out3, &e->p.ctl->sel_fallback, 3 * sizeof(uint64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
     if (err != cudaSuccess) return fail("gmz_select_counters: %s", cudaGetErrorString(err));
     return 0;
@@ -678,7 +708,8 @@ extern "C" int gmz_fill_gumbel(double *out, size_t n, uint64_t seed, uint64_t of
 }
 extern "C" int gmz_game_step(gmz_engine *e, const int32_t *actions, int32_t *out_winner, gmz_stream stream)
 {
-    if (!e || !actions) return fail("gmz_game_step: null argument");
+    LIVE(e, "gmz_game_step");
+    if (!actions) return fail("gmz_game_step: null argument");
     k_game_step<<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, actions, out_winner);
     return check_launch("k_game_step");
 }

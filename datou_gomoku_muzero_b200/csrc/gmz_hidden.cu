@@ -14,8 +14,8 @@
 #include <stdint.h>
 #include "../../include/gmz.h"
 
-extern "C" int gmz_set_error_(const char *msg);
-static int hd_fail(const char *m) { return gmz_set_error_(m); }
+extern "C" void gmz_set_error_(const char *msg);   // defined in gmz_engine.cu (feeds gmz_last_error)
+static int hd_fail(const char *m) { gmz_set_error_(m); return 1; }
 
 namespace {
 

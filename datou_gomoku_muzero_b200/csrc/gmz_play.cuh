@@ -15,7 +15,7 @@
 // Runs on one lane, only when the maximum visit count is not unique.  Restates
 // Objects/setobject.c (set_add_entry / set_table_resize / set_insert_clean, CPython >= 3.7).
 // `table` = 4096 shorts of scratch (two 2048-entry halves).
-__device__ __noinline__ int pyset_first_max(const u64 *vw, int A, const short *nvis, int maxn, short *table)
+static __device__ __noinline__ int pyset_first_max(const u64 *vw, int A, const short *nvis, int maxn, short *table)
 {
     int mask = 7, fill = 0;
     for (int i = 0; i < 8; ++i) table[i] = -1;
@@ -60,7 +60,7 @@ __device__ __noinline__ int pyset_first_max(const u64 *vw, int A, const short *n
 // Decision phase (mcts.py:271-280): improved policy at the root, root value, most-visited action.
 // policy / visits point at this game's [A] output rows (may be null).  nvis: 128*NC shorts of
 // per-warp shared scratch; table: 4096 shorts of per-warp global scratch (tie-break only).
-template <int NC, bool MZ>
+template <int NC, bool MZ, bool F32>
 __device__ __noinline__ void finalize_root(const Params &p, WG &w, int lane, double *policy, int32_t *visits,
                                            short *nvis, short *table, double &value, int &action)
 {
@@ -74,9 +74,9 @@ __device__ __noinline__ void finalize_root(const Params &p, WG &w, int lane, dou
     }
     wg_valid_bits<NC>(p, w, lane);
     Row<NC> r;
-    row_load<NC, MZ>(p, w, 0, lane, r);
+    row_load<NC, MZ, F32>(p, w, 0, lane, r);
     double x[4 * NC];
-    const double inv = row_softmax<NC>(p, w, r, x);
+    const double inv = row_softmax<NC, F32>(p, w, r, x);
     int bn = -1, ba = 0x7fffffff;
 #pragma unroll
     for (int i = 0; i < 4 * NC; ++i) {
@@ -102,7 +102,8 @@ __device__ __noinline__ void finalize_root(const Params &p, WG &w, int lane, dou
         if (lane == 0) best = pyset_first_max(vw, p.A, nvis, maxn, table);
         best = __shfl_sync(GMZ_FULL, best, 0);
     }
-    value = __ddiv_rn(p.nW[w.nbase], (double)p.nN[w.nbase]);
+    value = F32 ? (double)__fdiv_rn((float)p.nW[w.nbase], (float)p.nN[w.nbase])       // root.get_value(), mcts.py:273
+                : __ddiv_rn(p.nW[w.nbase], (double)p.nN[w.nbase]);
     action = best;
     __syncwarp();
 }
@@ -188,8 +189,8 @@ struct TrajDev {
 };
 
 struct PlayArgs {
-    u64 eval_seed, noise_seed;
-    float logit_div, inv_div;
+    E0Spec e0;            // the fixed evaluator (seed, quantised / dense heads)
+    u64 noise_seed;
     long long total_tickets;
     int do_step;          // 1: self-play move (decision + record + do_move + restart); 0: search only
     int restart;          // self-play: restart finished games inside the launch
@@ -226,22 +227,22 @@ template <int NC>
 __device__ __noinline__ u64 play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane)
 {
     const int g = w.g;
-    const u64 h = e0_hash_planes(a.eval_seed, w.to_move > 0 ? w.P : w.M, w.to_move > 0 ? w.M : w.P, p.NW, w.last_move);
+    const u64 h = e0_hash_planes(a.e0.h0, w.to_move > 0 ? w.P : w.M, w.to_move > 0 ? w.M : w.P, p.NW, w.last_move, lane);
     const u64 nctr = ((u64)noise_ctr * (u64)p.G + (u64)g) * (u64)p.A;
     float lg[4 * NC]; double gum[4 * NC];
 #pragma unroll 1
     for (int i = 0; i < 4 * NC; ++i) {
         const int ac = 128 * (i >> 2) + 4 * lane + (i & 3);
-        lg[i] = ac < p.A ? e0_logit(h, ac, a.logit_div, a.inv_div) : 0.0f;
+        lg[i] = ac < p.A ? e0_logit(h, ac, a.e0) : 0.0f;
         gum[i] = ac < p.A ? (a.gumbel_in ? a.gumbel_in[(size_t)g * p.A + ac] : gumbel_at(noise_mixed, nctr + ac)) : 0.0;
     }
-    root_init<NC>(p, w, lg, gum, e0_value(h), lane);
+    root_init<NC>(p, w, lg, gum, e0_value(h, a.e0.dense), lane);
     return h;
 }
 
 // One search (mcts.py:197-280) -- and in self-play mode one whole move (workers.py:168-189) --
 // per ticket, one game per warp, E0 inlined.
-template <int NC, bool MZ>
+template <int NC, bool MZ, bool F32>
 __global__ void __launch_bounds__(32 * GMZ_PLAY_WARPS, GMZ_PLAY_MIN_CTAS)
 k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
 {
@@ -308,29 +309,29 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                 u64 P = w.P, M = w.M; int colour = w.to_move;
                 int lp, la;
                 int mypath;
-                const int depth = descend<NC, MZ>(p, w, path, mypath, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
+                const int depth = descend<NC, MZ, F32>(p, w, path, mypath, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
                 prefetch_parent_rows<NC>(p, w, lp, lane);
                 // AlphaZero mode: evaluate the replayed board (mcts.py:251-253).  MuZero mode: the learned
                 // dynamics, here E0's recurrent half on the parent's hidden state (mcts.py:336-343).
                 const u64 h = MZ ? e0_child_hidden(p.nH[w.nbase + (size_t)lp], la)
-                                 : e0_hash_planes(a.eval_seed, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la);
+                                 : e0_hash_planes(a.e0.h0, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la, lane);
                 const int reps = MZ ? w.n_surv : 1;            // MuZero: len(selected) identical selections -> that many backups
                 const int nn = w.num_nodes;
                 {   // evaluate + leaf.expand fused: logits go straight into the new node's row
                     float lg[4 * NC];
-                    const u64 zb = h + (u64)(4 * lane + 1) * E0_GOLD;       // h + (a + 1) * G for this lane's first action
-                    if (a.inv_div != 0.0f) {                                 // logit_div a power of two: exact reciprocal
-#pragma unroll kExpUnroll
-                        for (int i = 0; i < 4 * NC; ++i) {  // lightly unrolled: two independent hash chains in flight
+                    const unsigned xb = e0_seed32(h) + (unsigned)(4 * lane + 1) * E0_GOLD32;   // seed + (a + 1) * G for this lane's first action
+                    if (a.e0.lmul != 0.0f) {                                 // power-of-two divisor / dense: one multiply
+#pragma unroll
+                        for (int i = 0; i < 4 * NC; ++i) {
                             const int off = 128 * (i >> 2) + (i & 3);
-                            const int k = (int)(mix64(zb + (u64)off * E0_GOLD) >> 58);
-                            lg[i] = off + 4 * lane < p.A ? __fmul_rn((float)(k - 32), a.inv_div) : 0.0f;
+                            const unsigned x = e0_action_hash(xb + (unsigned)off * E0_GOLD32);
+                            lg[i] = off + 4 * lane < p.A ? __fmul_rn((float)((int)(x >> a.e0.lshift) - a.e0.lbias), a.e0.lmul) : 0.0f;
                         }
                     } else {
 #pragma unroll 1
                         for (int i = 0; i < 4 * NC; ++i) {
                             const int ac = 128 * (i >> 2) + 4 * lane + (i & 3);
-                            lg[i] = ac < p.A ? e0_logit(h, ac, a.logit_div, a.inv_div) : 0.0f;
+                            lg[i] = ac < p.A ? e0_logit(h, ac, a.e0) : 0.0f;
                         }
                     }
                     node_write_row<NC>(p, w, nn, lg, lane);
@@ -344,11 +345,11 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                 }
                 w.num_nodes = nn + 1; ++ev;
                 __syncwarp();
-                backup<MZ>(p, w, path, mypath, depth, nn, e0_value(h), MZ ? e0_reward(h) : 0.0, reps, lane);
+                backup<MZ, F32>(p, w, path, mypath, depth, nn, e0_value(h, a.e0.dense), MZ ? e0_reward(h, a.e0.dense) : 0.0, reps, lane);
                 survivor_visit(w, depth, mypath, nn, la, reps, lane);
                 w.sim_count += reps;
                 __syncwarp();
-                if (halving_ready(p, w)) sequential_halving<MZ>(p, w, lane);
+                if (halving_ready(p, w)) sequential_halving<MZ, F32>(p, w, lane);
             }
             wg_store_search(p, lane, w);
             __syncwarp();
@@ -375,7 +376,7 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
             if (a.out_policy) pol = a.out_policy + (size_t)g * p.A;
             if (a.out_visits) vis = a.out_visits + (size_t)g * p.A;
         }
-        { WG t = w; finalize_root<NC, MZ>(p, t, lane, pol, vis, s_nvis[wi], table, value, action); }
+        { WG t = w; finalize_root<NC, MZ, F32>(p, t, lane, pol, vis, s_nvis[wi], table, value, action); }
         if (!a.do_step) {
             if (lane == 0) { if (a.out_value) a.out_value[g] = value; if (a.out_action) a.out_action[g] = action; }
         } else if (action < 0) {

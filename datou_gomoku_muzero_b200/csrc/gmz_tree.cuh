@@ -71,6 +71,28 @@ __device__ __forceinline__ double mm_norm(double q, bool rng, double mn, double 
     return n > 0.0 ? n : 0.0;
 }
 
+// Arithmetic mode.  F32 = false: the evaluator handed Python floats, everything is float64 (the upstream
+// test mock).  F32 = true: it handed np.float32 scalars (the reference's inference server, workers.py:355,368);
+// under NumPy >= 2 value_sum, the backed-up value, get_value / get_qsa and the MinMaxStats bounds are then
+// float32 (one float32 rounding per operation, DISCOUNT and VALUE_MINMAX_DELTA rounded to float32 first), while
+// normalize()'s numerator / division, sigma, the softmax and the scores stay float64 (SURVEY.md App. A.7;
+// pinned by the vdtype = 1 goldens of tests/golden/).  Values are stored widened in the
+// same double arrays.
+// Node.get_qsa for a visited child (mcts.py:35-38): child.reward + DISCOUNT * (value_sum / visit_count)
+template <bool F32>
+__device__ __forceinline__ double q_of(const Params &p, double W, int n, double R)
+{
+    if (F32) return (double)__fadd_rn((float)R, __fmul_rn(p.discf, __fdiv_rn((float)W, (float)n)));
+    return __dadd_rn(R, __dmul_rn(p.discount, __ddiv_rn(W, (double)n)));
+}
+// denominator of MinMaxStats.normalize (utils.py:19): maximum - minimum + minmax_delta
+template <bool F32>
+__device__ __forceinline__ double mm_denom(const Params &p, double mn, double mx)
+{
+    if (F32) return (double)__fadd_rn(__fsub_rn((float)mx, (float)mn), p.deltaf);
+    return __dadd_rn(__dsub_rn(mx, mn), p.delta);
+}
+
 // Loaded view of one expanded node's row: logits, child ids, child visit counts and q values.
 template <int NC>
 struct Row {
@@ -83,7 +105,7 @@ struct Row {
 
 // Node.get_qsa for every action of `node` (mcts.py:35-38) + max / sum of child visits
 // (mcts.py:144-147, 110).  Only visited children (child id >= 0) touch memory beyond the row.
-template <int NC, bool MZ>
+template <int NC, bool MZ, bool F32>
 __device__ __forceinline__ void row_load(const Params &p, const WG &w, int node, int lane, Row<NC> &r)
 {
     const size_t ni = w.nbase + (size_t)node;
@@ -103,9 +125,7 @@ __device__ __forceinline__ void row_load(const Params &p, const WG &w, int node,
         if (r.ch[i] >= 0) {
             const size_t ci = w.nbase + (size_t)r.ch[i];
             const int nn = p.nN[ci];
-            const double val = __ddiv_rn(p.nW[ci], (double)nn);          // child.get_value()
-            const double rew = MZ ? p.nR[ci] : 0.0;                        // child.reward
-            r.q[i] = __dadd_rn(rew, __dmul_rn(p.discount, val));
+            r.q[i] = q_of<F32>(p, p.nW[ci], nn, MZ ? p.nR[ci] : 0.0);
             r.n[i] = nn; lmax = max(lmax, nn); lsum += nn;
         }
     }
@@ -115,12 +135,12 @@ __device__ __forceinline__ void row_load(const Params &p, const WG &w, int node,
 
 // softmax over the root-valid actions of logits + sigma(q) (mcts.py:141-156): on return
 // x[i] = exp(logit + sigma - max) (0 for invalid actions) and the return value is 1/sum.
-template <int NC>
+template <int NC, bool F32>
 __device__ __forceinline__ double row_softmax(const Params &p, const WG &w, const Row<NC> &r, double *x)
 {
     const double scale = __dmul_rn(__dadd_rn(p.c_visit, (double)r.maxN), p.c_scale);
     const bool rng = w.mm_max > w.mm_min;
-    const double denom = __dadd_rn(__dsub_rn(w.mm_max, w.mm_min), p.delta);
+    const double denom = mm_denom<F32>(p, w.mm_min, w.mm_max);
     const double sig0 = __dmul_rn(scale, mm_norm(0.0, rng, w.mm_min, denom));   // unvisited: q = 0.0
     double lmx = -INFINITY;
 #pragma unroll
@@ -187,7 +207,7 @@ __device__ __forceinline__ void sel_unpack(int packed, int &action, int &child)
 // Most of a node's A children are unvisited (q = 0, N = 0, same sigma): those are scored in a
 // branch-free dense pass from the row alone.  The few visited children are compacted into
 // `sc` (one per lane) and scored in a sparse pass that gathers their N / W.
-template <int NC, bool MZ>
+template <int NC, bool MZ, bool F32>
 __device__ __noinline__ int select_interior_big(const Params &p, const SelCtx w, int node, int lane, SelSmem &sm, int warp_slot)
 {
     int action, child;
@@ -238,14 +258,13 @@ __device__ __noinline__ int select_interior_big(const Params &p, const SelCtx w,
     if (total > 0) { maxN = __reduce_max_sync(GMZ_FULL, lmax); sumN = __reduce_add_sync(GMZ_FULL, lsum); }
     const double scale = __dmul_rn(__dadd_rn(p.c_visit, (double)maxN), p.c_scale);
     const bool rng = w.mm_max > w.mm_min;
-    const double denom = __dadd_rn(__dsub_rn(w.mm_max, w.mm_min), p.delta);
+    const double denom = mm_denom<F32>(p, w.mm_min, w.mm_max);
     const double sig0 = __dmul_rn(scale, mm_norm(0.0, rng, w.mm_min, denom));   // unvisited: q = 0.0
     double lmx = -INFINITY;
     // sparse pass B: q -> sigma -> x
     for (int k = lane; k < total; k += 32) {
-        const double val = __ddiv_rn(sc.x[k], (double)sc.n[k]);                 // child.get_value()
         const double rew = MZ ? p.nR[w.nbase + (size_t)(sc.key[k] & 0xffff)] : 0.0;
-        const double q = __dadd_rn(rew, __dmul_rn(p.discount, val));
+        const double q = q_of<F32>(p, sc.x[k], sc.n[k], rew);
         const double x = __dadd_rn((double)sc.lg[k], __dmul_rn(scale, mm_norm(q, rng, w.mm_min, denom)));
         sc.x[k] = x; lmx = dmax2(lmx, x);
     }
@@ -332,7 +351,7 @@ __device__ __noinline__ int select_interior_big(const Params &p, const SelCtx w,
 // visited child k in registers (N, W -> q -> sigma -> exp -> score), every lane owns 4*NC dense
 // (unvisited) actions.  Same arithmetic, same order of operations per element as the big variant.
 // Out of line: it only runs when the certified path below cannot decide.
-template <int NC, bool MZ>
+template <int NC, bool MZ, bool F32>
 __device__ __noinline__ int select_interior_exact(const Params &p, const SelCtx w, int node, int lane, SelSmem &sm, int warp_slot)
 {
     int action, child;
@@ -358,7 +377,7 @@ __device__ __noinline__ int select_interior_exact(const Params &p, const SelCtx 
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(GMZ_FULL, inc, o); if (lane >= o) inc += t; }
         total = __shfl_sync(GMZ_FULL, inc, 31);
-        if (total > 32) return select_interior_big<NC, MZ>(p, w, node, lane, sm, warp_slot);
+        if (total > 32) return select_interior_big<NC, MZ, F32>(p, w, node, lane, sm, warp_slot);
         int pos = inc - cnt;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
@@ -382,12 +401,11 @@ __device__ __noinline__ int select_interior_exact(const Params &p, const SelCtx 
     const int maxN = __reduce_max_sync(GMZ_FULL, nn), sumN = __reduce_add_sync(GMZ_FULL, nn);
     const double scale = __dmul_rn(__dadd_rn(p.c_visit, (double)maxN), p.c_scale);
     const bool rng = w.mm_max > w.mm_min;
-    const double denom = __dadd_rn(__dsub_rn(w.mm_max, w.mm_min), p.delta);
+    const double denom = mm_denom<F32>(p, w.mm_min, w.mm_max);
     const double sig0 = __dmul_rn(scale, mm_norm(0.0, rng, w.mm_min, denom));   // unvisited: q = 0.0
     double lmx = -INFINITY, xs = -INFINITY;
     if (sp) {
-        const double val = __ddiv_rn(W, (double)nn);                            // child.get_value()
-        const double q = __dadd_rn(rew, __dmul_rn(p.discount, val));
+        const double q = q_of<F32>(p, W, nn, rew);
         xs = __dadd_rn((double)slg, __dmul_rn(scale, mm_norm(q, rng, w.mm_min, denom)));
         lmx = xs;
     }
@@ -567,7 +585,7 @@ __device__ __forceinline__ void node_link(const Params &p, const WG &w, int pare
     if (lane == 0) p.nHdr[pi] = hdr_pack(U, lub, ub, min(nvis, 32767), (amb || nvis > kFastMaxVisited) ? 1 : 0);
 }
 
-template <int NC, bool MZ>
+template <int NC, bool MZ, bool F32>
 __device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
                                                 double mn, double rden, int &action, int &child)
 {
@@ -593,7 +611,8 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         const double scale = (p.c_visit + (double)maxN) * p.c_scale;
         double xs = -INFINITY;
         if (cand) {
-            const double q = vis ? rew + p.discount * (W * rcp_newton((double)nn)) : 0.0;
+            // float32 mode: q IS float32 arithmetic in the reference, so it is computed exactly here too
+            const double q = !vis ? 0.0 : (F32 ? q_of<true>(p, W, nn, rew) : rew + p.discount * (W * rcp_newton((double)nn)));
             double nrm = (q - mn) * rden;                       // (mn, rden) = (0, 0) while max <= min: normalize() is 0 then
             const int hi = __double2hiint(nrm);                  // clamp to [0, 1] on the high word
             nrm = hi < 0 ? 0.0 : (hi >= 0x3ff00000 ? 1.0 : nrm);
@@ -624,7 +643,7 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
             action = a; child = (wkey & 0xffff) == 0xffff ? -1 : (wkey & 0xffff);
 #ifdef GMZ_VERIFY_FAST
             int ea, ec;
-            sel_unpack(select_interior_exact<NC, MZ>(p, sel_ctx(w), node, lane, sm, warp_slot), ea, ec);
+            sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w), node, lane, sm, warp_slot), ea, ec);
             if (lane == 0) {
                 atomicAdd(&p.ctl->sel_fast, 1ull);
                 if (ea != action || ec != child) atomicAdd(&p.ctl->sel_mismatch, 1ull);
@@ -635,13 +654,13 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         }
         if (lane == 0) atomicAdd(&p.ctl->sel_fallback, 1ull);
     }
-    sel_unpack(select_interior_exact<NC, MZ>(p, sel_ctx(w), node, lane, sm, warp_slot), action, child);
+    sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w), node, lane, sm, warp_slot), action, child);
 }
 
 // _select_leaf (mcts.py:88-104): root = first least-visited survivor (strict <, list order),
 // then interior selection until an unexpanded child is reached.  In AlphaZero mode the path
 // is replayed on the bitboards while descending (mcts.py:236-248).  Returns depth (edges).
-template <int NC, bool MZ>
+template <int NC, bool MZ, bool F32>
 __device__ __forceinline__ int descend(const Params &p, const WG &w, short *path, int &mypath, SelSmem &sc, int warp_slot, int lane,
                                        int &leaf_parent, int &leaf_action, u64 &P, u64 &M, int &colour)
 {
@@ -656,12 +675,12 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, short *path
     if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
     // MinMaxStats only change in the backup: 1 / (max - min + delta) is the same at every level of this descent
     const bool rng = w.mm_max > w.mm_min;
-    const double rden = rng ? rcp_newton((w.mm_max - w.mm_min) + p.delta) : 0.0, mn = rng ? w.mm_min : 0.0;
+    const double rden = rng ? rcp_newton(F32 ? mm_denom<true>(p, w.mm_min, w.mm_max) : (w.mm_max - w.mm_min) + p.delta) : 0.0, mn = rng ? w.mm_min : 0.0;
     while (node >= 0) {
         if (depth < 32) mypath = lane == depth ? node : mypath;
         else if (lane == 0) path[depth] = (short)node;
         int c;
-        select_interior<NC, MZ>(p, w, node, lane, sc, warp_slot, mn, rden, a, c);
+        select_interior<NC, MZ, F32>(p, w, node, lane, sc, warp_slot, mn, rden, a, c);
         if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
         parent = node; node = c; ++depth;
     }
@@ -699,13 +718,13 @@ __device__ __forceinline__ void node_write_row(const Params &p, const WG &w, int
 // same value len(selected) times, mcts.py:345).  Positions 0..depth-1 are path[], position
 // `depth` is the new node.  Lane l of a 32-wide segment owns position hi - l.  Also maintains
 // the survivor visit counts and the MinMaxStats (min/max are order-independent).
-template <bool MZ>
+template <bool MZ, bool F32>
 __device__ __forceinline__ void backup(const Params &p, WG &w, const short *path, int mypath, int depth, int new_node,
                                        double value, double reward, int reps, int lane)
 {
     double v = dclip1(value);
     double qmin = INFINITY, qmax = -INFINITY;
-    const bool noclip = p.discount <= 1.0 && p.discount >= -1.0;
+    const bool noclip = p.discount <= 1.0 && p.discount >= -1.0;      // (float32(discount) then is in [-1, 1] too)
 
     for (int hi = depth; hi >= 0; hi -= 32) {
         const int pos = hi - lane;
@@ -722,20 +741,21 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const short *path
         if (!MZ && noclip) {            // no rewards, |discount| <= 1: after the first clip |v| can only shrink
             for (int l = 0; l < cnt; ++l) {
                 if (lane == l) myv = v;
-                v = __dadd_rn(0.0, __dmul_rn(p.discount, v));
+                v = F32 ? (double)__fmul_rn(p.discf, (float)v) : __dadd_rn(0.0, __dmul_rn(p.discount, v));
             }
         } else {
             for (int l = 0; l < cnt; ++l) {
                 const double Rl = MZ ? __shfl_sync(GMZ_FULL, R, l) : 0.0;
                 if (lane == l) myv = v;
-                v = dclip1(__dadd_rn(Rl, __dmul_rn(p.discount, v)));   // value = node.reward + DISCOUNT * value; clip
+                v = dclip1(F32 ? (double)__fadd_rn((float)Rl, __fmul_rn(p.discf, (float)v))
+                               : __dadd_rn(Rl, __dmul_rn(p.discount, v)));   // value = node.reward + DISCOUNT * value; clip
             }
         }
         if (act) {
             for (int r = 0; r < reps; ++r) {
-                W = __dadd_rn(W, myv); n += 1;
+                W = F32 ? (double)__fadd_rn((float)W, (float)myv) : __dadd_rn(W, myv); n += 1;
                 if (pos > 0) {   // min_max_stats.update(parent.get_qsa(node.action))
-                    const double q = __dadd_rn(R, __dmul_rn(p.discount, __ddiv_rn(W, (double)n)));
+                    const double q = q_of<F32>(p, W, n, R);
                     qmin = dmin2(qmin, q); qmax = dmax2(qmax, q);
                 }
             }
@@ -761,7 +781,7 @@ __device__ __forceinline__ bool halving_ready(const Params &p, WG &w)
 
 // _sequential_halving (mcts.py:183-185): survivors = first m of the current survivors sorted
 // (stable, descending) by gumbel + logit + sigma(q) at the root.
-template <bool MZ>
+template <bool MZ, bool F32>
 __device__ __forceinline__ void sequential_halving(const Params &p, WG &w, int lane)
 {
     const bool mine = lane < w.n_init;
@@ -769,14 +789,12 @@ __device__ __forceinline__ void sequential_halving(const Params &p, WG &w, int l
     const int n = mine ? w.s_n : 0;
     if (mine && w.s_child >= 0) {
         const size_t ci = w.nbase + (size_t)w.s_child;
-        const double val = __ddiv_rn(p.nW[ci], (double)n);
-        const double rew = MZ ? p.nR[ci] : 0.0;
-        q = __dadd_rn(rew, __dmul_rn(p.discount, val));
+        q = q_of<F32>(p, p.nW[ci], n, MZ ? p.nR[ci] : 0.0);
     }
     const int maxN = __reduce_max_sync(GMZ_FULL, n);
     const double scale = __dmul_rn(__dadd_rn(p.c_visit, (double)maxN), p.c_scale);
     const bool rng = w.mm_max > w.mm_min;
-    const double denom = __dadd_rn(__dsub_rn(w.mm_max, w.mm_min), p.delta);
+    const double denom = mm_denom<F32>(p, w.mm_min, w.mm_max);
     const double sig = __dmul_rn(scale, mm_norm(q, rng, w.mm_min, denom));
     GState *gs = p.gs + w.g;
     double s_g = gs->surv_g[lane]; float s_logit = gs->surv_logit[lane];

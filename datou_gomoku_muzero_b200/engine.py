@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GMZ_F32, GMZ_F64, GMZ_MODE_ALPHAZERO, GMZ_MODE_MUZERO, GmzConfig, check
+from ._lib import GMZ_ACCUM_F32, GMZ_ACCUM_F64, GMZ_F32, GMZ_F64, GMZ_MODE_ALPHAZERO, GMZ_MODE_MUZERO, GmzConfig, check
 
 
 def _ptr(t):
@@ -26,8 +26,15 @@ def _ptr(t):
 
 
 class SearchEngine:
+    """accum_dtype: the dtype the reference's tree arithmetic runs in, which follows the evaluator's value
+    scalars.  "float64": the evaluator hands Python floats (the upstream test mock,
+    tests/test_mcts_logic.py:43).  "float32": it hands np.float32 scalars -- the reference's inference server
+    (workers.py:355,368) -- so under NumPy >= 2 value_sum, the backed-up value, Q and the MinMaxStats bounds
+    are float32; use this mode behind a real network to reproduce the reference's visit counts."""
+
     def __init__(self, num_games, board_size=15, n_in_row=5, num_simulations=400, num_top_actions=16,
-                 mode="AlphaZero", c_visit=30, c_scale=1.0, minmax_delta=1e-3, discount=0.997, device=None):
+                 mode="AlphaZero", c_visit=30, c_scale=1.0, minmax_delta=1e-3, discount=0.997, device=None,
+                 accum_dtype="float64"):
         if not torch.cuda.is_available():
             raise _lib.GmzError("SearchEngine needs a CUDA device (there is no CPU fallback)")
         self.lib = _lib.load()
@@ -35,10 +42,15 @@ class SearchEngine:
         if mode not in ("AlphaZero", "MuZero"):
             raise ValueError(f"Unknown MCTS implementation in config: '{mode}'")   # workers.py:142
         self.mode = mode
+        name = getattr(accum_dtype, "__name__", str(accum_dtype)).replace("torch.", "")     # "float32", np.float32, torch.float32
+        acc = {"float64": GMZ_ACCUM_F64, "f64": GMZ_ACCUM_F64, "float32": GMZ_ACCUM_F32, "f32": GMZ_ACCUM_F32}.get(name)
+        if acc is None:
+            raise ValueError(f"accum_dtype must be 'float64' or 'float32', not {accum_dtype!r}")
+        self.accum_dtype = "float32" if acc == GMZ_ACCUM_F32 else "float64"
         self.G, self.N, self.A = int(num_games), int(board_size), int(board_size) ** 2
         self.S, self.K = int(num_simulations), int(num_top_actions)
         self.cfg = GmzConfig(self.N, int(n_in_row), self.S, self.K,
-                             GMZ_MODE_ALPHAZERO if mode == "AlphaZero" else GMZ_MODE_MUZERO, self.G, 0, 0,
+                             GMZ_MODE_ALPHAZERO if mode == "AlphaZero" else GMZ_MODE_MUZERO, self.G, 0, acc,
                              float(c_visit), float(c_scale), float(minmax_delta), float(discount))
         nbytes = self.lib.gmz_workspace_bytes(C.byref(self.cfg))
         if nbytes == 0:

@@ -7,6 +7,10 @@ Two ways in:
     (mcts.py:73-85).  Same outputs `(policy float64[A], value, int action)`, same sentinel
     `(zeros, 0.0, -1)`, same request pattern (NUM_SIMULATIONS 'initial' requests in AlphaZero mode;
     one 'initial' + 'recurrent_batch' requests in MuZero mode), same use of `np.random.gumbel`.
+    The tree arithmetic follows the dtype of the evaluator's value scalar exactly as the reference's
+    does under NumPy >= 2: Python floats -> float64 engine; np.float32 (what the
+    reference's inference server returns, workers.py:355,368) -> float32-accumulation engine, and the
+    returned `value` is then an np.float32 as well.
   * `AlphaZeroMCTS.for_engine(engine, evaluator=...)` + `search_batch(...)` -- G searches at once
     from host buffers, evaluator on the device (the fixed evaluator E0 or a network callable).
 The tree itself (selection, expansion, backup, halving, decision) always runs in the kernels.
@@ -59,16 +63,21 @@ class _GumbelEngineMCTS(MCTS):
             self.logger.warning(f"Worker {self.worker_id} timed out waiting for recurrent inference.")
             return []
 
-    def _engine_for_config(self):
+    @staticmethod
+    def _accum_of(value):
+        """dtype the reference's value_sum takes from this evaluator scalar (0 + np.float32 stays float32)."""
+        return "float32" if isinstance(value, np.float32) else "float64"
+
+    def _engine_for_config(self, accum="float64"):
         from .engine import SearchEngine
         key = (config.BOARD_SIZE, config.N_IN_ROW, config.NUM_SIMULATIONS, config.NUM_TOP_ACTIONS, config.C_VISIT,
-               config.C_SCALE, config.VALUE_MINMAX_DELTA, config.DISCOUNT)
+               config.C_SCALE, config.VALUE_MINMAX_DELTA, config.DISCOUNT, accum)
         eng = self._engines.get(key)
         if eng is None:
             eng = SearchEngine(1, board_size=config.BOARD_SIZE, n_in_row=config.N_IN_ROW,
                                num_simulations=config.NUM_SIMULATIONS, num_top_actions=config.NUM_TOP_ACTIONS,
                                mode=self.MODE, c_visit=config.C_VISIT, c_scale=config.C_SCALE,
-                               minmax_delta=config.VALUE_MINMAX_DELTA, discount=config.DISCOUNT)
+                               minmax_delta=config.VALUE_MINMAX_DELTA, discount=config.DISCOUNT, accum_dtype=accum)
             self._engines = {key: eng}      # one live engine per instance
         return eng
 
@@ -88,7 +97,10 @@ class _GumbelEngineMCTS(MCTS):
 
     def _decision(self, eng):
         pol, val, act, _ = eng.finalize(want_visits=False)
-        return pol[0].cpu().numpy(), val[0].cpu().numpy()[()], int(act[0].item())
+        value = val[0].cpu().numpy()[()]
+        if eng.accum_dtype == "float32":
+            value = np.float32(value)          # root.get_value() is an np.float32 in this mode (exact: it was computed in float32)
+        return pol[0].cpu().numpy(), value, int(act[0].item())
 
     # ------------------------------------------------------------------ batched entry
     @classmethod
@@ -207,11 +219,11 @@ class AlphaZeroMCTS(_GumbelEngineMCTS):
             return np.zeros(A), 0.0, -1
         if not (np.asarray(game.board) == 0).any():
             return np.zeros(A), 0.0, -1
-        eng = self._engine_for_config()
+        vdt = np.float32 if isinstance(value, np.float32) else np.float64
+        eng = self._engine_for_config(self._accum_of(value))
         self._load_root(eng, game)
         gumbel = np.random.gumbel(0, 1, A)
-        eng.root_expand(np.asarray(policy_logits, np.float32).reshape(1, A), np.array([float(value)], np.float64),
-                        gumbel.reshape(1, A))
+        eng.root_expand(np.asarray(policy_logits, np.float32).reshape(1, A), np.array([value], vdt), gumbel.reshape(1, A))
         sim_count = 1
         while sim_count < config.NUM_SIMULATIONS:
             leaf_obs = eng.select()[0].cpu().numpy()
@@ -220,7 +232,7 @@ class AlphaZeroMCTS(_GumbelEngineMCTS):
             except Empty:
                 self.logger.warning(f"Worker {self.worker_id} timed out during MCTS expansion.")
                 continue
-            eng.expand_backup(np.asarray(lg, np.float32).reshape(1, A), np.array([float(v)], np.float64))
+            eng.expand_backup(np.asarray(lg, np.float32).reshape(1, A), np.array([v], vdt))
             sim_count += 1
         return self._decision(eng)
 
@@ -241,11 +253,11 @@ class MuZeroMCTS(_GumbelEngineMCTS):
             return np.zeros(A), 0.0, -1
         if not (np.asarray(game.board) == 0).any():
             return np.zeros(A), 0.0, -1
-        eng = self._engine_for_config()
+        vdt = np.float32 if isinstance(value, np.float32) else np.float64
+        eng = self._engine_for_config(self._accum_of(value))
         self._load_root(eng, game)
         gumbel = np.random.gumbel(0, 1, A)
-        eng.root_expand(np.asarray(policy_logits, np.float32).reshape(1, A), np.array([float(value)], np.float64),
-                        gumbel.reshape(1, A))
+        eng.root_expand(np.asarray(policy_logits, np.float32).reshape(1, A), np.array([value], vdt), gumbel.reshape(1, A))
         hidden_of = {0: hidden}
         while True:
             parent, action, child, _depth, reps = eng.select_mz(with_reps=True)
@@ -258,6 +270,5 @@ class MuZeroMCTS(_GumbelEngineMCTS):
                 continue
             lg, v, h, r = results[-1]
             hidden_of[child] = h
-            eng.expand_backup(np.asarray(lg, np.float32).reshape(1, A), np.array([float(results[0][1])], np.float64),
-                              np.array([float(r)], np.float64))
+            eng.expand_backup(np.asarray(lg, np.float32).reshape(1, A), np.array([results[0][1]], vdt), np.array([r], vdt))
         return self._decision(eng)

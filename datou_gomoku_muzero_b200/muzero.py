@@ -169,14 +169,17 @@ class MuZeroDeviceSearch:
 
 class TorchE0:
     """The fixed evaluator E0 in MuZero mode, as torch integer ops on the device (hidden state = the
-    64-bit hash, one int64 per node).  Same integers as the CUDA E0 (csrc/gmz_common.cuh) and tests/golden/e0_py.py."""
+    64-bit hash, one int64 per node).  Same integers as the CUDA E0 (csrc/gmz_common.cuh) and
+    tests/golden/e0_py.py; logit_div = 0 selects the dense (unquantised) heads."""
 
-    GOLD, CV, CA, CR = 0x9E3779B97F4A7C15, 0xD1B54A32D192ED03, 0x8CB92BA72F3D8DD7, 0xA24BAED4963EE407
+    GOLD, CV, CA = 0x9E3779B97F4A7C15, 0xD1B54A32D192ED03, 0x8CB92BA72F3D8DD7
+    GOLD32, M1, M2 = 0x9E3779B1, 0x7FEB352D, 0x846CA68B
 
     def __init__(self, board_size, seed=0, logit_div=16, device="cuda"):
         self.N, self.A = board_size, board_size * board_size
-        self.seed, self.div, self.device = int(seed), float(logit_div), device
-        self.a1 = self._c(((np.arange(1, self.A + 1, dtype=np.uint64) * np.uint64(self.GOLD))).astype(np.int64))
+        self.seed, self.div, self.device = int(seed), int(logit_div), device
+        self.a1 = self._c((np.arange(1, self.A + 1, dtype=np.int64) * self.GOLD32) & 0xFFFFFFFF)     # (a + 1) * GOLD32 mod 2^32
+        self.h0 = self._s(self.mix_int(self.seed ^ self.GOLD))
 
     def _c(self, x):
         return torch.as_tensor(x, dtype=torch.int64, device=self.device)
@@ -197,11 +200,25 @@ class TorchE0:
         z = z * self._s(0x94D049BB133111EB)
         return z ^ self._shr(z, 31)
 
-    def heads(self, h):
-        k = self._shr(self.mix(h[:, None] + self.a1[None, :]), 58)
-        logits = (k - 32).to(torch.float32) / self.div
-        value = ((self._shr(self.mix(h ^ self._s(self.CV)), 40) % 33) - 16).to(torch.float64) / 16.0
-        return logits, value
+    def heads(self, h, with_reward=False):
+        m32 = 0xFFFFFFFF
+        s = (h & m32) ^ self._shr(h, 32)                           # 32-bit arithmetic carried in int64 lanes
+        x = (s[:, None] + self.a1[None, :]) & m32
+        x = x ^ (x >> 16)
+        x = (x * self.M1) & m32
+        x = x ^ (x >> 15)
+        x = (x * self.M2) & m32
+        vk = self._shr(h, 40) & 0xFFFFFF
+        rk = self._shr(h, 16) & 0xFFFFFF
+        if self.div > 0:
+            logits = ((x >> 26) - 32).to(torch.float32) / float(self.div)
+            value = ((vk % 33) - 16).to(torch.float64) / 16.0
+            reward = ((rk % 5) - 2).to(torch.float64) / 16.0
+        else:
+            logits = ((x >> 8) - (1 << 23)).to(torch.float32) * (2.0 ** -21)
+            value = (vk - (1 << 23)).to(torch.float64) * (2.0 ** -23)
+            reward = (rk - (1 << 23)).to(torch.float64) * (2.0 ** -25)
+        return (logits, value, reward) if with_reward else (logits, value)
 
     def initial(self, obs):
         B, A = obs.shape[0], self.A
@@ -215,12 +232,11 @@ class TorchE0:
         opp = (planes[:, 1, None, :].long() * weights[None]).sum(-1)
         has_last = planes[:, 2].any(dim=1)
         last = torch.where(has_last, planes[:, 2].float().argmax(dim=1), torch.full((B,), -1, device=obs.device))
-        h = torch.full((B,), self._s(self.mix_int(self.seed ^ self.GOLD)), dtype=torch.int64, device=obs.device)
+        acc = torch.zeros((B,), dtype=torch.int64, device=obs.device)
         for w in range(nw):
-            h = self.mix(h ^ own[:, w])
-        for w in range(nw):
-            h = self.mix(h ^ opp[:, w])
-        h = self.mix(h ^ (last + 1))
+            acc = acc ^ self.mix((own[:, w] ^ self.h0) + self._s((2 * w + 1) * self.GOLD))
+            acc = acc ^ self.mix((opp[:, w] ^ self.h0) + self._s((2 * w + 2) * self.GOLD))
+        h = self.mix(acc + (last + 1) * self._s(self.CV))
         lg, v = self.heads(h)
         return lg, v, h
 
@@ -232,9 +248,8 @@ class TorchE0:
         return z ^ (z >> 31)
 
     def recurrent(self, h_parent, actions):
-        hc = self.mix(h_parent ^ self.mix(actions + 1 + self._s(self.CA)))
-        lg, v = self.heads(hc)
-        r = ((self._shr(self.mix(hc ^ self._s(self.CR)), 40) % 5) - 2).to(torch.float64) / 16.0
+        hc = self.mix(h_parent + (actions + 1) * self._s(self.CA))
+        lg, v, r = self.heads(hc, with_reward=True)
         return lg, v, r, hc
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GMZ_VERSION 100
+#define GMZ_VERSION 200
 #define GMZ_MODE_ALPHAZERO 0 /* AlphaZeroMCTS, mcts.py:191-280 */
 #define GMZ_MODE_MUZERO 1    /* MuZeroMCTS,   mcts.py:283-362 */
 #define GMZ_MAX_BOARD 19
@@ -39,6 +39,8 @@ extern "C" {
 #define GMZ_F32 0
 #define GMZ_F64 1
 #define GMZ_BF16 2
+#define GMZ_ACCUM_F64 0 /* gmz_config.accum_dtype */
+#define GMZ_ACCUM_F32 1
 
 typedef struct gmz_engine gmz_engine;
 typedef void *gmz_stream;
@@ -52,7 +54,12 @@ typedef struct gmz_config {
     int32_t mode;            /* GMZ_MODE_* (MCTS_IMPLEMENTATION) */
     int32_t num_games;       /* G: concurrent game trees held by this engine */
     int32_t max_moves;       /* trajectory capacity per game (0 = board_size^2) */
-    int32_t reserved;
+    int32_t accum_dtype;     /* GMZ_ACCUM_*: the dtype the reference's tree arithmetic runs in.  It follows
+                              * the evaluator's value scalars: Python floats (the upstream test
+                              * mock) -> float64 = GMZ_ACCUM_F64; np.float32 (the reference's inference server,
+                              * workers.py:355,368, NumPy >= 2) -> value_sum / backed-up value / Q / MinMaxStats in
+                              * float32 = GMZ_ACCUM_F32.  Visit counts are bit-exact against the reference in
+                              * either mode only if the mode matches what the evaluator hands the reference. */
     double c_visit;          /* C_VISIT */
     double c_scale;          /* C_SCALE */
     double minmax_delta;     /* VALUE_MINMAX_DELTA */
@@ -118,7 +125,10 @@ int gmz_finalize(gmz_engine *e, double *policy, double *value, int32_t *action, 
 
 /* ---- E0, the fixed deterministic evaluator --------------------- */
 /* Stand-alone evaluator kernel over observations obs f32 [B,3,N,N] ->
- * logits f32 [B,A], values f64 [B] (the device twin of tests/golden/e0_py.py). */
+ * logits f32 [B,A], values f64 [B] (the device twin of tests/golden/e0_py.py).
+ * logit_div > 0: quantised logits (k-32)/logit_div, k in 0..63, values k/16; logit_div = 0: DENSE
+ * logits (24 random mantissa bits in [-4, 4)) and values in [-1, 1) -- what a network's outputs look
+ * like to the search.  Every value / reward E0 produces is exactly representable in float32. */
 int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint64_t seed, int logit_div,
                     float *logits, double *values, gmz_stream stream);
 /* Whole search (root evaluation + S-1 simulations) in ONE persistent kernel

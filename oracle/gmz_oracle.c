@@ -31,9 +31,11 @@ typedef struct {
     int32_t num_simulations; /* config.NUM_SIMULATIONS   config.py:22 */
     int32_t num_top_actions; /* config.NUM_TOP_ACTIONS   config.py:23 */
     int32_t mode;            /* 0 = AlphaZeroMCTS, 1 = MuZeroMCTS (config.py:25) */
-    int32_t eval_kind;       /* 0 = E0 hash evaluator, 1 = constant (tests/test_mcts_logic.py:60-80) */
-    int32_t logit_div;       /* E0: logits = (k-32)/logit_div, k in 0..63 */
-    int32_t reserved;
+    int32_t eval_kind;       /* 0 = E0 hash evaluator, 1 = constant (tests/test_mcts_logic.py:60-80), 3 = harness callback (AlphaZero mode) */
+    int32_t logit_div;       /* E0: > 0 quantised logits (k-32)/logit_div, k in 0..63; 0 = dense 24-bit logits / values */
+    int32_t accum_dtype;     /* 0: the evaluator hands Python floats -> float64 arithmetic (upstream test mock);
+                              * 1: it hands np.float32 scalars (workers.py:355,368) -> float32 value_sum / Q /
+                              *    MinMaxStats under NumPy >= 2 */
     double c_visit;          /* config.py:31 */
     double c_scale;          /* config.py:32 */
     double minmax_delta;     /* config.py:33 */
@@ -50,7 +52,6 @@ typedef struct {
 #define E0_GOLD 0x9E3779B97F4A7C15ULL
 #define E0_CV 0xD1B54A32D192ED03ULL
 #define E0_CA 0x8CB92BA72F3D8DD7ULL
-#define E0_CR 0xA24BAED4963EE407ULL
 
 static inline uint64_t mix64(uint64_t z)
 {
@@ -60,7 +61,8 @@ static inline uint64_t mix64(uint64_t z)
     return z;
 }
 
-/* hash of the observation planes game.py:12-17 builds: own / opp / last move */
+/* hash of the observation planes game.py:12-17 builds: own / opp / last move.  The per-word terms
+ * are combined with XOR, so the words can be hashed in any order (in parallel on the GPU). */
 static uint64_t e0_hash_obs(const orc_config *c, const int8_t *board, int player, int last_move)
 {
     const int A = c->board_size * c->board_size, nw = (A + 63) / 64;
@@ -69,36 +71,65 @@ static uint64_t e0_hash_obs(const orc_config *c, const int8_t *board, int player
         if (board[a] == player) own[a >> 6] |= 1ULL << (a & 63);
         else if (board[a] == -player) opp[a >> 6] |= 1ULL << (a & 63);
     }
-    uint64_t h = mix64(c->eval_seed ^ E0_GOLD);
-    for (int w = 0; w < nw; ++w) h = mix64(h ^ own[w]);
-    for (int w = 0; w < nw; ++w) h = mix64(h ^ opp[w]);
-    return mix64(h ^ (uint64_t)(int64_t)(last_move + 1));
+    const uint64_t h0 = mix64(c->eval_seed ^ E0_GOLD);
+    uint64_t acc = 0;
+    for (int w = 0; w < nw; ++w) {
+        acc ^= mix64((own[w] ^ h0) + (uint64_t)(2 * w + 1) * E0_GOLD);
+        acc ^= mix64((opp[w] ^ h0) + (uint64_t)(2 * w + 2) * E0_GOLD);
+    }
+    return mix64(acc + (uint64_t)(int64_t)(last_move + 1) * E0_CV);
+}
+
+/* per-action 32-bit hash (two multiplies; only the high bits are used) */
+static inline uint32_t e0_action_hash(uint32_t s, int a)
+{
+    uint32_t x = s + (uint32_t)(a + 1) * 0x9E3779B1u;
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    return x;
 }
 
 static void e0_heads(const orc_config *c, uint64_t h, float *logits, double *value)
 {
     const int A = c->board_size * c->board_size;
-    for (int a = 0; a < A; ++a) {
-        int k = (int)(mix64(h + (uint64_t)(a + 1) * E0_GOLD) >> 58);
-        logits[a] = (float)(k - 32) / (float)c->logit_div;
+    const uint32_t s = (uint32_t)h ^ (uint32_t)(h >> 32);
+    const int vk = (int)((h >> 40) & 0xFFFFFF);
+    if (c->logit_div > 0) {
+        for (int a = 0; a < A; ++a) logits[a] = (float)((int)(e0_action_hash(s, a) >> 26) - 32) / (float)c->logit_div;
+        *value = (double)(vk % 33 - 16) / 16.0;
+    } else {   /* dense: 24 random mantissa bits, no quantisation */
+        for (int a = 0; a < A; ++a) logits[a] = (float)((int)(e0_action_hash(s, a) >> 8) - (1 << 23)) * 0x1p-21f;
+        *value = (double)(vk - (1 << 23)) * 0x1p-23;
     }
-    *value = (double)((int)((mix64(h ^ E0_CV) >> 40) % 33) - 16) / 16.0;
 }
 
 static uint64_t e0_child_hidden(uint64_t h_parent, int action)
 {
-    return mix64(h_parent ^ mix64((uint64_t)(action + 1) + E0_CA));
+    return mix64(h_parent + (uint64_t)(action + 1) * E0_CA);
 }
 
-static double e0_reward(uint64_t h)
+static double e0_reward(const orc_config *c, uint64_t h)
 {
-    return (double)((int)((mix64(h ^ E0_CR) >> 40) % 5) - 2) / 16.0;
+    const int rk = (int)((h >> 16) & 0xFFFFFF);
+    return c->logit_div > 0 ? (double)(rk % 5 - 2) / 16.0 : (double)(rk - (1 << 23)) * 0x1p-25;
 }
+
+/* eval_kind 3: an evaluator supplied by the test harness (e.g. a table of what a real network returned
+ * for each observation): called with the position the reference would build its observation from. */
+typedef void (*orc_eval_fn)(const int8_t *board, int32_t board_size, int32_t player, int32_t last_move,
+                            float *logits, double *value);
+static orc_eval_fn g_eval_cb = 0;
+void orc_set_eval_callback(orc_eval_fn fn) { g_eval_cb = fn; }
 
 /* exported so tests can check the Python and CUDA evaluators against it */
 void orc_e0_initial(const orc_config *c, const int8_t *board, int player, int last_move,
                     float *logits, double *value, uint64_t *hidden)
 {
+    if (c->eval_kind == 3 && g_eval_cb) {
+        g_eval_cb(board, c->board_size, player, last_move, logits, value);
+        *hidden = 3;
+        return;
+    }
     if (c->eval_kind == 1) {
         const int A = c->board_size * c->board_size;
         for (int a = 0; a < A; ++a) logits[a] = 0.0f;
@@ -121,16 +152,16 @@ void orc_e0_recurrent(const orc_config *c, uint64_t h_parent, int action,
     }
     uint64_t h = e0_child_hidden(h_parent, action);
     e0_heads(c, h, logits, value);
-    *reward = e0_reward(h);
+    *reward = e0_reward(c, h);
     *hidden = h;
 }
 
 /* ------------------------------------------------------------------ */
 /* utils.MinMaxStats  (utils.py:6-25)                                  */
 /* ------------------------------------------------------------------ */
-typedef struct { double maximum, minimum, delta; } MinMax;
+typedef struct { double maximum, minimum, delta; int f32; } MinMax;
 
-static void mm_init(MinMax *m, double delta) { m->maximum = -INFINITY; m->minimum = INFINITY; m->delta = delta; }
+static void mm_init(MinMax *m, double delta, int f32) { m->maximum = -INFINITY; m->minimum = INFINITY; m->delta = delta; m->f32 = f32; }
 static void mm_update(MinMax *m, double v)
 { /* utils.py:12-14 */
     if (v > m->maximum) m->maximum = v;
@@ -139,7 +170,15 @@ static void mm_update(MinMax *m, double v)
 static double mm_normalize(const MinMax *m, double v)
 { /* utils.py:16-25 */
     if (m->maximum > m->minimum) {
-        double n = (v - m->minimum) / (m->maximum - m->minimum + m->delta);
+        /* float32 mode: maximum / minimum are np.float32, so the denominator (max - min + delta) is
+         * float32 arithmetic with delta rounded to float32; `v` arrives as np.float64 -- the element of
+         * the float64 array np.array([get_qsa(a) ...]) (mcts.py:142: Python 0.0 for the unvisited
+         * actions mixed with np.float32 promotes the array) -- so the numerator and the division are
+         * float64.  (An array with NO Python float, i.e. every one of the A actions visited, would
+         * stay float32: see `all_visited` in transformed_qs.) */
+        double den = m->f32 ? (double)(((float)m->maximum - (float)m->minimum) + (float)m->delta)
+                            : m->maximum - m->minimum + m->delta;
+        double n = (v - m->minimum) / den;
         double lo = n < 1.0 ? n : 1.0;     /* min(1.0, normalized) */
         return lo > 0.0 ? lo : 0.0;        /* max(0.0, ...)        */
     }
@@ -163,6 +202,8 @@ typedef struct {
     Node *nodes; int n_nodes, cap;
     MinMax mm;
     const uint8_t *valid;     /* [A] root-valid mask, fixed for the whole search (mcts.py:213) */
+    int f32;                  /* cfg->accum_dtype == 1: value_sum / value / Q carried as np.float32 (stored widened) */
+    int all_visited;          /* float32 mode: a node with all A children visited was scored (dtype case not restated) */
     /* per-search engine state that the reference keeps on self (mcts.py:159,221,226) */
     int *sel; int n_sel;      /* selected_children_actions */
     const double *gumbel;
@@ -195,15 +236,18 @@ static int node_child_or_neg(const Tree *t, int node, int action)
     const Node *n = &t->nodes[node];
     return n->children ? n->children[action] : -1;
 }
-static double node_get_value(const Node *n)
-{ /* mcts.py:32-33 */
-    return n->visit_count > 0 ? n->value_sum / (double)n->visit_count : 0.0;
+static double node_get_value(const Tree *t, const Node *n)
+{ /* mcts.py:32-33; float32 mode: np.float32 / int -> float32 division */
+    if (n->visit_count <= 0) return 0.0;
+    return t->f32 ? (double)((float)n->value_sum / (float)n->visit_count) : n->value_sum / (double)n->visit_count;
 }
 static double node_get_qsa(const Tree *t, int node, int action)
-{ /* mcts.py:35-38 */
+{ /* mcts.py:35-38; float32 mode: reward + float32(discount) * value, both operations in float32 */
     int c = node_child_or_neg(t, node, action);
-    if (c >= 0 && t->nodes[c].visit_count > 0)
-        return t->nodes[c].reward + t->cfg->discount * node_get_value(&t->nodes[c]);
+    if (c >= 0 && t->nodes[c].visit_count > 0) {
+        if (t->f32) return (double)((float)t->nodes[c].reward + (float)t->cfg->discount * (float)node_get_value(t, &t->nodes[c]));
+        return t->nodes[c].reward + t->cfg->discount * node_get_value(t, &t->nodes[c]);
+    }
     return 0.0;
 }
 static void node_expand(Tree *t, int node, const float *logits, uint64_t hidden, double reward)
@@ -223,10 +267,12 @@ static void backpropagate(Tree *t, int leaf, double value)
     int node = leaf;
     while (node >= 0) {
         Node *n = &t->nodes[node];
-        n->value_sum += value;
+        if (t->f32) n->value_sum = (double)((float)n->value_sum + (float)value);   /* int 0 + np.float32 -> np.float32 */
+        else n->value_sum += value;
         n->visit_count += 1;
         if (n->parent >= 0) mm_update(&t->mm, node_get_qsa(t, n->parent, n->action));
-        value = n->reward + t->cfg->discount * value;
+        if (t->f32) value = (double)((float)n->reward + (float)t->cfg->discount * (float)value);
+        else value = n->reward + t->cfg->discount * value;
         value = clip1(value);
         node = n->parent;
     }
@@ -236,11 +282,15 @@ static void backpropagate(Tree *t, int leaf, double value)
 static void transformed_qs(const Tree *t, int node, double *out)
 {
     const orc_config *c = t->cfg;
-    int max_child_visit = 0;
+    int max_child_visit = 0, n_visited = 0;
     for (int a = 0; a < t->A; ++a) {
         int ch = node_child_or_neg(t, node, a);
         if (ch >= 0 && t->nodes[ch].visit_count > max_child_visit) max_child_visit = t->nodes[ch].visit_count;
+        if (ch >= 0 && t->nodes[ch].visit_count > 0) ++n_visited;
     }
+    /* float32 mode with every action visited: the reference's q array would be float32 and the rest of
+     * the transform / softmax follow in float32 (not restated; reported through out_counts[4]) */
+    if (t->f32 && n_visited == t->A) ((Tree *)t)->all_visited = 1;
     const double scale = (c->c_visit + (double)max_child_visit) * c->c_scale;
     for (int a = 0; a < t->A; ++a)
         out[a] = scale * mm_normalize(&t->mm, node_get_qsa(t, node, a));
@@ -420,7 +470,7 @@ static void do_move(int8_t *board, int *player, int *last_move, int *move_count,
  * Returns 0, or 1 for the sentinel "(zeros, 0.0, -1)" of mcts.py:214-215.
  * Optional outputs (may be NULL): out_visits[A] root-child visit counts,
  * out_leaf_actions/out_leaf_depths[num_simulations] one entry per evaluation
- * after the root, out_counts[4] = {sim_count, n_evals, n_nodes, max_depth},
+ * after the root, out_counts[5] = {sim_count, n_evals, n_nodes, max_depth, all_visited (float32 mode)},
  * out_minmax[2] = {minimum, maximum}.
  */
 int orc_search(const orc_config *cfg, const int8_t *board, int player, int last_move, int move_count,
@@ -436,12 +486,12 @@ int orc_search(const orc_config *cfg, const int8_t *board, int player, int last_
     for (int a = 0; a < A; ++a) out_policy[a] = 0.0;
     *out_value = 0.0; *out_action = -1;
     if (out_visits) memset(out_visits, 0, sizeof(int32_t) * (size_t)A);
-    if (out_counts) memset(out_counts, 0, sizeof(int32_t) * 4);
+    if (out_counts) memset(out_counts, 0, sizeof(int32_t) * 5);
     if (n_valid == 0) { free(valid); return 1; }
 
     Tree t; memset(&t, 0, sizeof(t));
     t.cfg = cfg; t.A = A; t.cap = S + 4; t.nodes = (Node *)malloc(sizeof(Node) * (size_t)t.cap);
-    t.valid = valid; t.gumbel = gumbel; mm_init(&t.mm, cfg->minmax_delta);
+    t.valid = valid; t.gumbel = gumbel; t.f32 = cfg->accum_dtype == 1; mm_init(&t.mm, cfg->minmax_delta, t.f32);
     float *logits = (float *)malloc(sizeof(float) * (size_t)A);
     double *tq = (double *)malloc(sizeof(double) * (size_t)A), *pol = (double *)malloc(sizeof(double) * (size_t)A);
     int8_t *tmp = (int8_t *)malloc((size_t)A);
@@ -512,7 +562,7 @@ int orc_search(const orc_config *cfg, const int8_t *board, int player, int last_
     /* decision (mcts.py:271-280) */
     transformed_qs(&t, root, tq);
     improved_policy(&t, root, tq, out_policy);
-    *out_value = node_get_value(&t.nodes[root]);
+    *out_value = node_get_value(&t, &t.nodes[root]);
     {
         int32_t *keys = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_valid), *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_valid);
         int k = 0;
@@ -529,7 +579,7 @@ int orc_search(const orc_config *cfg, const int8_t *board, int player, int last_
     }
     if (out_visits)
         for (int a = 0; a < A; ++a) { int ch = node_child_or_neg(&t, root, a); out_visits[a] = ch >= 0 ? t.nodes[ch].visit_count : 0; }
-    if (out_counts) { out_counts[0] = sim_count; out_counts[1] = n_evals; out_counts[2] = t.n_nodes; out_counts[3] = max_depth; }
+    if (out_counts) { out_counts[0] = sim_count; out_counts[1] = n_evals; out_counts[2] = t.n_nodes; out_counts[3] = max_depth; out_counts[4] = t.all_visited; }
     if (out_minmax) { out_minmax[0] = t.mm.minimum; out_minmax[1] = t.mm.maximum; }
 
     tree_free(&t); free(valid); free(logits); free(tq); free(pol); free(tmp); free(hist);

@@ -21,7 +21,7 @@ class OrcConfig(C.Structure):
     _fields_ = [
         ("board_size", C.c_int32), ("n_in_row", C.c_int32),
         ("num_simulations", C.c_int32), ("num_top_actions", C.c_int32),
-        ("mode", C.c_int32), ("eval_kind", C.c_int32), ("logit_div", C.c_int32), ("reserved", C.c_int32),
+        ("mode", C.c_int32), ("eval_kind", C.c_int32), ("logit_div", C.c_int32), ("accum_dtype", C.c_int32),
         ("c_visit", C.c_double), ("c_scale", C.c_double), ("minmax_delta", C.c_double), ("discount", C.c_double),
         ("const_value", C.c_double), ("const_reward", C.c_double),
         ("eval_seed", C.c_uint64),
@@ -51,8 +51,10 @@ def lib():
 
 def make_config(board_size=15, n_in_row=5, num_simulations=400, num_top_actions=16, mode=0,
                 eval_kind=0, logit_div=16, c_visit=30.0, c_scale=1.0, minmax_delta=1e-3, discount=0.997,
-                const_value=0.5, const_reward=0.0, eval_seed=0) -> OrcConfig:
-    return OrcConfig(board_size, n_in_row, num_simulations, num_top_actions, mode, eval_kind, logit_div, 0,
+                const_value=0.5, const_reward=0.0, eval_seed=0, accum_dtype=0) -> OrcConfig:
+    """logit_div 0 = dense (unquantised) E0 logits / values; accum_dtype 1 = the evaluator returns np.float32
+    scalars (the reference's inference server), i.e. float32 value_sum / Q / MinMaxStats."""
+    return OrcConfig(board_size, n_in_row, num_simulations, num_top_actions, mode, eval_kind, logit_div, int(accum_dtype),
                      float(c_visit), float(c_scale), float(minmax_delta), float(discount),
                      float(const_value), float(const_reward), int(eval_seed) & 0xFFFFFFFFFFFFFFFF)
 
@@ -73,7 +75,7 @@ def search(cfg: OrcConfig, board, player, last_move, move_count, gumbel, trace=F
     visits = np.zeros(A, np.int32)
     la = np.full(S + 1, -1, np.int32)
     ld = np.full(S + 1, -1, np.int32)
-    counts = np.zeros(4, np.int32)
+    counts = np.zeros(5, np.int32)
     mm = np.zeros(2, np.float64)
     rc = lib().orc_search(C.byref(cfg), _p(board, C.c_int8), int(player), int(last_move), int(move_count),
                           _p(gumbel, C.c_double), _p(policy, C.c_double), C.byref(value), C.byref(action),
@@ -81,6 +83,7 @@ def search(cfg: OrcConfig, board, player, last_move, move_count, gumbel, trace=F
                           _p(counts, C.c_int32), _p(mm, C.c_double))
     out = dict(rc=rc, policy=policy, value=value.value, action=action.value, visits=visits,
                sim_count=int(counts[0]), n_evals=int(counts[1]), n_nodes=int(counts[2]), max_depth=int(counts[3]),
+               all_visited=int(counts[4]),
                minmax=mm)
     if trace:
         out["leaf_actions"] = la[:counts[1]].copy()
@@ -105,6 +108,29 @@ def search_batch(cfg: OrcConfig, boards, players, last_moves, move_counts, gumbe
                            _p(value, C.c_double), _p(action, C.c_int32),
                            _p(visits, C.c_int32) if want_visits else None, int(n_threads))
     return policy, value, action, visits
+
+
+_EVAL_FN = C.CFUNCTYPE(None, C.POINTER(C.c_int8), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_double))
+_eval_keepalive = None
+
+
+def set_eval_callback(fn):
+    """Evaluator for configs made with eval_kind=3 (AlphaZero mode, single-threaded `search` only):
+    fn(board int8 [N,N], player, last_move) -> (logits float32 [A], value).  None removes it."""
+    global _eval_keepalive
+    if fn is None:
+        lib().orc_set_eval_callback(_EVAL_FN(0))
+        _eval_keepalive = None
+        return
+
+    def tramp(board_p, n, player, last_move, logits_p, value_p):
+        A = n * n
+        board = np.ctypeslib.as_array(board_p, shape=(A,)).reshape(n, n).copy()
+        lg, v = fn(board, int(player), int(last_move))
+        np.ctypeslib.as_array(logits_p, shape=(A,))[:] = np.asarray(lg, np.float32).reshape(A)
+        value_p[0] = float(v)
+    _eval_keepalive = _EVAL_FN(tramp)
+    lib().orc_set_eval_callback(_eval_keepalive)
 
 
 def max_threads() -> int:

@@ -2,8 +2,23 @@
 reference's inference-queue protocol (mcts.py:73-85, tests/test_mcts_logic.py:26-58).
 
 Used (a) by make_golden.py to drive the imported reference and (b) by CPU tests to check
-that the C oracle's and the CUDA engine's E0 produce the same integers.  Values are returned
-as Python floats / float64 so the reference accumulates in float64.
+that the C oracle's and the CUDA engine's E0 produce the same integers.
+
+Definition (round 2; cheap on a GPU: the board hash is order-free over the words, the per-action
+hash is 32-bit):
+    h0 = mix64(seed ^ GOLD)
+    h  = mix64( XOR_w [ mix64((own_w ^ h0) + (2w+1) GOLD) ^ mix64((opp_w ^ h0) + (2w+2) GOLD) ]  +  (last+1) CV )
+    s  = lo32(h) ^ hi32(h);   x_a = lowbias32-style mix of  s + (a+1) * 0x9E3779B1   (two multiplies)
+    logit_div > 0 (quantised):  logit_a = ((x_a >> 26) - 32) / logit_div       value = (((h >> 40) % 33) - 16) / 16
+                                reward  = ((((h >> 16) & 0xFFFFFF) % 5) - 2) / 16
+    logit_div = 0 (dense):      logit_a = ((x_a >> 8) - 2^23) * 2^-21  in [-4, 4)   -- 24 random mantissa bits
+                                value   = ((h >> 40) - 2^23) * 2^-23   in [-1, 1)
+                                reward  = (((h >> 16) & 0xFFFFFF) - 2^23) * 2^-25 in [-0.25, 0.25)
+    MuZero mode: h_child = mix64(h_parent + (a+1) CA)
+Every value / reward is exactly representable in float32, so the evaluator can hand the search
+Python floats (the upstream test mock, float64 accumulation) or np.float32 scalars (what the
+reference's inference server returns, workers.py:355,368 -- float32 accumulation under NumPy >= 2,
+SURVEY.md App. A.7) without changing the numbers themselves: `value_dtype`.
 """
 from __future__ import annotations
 
@@ -15,7 +30,7 @@ M64 = (1 << 64) - 1
 GOLD = 0x9E3779B97F4A7C15
 CV = 0xD1B54A32D192ED03
 CA = 0x8CB92BA72F3D8DD7
-CR = 0xA24BAED4963EE407
+GOLD32, M1_32, M2_32 = 0x9E3779B1, 0x7FEB352D, 0x846CA68B
 
 
 def mix64(z: int) -> int:
@@ -25,17 +40,6 @@ def mix64(z: int) -> int:
     z ^= z >> 27
     z = (z * 0x94D049BB133111EB) & M64
     z ^= z >> 31
-    return z
-
-
-def _mix64_vec(z: np.ndarray) -> np.ndarray:
-    z = z.astype(np.uint64)
-    with np.errstate(over="ignore"):
-        z ^= z >> np.uint64(30)
-        z *= np.uint64(0xBF58476D1CE4E5B9)
-        z ^= z >> np.uint64(27)
-        z *= np.uint64(0x94D049BB133111EB)
-        z ^= z >> np.uint64(31)
     return z
 
 
@@ -52,39 +56,60 @@ def hash_obs(obs: np.ndarray, seed: int) -> int:
     opp = _words(obs[1].reshape(-1) > 0.5, nw)
     lm = np.flatnonzero(obs[2].reshape(-1) > 0.5)
     last = int(lm[0]) if len(lm) else -1
-    h = mix64((seed & M64) ^ GOLD)
-    for w in own:
-        h = mix64(h ^ w)
-    for w in opp:
-        h = mix64(h ^ w)
-    return mix64(h ^ ((last + 1) & M64))
+    h0 = mix64((seed & M64) ^ GOLD)
+    acc = 0
+    for w in range(nw):
+        acc ^= mix64((own[w] ^ h0) + (2 * w + 1) * GOLD)
+        acc ^= mix64((opp[w] ^ h0) + (2 * w + 2) * GOLD)
+    return mix64(acc + (last + 1) * CV)
+
+
+def action_hash(h: int, A: int) -> np.ndarray:
+    """x_a for a = 0..A-1 (uint32)."""
+    s = np.uint32((h & 0xFFFFFFFF) ^ (h >> 32))
+    with np.errstate(over="ignore"):
+        x = s + np.arange(1, A + 1, dtype=np.uint32) * np.uint32(GOLD32)
+        x ^= x >> np.uint32(16)
+        x *= np.uint32(M1_32)
+        x ^= x >> np.uint32(15)
+        x *= np.uint32(M2_32)
+    return x
 
 
 def heads(h: int, A: int, logit_div: int):
-    a = np.arange(1, A + 1, dtype=np.uint64)
-    with np.errstate(over="ignore"):
-        z = np.uint64(h) + a * np.uint64(GOLD)
-    k = (_mix64_vec(z) >> np.uint64(58)).astype(np.int64)
-    logits = (k - 32).astype(np.float32) / np.float32(logit_div)
-    value = float(((mix64(h ^ CV) >> 40) % 33) - 16) / 16.0
+    """(logits float32 [A], value as a Python float)."""
+    x = action_hash(h, A)
+    vk = (h >> 40) & 0xFFFFFF
+    if logit_div > 0:
+        logits = ((x >> np.uint32(26)).astype(np.int64) - 32).astype(np.float32) / np.float32(logit_div)
+        value = float((vk % 33) - 16) / 16.0
+    else:
+        logits = ((x >> np.uint32(8)).astype(np.int64) - (1 << 23)).astype(np.float32) * np.float32(2.0 ** -21)
+        value = float(vk - (1 << 23)) * 2.0 ** -23
     return logits.astype(np.float32), value
 
 
 def child_hidden(h_parent: int, action: int) -> int:
-    return mix64(h_parent ^ mix64(((action + 1) + CA) & M64))
+    return mix64(h_parent + (action + 1) * CA)
 
 
-def reward_of(h: int) -> float:
-    return float(((mix64(h ^ CR) >> 40) % 5) - 2) / 16.0
+def reward_of(h: int, logit_div: int = 16) -> float:
+    rk = (h >> 16) & 0xFFFFFF
+    if logit_div > 0:
+        return float((rk % 5) - 2) / 16.0
+    return float(rk - (1 << 23)) * 2.0 ** -25
 
 
 class E0Queue:
     """Synchronous stand-in for (request_queue, result_queue), same shape as the reference's
-    MockInferenceQueue / LocalInferenceEngine.  kind 0 = hash evaluator, 1 = constant."""
+    MockInferenceQueue / LocalInferenceEngine.  kind 0 = hash evaluator (logit_div 0 = dense), 1 = constant.
+    value_dtype: None -> Python floats / float64 arrays (the upstream test mock); np.float32 -> np.float32
+    scalars and float32 [k,1] arrays (the reference's inference server, workers.py:355,368)."""
 
-    def __init__(self, seed=0, logit_div=16, kind=0, const_value=0.5, const_reward=0.0):
+    def __init__(self, seed=0, logit_div=16, kind=0, const_value=0.5, const_reward=0.0, value_dtype=None):
         self.seed, self.logit_div, self.kind = int(seed), int(logit_div), int(kind)
         self.const_value, self.const_reward = float(const_value), float(const_reward)
+        self.f32 = value_dtype is not None and np.dtype(value_dtype) == np.float32
         self.pending = []
         self.n_initial = 0
         self.n_recurrent = 0
@@ -97,6 +122,9 @@ class E0Queue:
             raise Empty
         return self.pending.pop(0)
 
+    def _scalar(self, v):
+        return np.float32(v) if self.f32 else float(v)
+
     def get(self, timeout=None):
         if not self.pending:
             raise Empty
@@ -105,10 +133,10 @@ class E0Queue:
             self.n_initial += 1
             A = data.shape[1] * data.shape[2]
             if self.kind == 1:
-                return np.zeros(A, np.float32), self.const_value, np.array([[1]], np.uint64)
+                return np.zeros(A, np.float32), self._scalar(self.const_value), np.array([[1]], np.uint64)
             h = hash_obs(data, self.seed)
             logits, value = heads(h, A, self.logit_div)
-            return logits, value, np.array([[h]], dtype=np.uint64)
+            return logits, self._scalar(value), np.array([[h]], dtype=np.uint64)
         hidden, actions = data
         self.n_recurrent += 1
         k = len(actions)
@@ -121,9 +149,10 @@ class E0Queue:
                 continue
             hc = child_hidden(int(hidden[i, 0]), int(actions[i]))
             logits, value = heads(hc, self._A, self.logit_div)
-            ps.append(logits); vs.append(value); hs.append(hc); rs.append(reward_of(hc))
-        return (np.stack(ps), np.array(vs, np.float64).reshape(k, 1),
-                np.array(hs, np.uint64).reshape(k, 1), np.array(rs, np.float64).reshape(k, 1))
+            ps.append(logits); vs.append(value); hs.append(hc); rs.append(reward_of(hc, self.logit_div))
+        dt = np.float32 if self.f32 else np.float64
+        return (np.stack(ps), np.array(vs, dt).reshape(k, 1),
+                np.array(hs, np.uint64).reshape(k, 1), np.array(rs, dt).reshape(k, 1))
 
     _A = 0
 

@@ -73,6 +73,19 @@ def _search_cases(N):
     cases.append(dict(base, n_moves=5, kind=1, const_value=1.5, const_reward=0.25))  # exercises the clip
     if N == 15:
         cases = cases[:10] + cases[10:16:2] + cases[-6:]
+    # dense (unquantised) logits / values: logit_div = 0 -- what a real network's outputs look like
+    for n_moves in ([0, 5, A // 3, A - 9] if N != 15 else [0, 9, A // 2]):
+        cases.append(dict(base, n_moves=n_moves, logit_div=0))
+    # the production dtype: the evaluator returns np.float32 scalars like the reference's inference server
+    # (workers.py:355,368) -> float32 value_sum / Q / MinMaxStats under NumPy >= 2
+    f32 = [dict(base, n_moves=0), dict(base, n_moves=6), dict(base, n_moves=A // 2),
+           dict(base, n_moves=0, logit_div=0), dict(base, n_moves=4, logit_div=0), dict(base, n_moves=A // 3, logit_div=0),
+           dict(base, n_moves=A - 5, logit_div=0), dict(base, n_moves=3, logit_div=0, K=8),
+           dict(base, n_moves=7, logit_div=0, S=33), dict(base, n_moves=5, logit_div=0, discount=1.0, delta=0.01),
+           dict(base, n_moves=5, kind=1, const_value=0.5), dict(base, n_moves=5, kind=1, const_value=1.5, const_reward=0.25)]
+    if N == 15:
+        f32 = f32[:2] + f32[3:7] + f32[-2:]
+    cases += [dict(c, vdtype=1) for c in f32]
     return cases
 
 
@@ -88,7 +101,8 @@ def gen_search(mode_name, N):
         rs = np.random.RandomState(seed)
         g = _random_position(N, p["n_moves"], rs, game_mod, 5)
         q = E0Queue(seed=seed, logit_div=p.get("logit_div", 16), kind=p.get("kind", 0),
-                    const_value=p.get("const_value", 0.5), const_reward=p.get("const_reward", 0.0))
+                    const_value=p.get("const_value", 0.5), const_reward=p.get("const_reward", 0.0),
+                    value_dtype=np.float32 if p.get("vdtype", 0) else None)
         q.set_action_space(A)
         eng = Engine(0, q, q)
         # capture the root Node and the per-evaluation leaf (action, depth)
@@ -139,7 +153,8 @@ def gen_search(mode_name, N):
             ta, td = trace_a, trace_d
         lm = -1 if g.last_move is None else int(g.last_move[0]) * N + int(g.last_move[1])
         rows.append(dict(
-            params=np.array([N, 5, p["S"], p["K"], p.get("kind", 0), p.get("logit_div", 16), seed], np.int64),
+            params=np.array([N, 5, p["S"], p["K"], p.get("kind", 0), p.get("logit_div", 16), seed, p.get("vdtype", 0)], np.int64),
+            value_is_f32=int(isinstance(value, np.float32)),
             fparams=np.array([p.get("c_visit", 30), p.get("c_scale", 1.0), p.get("delta", 1e-3),
                               p.get("discount", 0.997), p.get("const_value", 0.5), p.get("const_reward", 0.0)], np.float64),
             board=board0.astype(np.int8), player=int(g.current_player), last_move=lm, move_count=int(g.move_count),
@@ -148,7 +163,9 @@ def gen_search(mode_name, N):
             n_initial=q.n_initial, n_recurrent=q.n_recurrent,
             leaf_actions=np.array(ta, np.int32), leaf_depths=np.array(td, np.int32),
             batch_sizes=np.array(batch_sizes, np.int32)))
-        print(f"[{mode_name} N={N}] case {ci}: S={p['S']} K={p['K']} moves={p['n_moves']} -> action {action} "
+        assert isinstance(value, np.float32) == bool(p.get("vdtype", 0)), type(value)
+        print(f"[{mode_name} N={N}] case {ci}: S={p['S']} K={p['K']} moves={p['n_moves']} div={p.get('logit_div', 16)} "
+              f"f32={p.get('vdtype', 0)} -> action {action} "
               f"value {float(value):+.6f} maxvisit {visits.max()} evals {q.n_initial}+{q.n_recurrent}", flush=True)
     out = {}
     for i, r in enumerate(rows):
@@ -158,8 +175,9 @@ def gen_search(mode_name, N):
     np.savez_compressed(os.path.join(HERE, f"search_{mode_name}_{N}.npz"), **out)
 
 
-def gen_selfplay(N, S, seed, mode_name="az"):
-    """One whole game through the reference's own universal_worker (workers.py:129-241)."""
+def gen_selfplay(N, S, seed, mode_name="az", logit_div=16, vdtype=0):
+    """One whole game through the reference's own universal_worker (workers.py:129-241).
+    logit_div 0 = dense E0 logits; vdtype 1 = np.float32 evaluator values (the production dtype)."""
     from e0_py import E0Queue
     import queue
     config, game_mod, mcts = _import_reference(N)
@@ -185,7 +203,7 @@ def gen_selfplay(N, S, seed, mode_name="az"):
 
     shutdown = Flag()
     data_q = Sink(on_put=shutdown.set)
-    q = E0Queue(seed=seed, logit_div=16)
+    q = E0Queue(seed=seed, logit_div=logit_div, value_dtype=np.float32 if vdtype else None)
     q.set_action_space(N * N)
     cwd = os.getcwd()
     tmp = tempfile.mkdtemp()
@@ -200,7 +218,7 @@ def gen_selfplay(N, S, seed, mode_name="az"):
     T = len(rec.actions)
     U = config.NUM_UNROLL_STEPS
     out = dict(
-        params=np.array([N, 5, S, 16, seed, U, config.N_STEPS, version], np.int64),
+        params=np.array([N, 5, S, 16, seed, U, config.N_STEPS, version, logit_div, vdtype], np.int64),
         discount=float(config.DISCOUNT),
         actions=np.array(rec.actions, np.int32),
         rewards=np.array(rec.rewards, np.float64),
@@ -232,7 +250,8 @@ def gen_selfplay(N, S, seed, mode_name="az"):
     out["search_values"] = np.array(sv, np.float64)
     out["winner"] = int(g.get_game_ended())
     print(f"[selfplay {mode_name} N={N} S={S}] T={T} winner={out['winner']} slices={len(slices)}", flush=True)
-    np.savez_compressed(os.path.join(HERE, f"selfplay_{mode_name}_{N}_{S}.npz"), **out)
+    suffix = ("_dense" if logit_div == 0 else "") + ("_f32" if vdtype else "")
+    np.savez_compressed(os.path.join(HERE, f"selfplay_{mode_name}_{N}_{S}{suffix}.npz"), **out)
 
 
 def gen_game():
@@ -368,7 +387,8 @@ def gen_augment():
     config.NUM_UNROLL_STEPS, config.N_STEPS = 5, 5
     config.DEVICE = torch.device("cpu")
     sp = np.load(os.path.join(HERE, "selfplay_az_6_36.npz"))
-    pick = np.array([0, 3, 7, 18, 29, 31, 33, 35])                      # includes slices padded at the game's end
+    T = len(sp["slice_obs"])
+    pick = np.array([0, 3, 7, T // 2, T - 7, T - 5, T - 3, T - 1])     # includes slices padded at the game's end
     obs_b, act_b = torch.from_numpy(sp["slice_obs"][pick]), torch.from_numpy(sp["slice_act"][pick])
     rew_b, pi_b, val_b = (torch.from_numpy(sp[k][pick]) for k in ("slice_rew", "slice_pi", "slice_val"))
     B, U1, A = pi_b.shape
@@ -435,11 +455,13 @@ if __name__ == "__main__":
         for N in (6, 9, 15):
             _sub("search_az", N); _sub("search_mz", N)
         _sub("selfplay", 6, 36, 11, "az"); _sub("selfplay", 9, 100, 12, "az"); _sub("selfplay", 6, 50, 13, "mz")
+        _sub("selfplay", 9, 64, 14, "az", 0, 1); _sub("selfplay", 6, 50, 15, "mz", 0, 1)
         _sub("game"); _sub("per"); _sub("tactics"); _sub("network"); _sub("augment")
     elif cmd in ("search_az", "search_mz"):
         gen_search(cmd[-2:], int(sys.argv[2]))
     elif cmd == "selfplay":
-        gen_selfplay(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5] if len(sys.argv) > 5 else "az")
+        gen_selfplay(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), sys.argv[5] if len(sys.argv) > 5 else "az",
+                     int(sys.argv[6]) if len(sys.argv) > 6 else 16, int(sys.argv[7]) if len(sys.argv) > 7 else 0)
     elif cmd == "game":
         gen_game()
     elif cmd == "per":

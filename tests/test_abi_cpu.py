@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/gmz.h but not exported by libgmz.so"
     assert set(_lib.SIGNATURES) == set(names), "ctypes SIGNATURES out of sync with include/gmz.h"
     loaded = _lib.load()
-    assert loaded.gmz_version() == 100
+    assert loaded.gmz_version() == 200
 
 
 def test_config_validation_without_gpu():
@@ -39,10 +39,17 @@ def test_config_validation_without_gpu():
     for bad in (_lib.GmzConfig(20, 5, 400, 16, 0, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997),      # board too large
                 _lib.GmzConfig(15, 5, 0, 16, 0, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997),        # no simulations
                 _lib.GmzConfig(15, 5, 400, 33, 0, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997),      # too many top actions
-                _lib.GmzConfig(15, 5, 400, 16, 7, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997)):     # unknown mode
+                _lib.GmzConfig(15, 5, 400, 16, 7, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997),      # unknown mode
+                _lib.GmzConfig(15, 5, 400, 16, 0, 1, 0, 5, 30.0, 1.0, 1e-3, 0.997)):     # unknown accumulation dtype
         assert lib.gmz_workspace_bytes(ctypes.byref(bad)) == 0
         assert lib.gmz_last_error()
     assert lib.gmz_set_roots(None, None, None, None, None, None) != 0     # null engine is an error, not a crash
+    f32 = _lib.GmzConfig(15, 5, 400, 16, 0, 4096, 0, _lib.GMZ_ACCUM_F32, 30.0, 1.0, 1e-3, 0.997)
+    assert lib.gmz_workspace_bytes(ctypes.byref(f32)) == nbytes           # float32 accumulation: same layout
+    # handles that are not live are rejected, and destroying one (again) is a harmless no-op
+    bogus = ctypes.c_void_p(0x1000)
+    assert lib.gmz_finalize(bogus, None, None, None, None, None) != 0 and b"destroyed" in lib.gmz_last_error()
+    assert lib.gmz_destroy(bogus) == 0 and lib.gmz_destroy(None) == 0
 
 
 def test_engine_fails_loudly_without_cuda():

@@ -43,15 +43,17 @@ def test_search_game_reproduces_reference(cfg, mode, N):
     for c in load_search_cases(mode, N)[::2]:
         _apply(cfg, c)
         q = E0Queue(seed=c["seed"], logit_div=c["logit_div"], kind=c["kind"], const_value=c["const_value"],
-                    const_reward=c["const_reward"])
+                    const_reward=c["const_reward"], value_dtype=np.float32 if c["vdtype"] else None)
         q.set_action_space(N * N)
         eng = (AlphaZeroMCTS if mode == "az" else MuZeroMCTS)(0, q, q)
         g = _game(c)
         board0 = g.board.copy()
         np.random.seed(c["seed"])
         policy, value, action = eng.search(g)
-        tag = f"{mode} N={N} case {c['idx']}"
+        tag = f"{mode} N={N} case {c['idx']} div={c['logit_div']} f32={c['vdtype']}"
         assert np.array_equal(g.board, board0), tag + ": search mutated the game"
+        assert isinstance(value, np.float32) == bool(c["vdtype"]), tag       # the value's type follows the evaluator's, as in the reference
+        assert float(value) == c["value"], tag
         assert isinstance(policy, np.ndarray) and policy.dtype == np.float64 and policy.shape == (N * N,)
         assert isinstance(action, int) and action == c["action"], tag
         assert isinstance(value, (float, np.floating))

@@ -38,30 +38,66 @@ def test_device_evaluator_and_weight_hot_swap():
     assert (p - p2).abs().max() > 1e-2
 
 
-def test_network_driven_search_is_self_consistent():
-    """Stepwise search with a real network: record every (logits, value) the network produced, then
-    replay the same numbers through the oracle's tree logic via a table evaluator -> same visits."""
+@pytest.mark.parametrize("accum", ["float32", "float64"])
+def test_network_driven_search_replayed_through_the_oracle(accum):
+    """Stepwise search with a real network (continuous float32 logits and values): record every
+    (observation -> logits, value) the network produced, then run the CPU oracle's tree logic with a table
+    evaluator returning exactly those numbers -> same visit counts, moves, root values.  accum = float32 is the
+    production dtype (the reference's inference server returns np.float32 scalars, workers.py:355)."""
     import torch
     from datou_gomoku_muzero_b200.engine import SearchEngine
     from datou_gomoku_muzero_b200.network import DeviceEvaluator
-    N, S, G = 9, 40, 8
+    from oracle import oracle
+    N, S, G = 9, 64, 12
     A = N * N
-    eng = SearchEngine(G, board_size=N, num_simulations=S)
-    eng.reset_games()
+    rs = np.random.RandomState(5)
+    boards = np.zeros((G, A), np.int8); players = np.ones(G, np.int8)
+    last = np.full(G, -1, np.int32); mc = np.zeros(G, np.int32)
+    for g in range(G):
+        p = 1
+        for a in rs.permutation(A)[: 3 * g]:
+            boards[g, a] = p; last[g] = a; p = -p; mc[g] += 1
+        players[g] = p
+    eng = SearchEngine(G, board_size=N, num_simulations=S, accum_dtype=accum)
+    eng.set_roots(boards, players, last, mc)
     ev = DeviceEvaluator(_net(3), eng.leaf_obs, dtype=torch.float32, graph=False)
-    gum = torch.from_numpy(np.random.RandomState(0).gumbel(0, 1, (G, A))).cuda()
-    lg, v = ev(eng.root_obs()); eng.root_expand(lg, v, gum)
-    seen = {}
+    gum_h = rs.gumbel(0, 1, (G, A))
+    gum = torch.from_numpy(gum_h).cuda()
+    table = {}
+
+    def record(obs, lg, v):
+        o, l, vv = obs.cpu().numpy(), lg.cpu().numpy(), v.cpu().numpy()
+        for g in range(G):                                  # the evaluator is a pure function of the observation
+            key = o[g].tobytes()
+            cur = (l[g].copy(), float(vv[g]))
+            if key in table:
+                assert np.array_equal(table[key][0], cur[0]) and table[key][1] == cur[1]
+            table[key] = cur
+
+    def net_values(v):
+        return v if accum == "float32" else v.double()       # float64 mode: the same numbers handed over as Python floats
+    obs = eng.root_obs(); lg, v = ev(obs); record(obs, lg, v); eng.root_expand(lg, net_values(v), gum)
     for _ in range(S - 1):
         obs = eng.select()
         lg, v = ev(obs)
-        for g in range(G):                                  # the evaluator is a pure function of the observation
-            key = obs[g].cpu().numpy().tobytes()
-            cur = (lg[g].cpu().numpy().copy(), float(v[g]))
-            if key in seen:
-                assert np.array_equal(seen[key][0], cur[0]) and seen[key][1] == cur[1]
-            seen[key] = cur
-        eng.expand_backup(lg, v)
+        record(obs, lg, v)
+        eng.expand_backup(lg, net_values(v))
     pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
     assert (vis.sum(1) == S - 1).all() and np.allclose(pol.sum(1), 1.0) and (np.abs(val) <= 1).all()
-    assert all(vis[g, act[g]] == vis[g].max() for g in range(G))
+
+    def table_eval(board, player, last_move):               # what game.get_board_state would build (game.py:12-17)
+        o = np.zeros((3, N, N), np.float32)
+        o[0] = board == player; o[1] = board == -player
+        if last_move >= 0:
+            o[2, last_move // N, last_move % N] = 1.0
+        return table[o.tobytes()]
+    oracle.set_eval_callback(table_eval)
+    try:
+        cfg = oracle.make_config(board_size=N, num_simulations=S, eval_kind=3, accum_dtype=int(accum == "float32"))
+        for g in range(G):
+            r = oracle.search(cfg, boards[g], players[g], last[g], mc[g], gum_h[g])
+            assert np.array_equal(vis[g], r["visits"]), (accum, g)
+            assert act[g] == r["action"] and val[g] == r["value"], (accum, g)
+            np.testing.assert_allclose(pol[g], r["policy"], rtol=1e-5, atol=1e-12)
+    finally:
+        oracle.set_eval_callback(None)

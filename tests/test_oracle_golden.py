@@ -15,7 +15,8 @@ def _cfg(c):
     return O.make_config(board_size=c["N"], n_in_row=c["n_in_row"], num_simulations=c["S"], num_top_actions=c["K"],
                          mode=0 if c["mode"] == "az" else 1, eval_kind=c["kind"], logit_div=c["logit_div"],
                          c_visit=c["c_visit"], c_scale=c["c_scale"], minmax_delta=c["delta"], discount=c["discount"],
-                         const_value=c["const_value"], const_reward=c["const_reward"], eval_seed=c["seed"])
+                         const_value=c["const_value"], const_reward=c["const_reward"], eval_seed=c["seed"],
+                         accum_dtype=c["vdtype"])
 
 
 @pytest.mark.parametrize("mode", ["az", "mz"])
@@ -23,14 +24,17 @@ def _cfg(c):
 def test_search_matches_reference(mode, N):
     cases = load_search_cases(mode, N)
     assert len(cases) >= 19
+    assert sum(c["logit_div"] == 0 for c in cases) >= 7 and sum(c["vdtype"] == 1 for c in cases) >= 8   # dense / float32 cases
     for c in cases:
         r = O.search(_cfg(c), c["board"], c["player"], c["last_move"], c["move_count"], c["gumbel"], trace=True)
-        tag = f"{mode} N={N} case {c['idx']}"
+        tag = f"{mode} N={N} case {c['idx']} div={c['logit_div']} f32={c['vdtype']}"
+        assert r["all_visited"] == 0, tag
+        assert int(c["value_is_f32"]) == c["vdtype"], tag
         assert np.array_equal(r["visits"], c["visits"]), tag
         assert r["action"] == c["action"], tag
         assert np.array_equal(r["leaf_actions"], c["leaf_actions"]), tag
         assert np.array_equal(r["leaf_depths"], c["leaf_depths"]), tag
-        assert r["value"] == c["value"], tag                      # float64 accumulation is bit-exact
+        assert r["value"] == c["value"], tag                      # float64 / float32 accumulation is bit-exact
         np.testing.assert_allclose(r["policy"], c["policy"], rtol=1e-12, atol=1e-15, err_msg=tag)
         assert abs(r["policy"].sum() - 1.0) < 1e-9
         if mode == "az":
@@ -49,7 +53,7 @@ def test_e0_python_and_c_agree():
             player = int(rs.choice([-1, 1]))
             last = int(rs.randint(-1, A))
             seed = int(rs.randint(0, 2**31))
-            div = int(rs.choice([2, 4, 16]))
+            div = int(rs.choice([0, 2, 4, 16]))
             cfg = O.make_config(board_size=N, eval_seed=seed, logit_div=div)
             lg, v, h = O.e0_initial(cfg, board, player, last)
             obs = np.zeros((3, N, N), np.float32)
@@ -63,7 +67,8 @@ def test_e0_python_and_c_agree():
             lg2, v2, r2, h2 = O.e0_recurrent(cfg, h, a)
             hc = e0_py.child_hidden(hp, a)
             lp2, vp2 = e0_py.heads(hc, A, div)
-            assert hc == h2 and vp2 == v2 and e0_py.reward_of(hc) == r2 and np.array_equal(lp2, lg2)
+            assert hc == h2 and vp2 == v2 and e0_py.reward_of(hc, div) == r2 and np.array_equal(lp2, lg2)
+            assert np.float32(vp) == vp and np.float32(r2) == r2        # exactly representable in float32
 
 
 def test_pyset_order_matches_cpython():
@@ -120,13 +125,15 @@ def test_sumtree_add_sequence():
     assert t.tree[0] == pytest.approx(sum([11, 12, 8, 9, 10]))
 
 
-@pytest.mark.parametrize("name,mode", [("selfplay_az_6_36", 0), ("selfplay_az_9_100", 0), ("selfplay_mz_6_50", 1)])
+@pytest.mark.parametrize("name,mode", [("selfplay_az_6_36", 0), ("selfplay_az_9_100", 0), ("selfplay_mz_6_50", 1),
+                                       ("selfplay_az_9_64_dense_f32", 0), ("selfplay_mz_6_50_dense_f32", 1)])
 def test_selfplay_game_matches_reference(name, mode):
     """Whole game through the reference's universal_worker vs the oracle's game loop."""
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
-    N, nir, S, K, seed, U, n_steps, version = (int(x) for x in z["params"])
+    N, nir, S, K, seed, U, n_steps, version, logit_div, vdtype = (int(x) for x in z["params"])
     A = N * N
-    cfg = O.make_config(board_size=N, n_in_row=nir, num_simulations=S, num_top_actions=K, mode=mode, eval_seed=seed)
+    cfg = O.make_config(board_size=N, n_in_row=nir, num_simulations=S, num_top_actions=K, mode=mode, eval_seed=seed,
+                        logit_div=logit_div, accum_dtype=vdtype)
     gumbel = np.random.RandomState(seed).gumbel(0, 1, (A + 1, A))
     g = O.selfplay_game(cfg, gumbel)
     T = len(z["actions"])

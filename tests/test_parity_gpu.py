@@ -18,10 +18,12 @@ def _engine(c, G=1, mode=None):
     from datou_gomoku_muzero_b200.engine import SearchEngine
     return SearchEngine(G, board_size=c["N"], n_in_row=c["n_in_row"], num_simulations=c["S"], num_top_actions=c["K"],
                         mode=mode or ("AlphaZero" if c["mode"] == "az" else "MuZero"), c_visit=c["c_visit"],
-                        c_scale=c["c_scale"], minmax_delta=c["delta"], discount=c["discount"])
+                        c_scale=c["c_scale"], minmax_delta=c["delta"], discount=c["discount"],
+                        accum_dtype="float32" if c["vdtype"] else "float64")
 
 
 def _check(c, pol, val, act, vis, ta, td, tag):
+    tag += f" div={c['logit_div']} f32={c['vdtype']}"
     assert np.array_equal(vis, c["visits"]), f"{tag}: visit counts"
     assert int(act) == c["action"], f"{tag}: action {act} vs {c['action']}"
     if ta is not None:
@@ -29,6 +31,7 @@ def _check(c, pol, val, act, vis, ta, td, tag):
         assert np.array_equal(ta[:n], c["leaf_actions"]), f"{tag}: leaf action trace"
         assert np.array_equal(td[:n], c["leaf_depths"]), f"{tag}: leaf depth trace"
     np.testing.assert_allclose(val, c["value"], rtol=RTOL, atol=1e-12, err_msg=tag)
+    assert float(val) == c["value"], f"{tag}: root value bits"        # float64 / float32 accumulation is bit-exact
     np.testing.assert_allclose(pol, c["policy"], rtol=RTOL, atol=1e-12, err_msg=tag)
 
 
@@ -67,7 +70,7 @@ def test_constant_evaluator_goldens(N):
         eng = _engine(c, G=1)
         eng.set_roots(c["board"].reshape(1, -1), [c["player"]], [c["last_move"]], [c["move_count"]])
         lg = torch.zeros((1, N * N), dtype=torch.float32, device="cuda")
-        v = torch.full((1,), c["const_value"], dtype=torch.float64, device="cuda")
+        v = torch.full((1,), c["const_value"], dtype=torch.float32 if c["vdtype"] else torch.float64, device="cuda")
         eng.root_expand(lg, v, c["gumbel"].reshape(1, -1))
         for _ in range(c["S"] - 1):
             eng.select()
@@ -97,7 +100,8 @@ def test_muzero_search_matches_reference_goldens(N):
         else:
             h0, lg, v = 1, np.zeros(A, np.float32), c["const_value"]
         hidden[0] = h0
-        eng.root_expand(lg.reshape(1, -1), np.array([v], np.float64), c["gumbel"].reshape(1, -1))
+        vdt = np.float32 if c["vdtype"] else np.float64
+        eng.root_expand(lg.reshape(1, -1), np.array([v], vdt), c["gumbel"].reshape(1, -1))
         trace_a, trace_d, n_eval = [], [], 0
         for _ in range(c["S"]):
             ps, ac, cs, dp = (int(t.cpu()[0]) for t in eng.select_mz())
@@ -106,12 +110,12 @@ def test_muzero_search_matches_reference_goldens(N):
             if c["kind"] == 0:
                 hc = e0_py.child_hidden(hidden[ps], ac)
                 lg, v = e0_py.heads(hc, A, c["logit_div"])
-                r = e0_py.reward_of(hc)
+                r = e0_py.reward_of(hc, c["logit_div"])
             else:
                 hc, lg, v, r = 2, np.zeros(A, np.float32), c["const_value"], c["const_reward"]
             hidden[cs] = hc
             trace_a.append(ac); trace_d.append(dp); n_eval += 1
-            eng.expand_backup(lg.reshape(1, -1), np.array([v], np.float64), np.array([r], np.float64))
+            eng.expand_backup(lg.reshape(1, -1), np.array([v], vdt), np.array([r], vdt))
         assert n_eval == c["n_recurrent"], f"mz N={N} case {c['idx']}: {n_eval} evaluations vs {c['n_recurrent']}"
         pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
         _check(c, pol[0], val[0], act[0], vis[0], np.array(trace_a), np.array(trace_d), f"mz N={N} case {c['idx']}")
@@ -132,7 +136,7 @@ def test_e0_kernel_matches_python():
             obs[b, 0] = cells == 1; obs[b, 1] = cells == -1
             if b % 4:
                 a = rs.randint(A); obs[b, 2, a // N, a % N] = 1
-        seed, div = int(rs.randint(1 << 30)), int(rs.choice([2, 4, 16]))
+        seed, div = int(rs.randint(1 << 30)), int(rs.choice([0, 2, 3, 16]))
         lg, v = eng.e0_eval(torch.from_numpy(obs).cuda(), seed, div)
         lg, v = lg.cpu().numpy(), v.cpu().numpy()
         for b in range(B):
@@ -141,9 +145,11 @@ def test_e0_kernel_matches_python():
             assert np.array_equal(lg[b], l2) and v[b] == v2, (N, b)
 
 
+@pytest.mark.parametrize("div,accum", [(16, "float64"), (0, "float64"), (0, "float32"), (16, "float32")])
 @pytest.mark.parametrize("N,S,G", [(9, 100, 64), (15, 400, 96), (19, 64, 16), (6, 50, 64)])
-def test_random_positions_match_oracle(N, S, G):
-    """Seeded random mid-game positions + random noise: fused kernel vs CPU oracle."""
+def test_random_positions_match_oracle(N, S, G, div, accum):
+    """Seeded random mid-game positions + random noise: fused kernel vs CPU oracle, with quantised and dense
+    (unquantised, div = 0) logits, in float64 and float32 (production dtype) accumulation."""
     from datou_gomoku_muzero_b200.engine import SearchEngine
     from oracle import oracle
     A = N * N
@@ -160,18 +166,19 @@ def test_random_positions_match_oracle(N, S, G):
         players[g] = p; mc[g] = k
     gumbel = rs.gumbel(0, 1, (G, A))
     seed = 77
-    eng = SearchEngine(G, board_size=N, num_simulations=S, num_top_actions=16)
+    eng = SearchEngine(G, board_size=N, num_simulations=S, num_top_actions=16, accum_dtype=accum)
     eng.set_roots(boards, players, last, mc)
-    eng.search_e0(gumbel, seed)
+    eng.search_e0(gumbel, seed, div)
     pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
-    cfg = oracle.make_config(board_size=N, num_simulations=S, num_top_actions=16, eval_seed=seed)
+    cfg = oracle.make_config(board_size=N, num_simulations=S, num_top_actions=16, eval_seed=seed, logit_div=div,
+                             accum_dtype=int(accum == "float32"))
     opol, oval, oact, ovis = oracle.search_batch(cfg, boards, players, last, mc, gumbel)
     assert act[0] == -1 and pol[0].sum() == 0 and val[0] == 0.0      # sentinel (mcts.py:214-215)
     assert np.array_equal(vis, ovis)
     assert np.array_equal(act, oact)
     np.testing.assert_allclose(val, oval, rtol=RTOL, atol=1e-12)
     np.testing.assert_allclose(pol, opol, rtol=RTOL, atol=1e-12)
-    assert np.array_equal(val, oval), "float64 value accumulation should be bit-exact"
+    assert np.array_equal(val, oval), "value accumulation should be bit-exact"
     # the roots must come back unchanged (search() must not mutate the game)
     b2, p2, l2, m2 = (t.cpu().numpy() for t in eng.get_roots())
     assert np.array_equal(b2.reshape(G, A), boards) and np.array_equal(p2, players)
@@ -257,8 +264,9 @@ def test_folded_recurrent_inference_matches_module():
     torch.testing.assert_close(lh, h2, rtol=1e-3, atol=2e-3)
 
 
+@pytest.mark.parametrize("div,accum", [(16, "float64"), (0, "float32")])
 @pytest.mark.parametrize("N,S,G", [(9, 100, 64), (15, 400, 64), (6, 50, 48)])
-def test_muzero_fused_search_matches_oracle(N, S, G):
+def test_muzero_fused_search_matches_oracle(N, S, G, div, accum):
     """MuZero mode inside the persistent kernel (E0's recurrent evaluator inlined) vs the oracle."""
     import torch
     from datou_gomoku_muzero_b200.engine import SearchEngine
@@ -274,11 +282,12 @@ def test_muzero_fused_search_matches_oracle(N, S, G):
             boards[g, a] = p; last[g] = a; p = -p
         players[g] = p; mc[g] = k
     gumbel = rs.gumbel(0, 1, (G, A))
-    eng = SearchEngine(G, board_size=N, num_simulations=S, mode="MuZero")
+    eng = SearchEngine(G, board_size=N, num_simulations=S, mode="MuZero", accum_dtype=accum)
     eng.set_roots(boards, players, last, mc)
-    ta, td = eng.search_e0(torch.from_numpy(gumbel).cuda(), seed, trace=True)
+    ta, td = eng.search_e0(torch.from_numpy(gumbel).cuda(), seed, div, trace=True)
     pol, val, act, vis = (t.cpu().numpy() for t in eng.finalize())
-    cfg = oracle.make_config(board_size=N, num_simulations=S, mode=1, eval_seed=seed)
+    cfg = oracle.make_config(board_size=N, num_simulations=S, mode=1, eval_seed=seed, logit_div=div,
+                             accum_dtype=int(accum == "float32"))
     opol, oval, oact, ovis = oracle.search_batch(cfg, boards, players, last, mc, gumbel)
     assert np.array_equal(vis, ovis) and np.array_equal(act, oact) and np.array_equal(val, oval)
     np.testing.assert_allclose(pol, opol, rtol=RTOL, atol=1e-12)
@@ -295,7 +304,7 @@ def test_deep_paths_match_oracle(mode):
     import torch
     from datou_gomoku_muzero_b200.engine import SearchEngine
     from oracle import oracle
-    N, S, G, seed, div = 9, 300, 12, 5, 2
+    N, S, G, seed, div = 9, 300, 12, 3, 2
     A = N * N
     rs = np.random.RandomState(4)
     boards = np.zeros((G, A), np.int8); players = np.ones(G, np.int8)

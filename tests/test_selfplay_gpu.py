@@ -108,7 +108,7 @@ def test_device_slice_store_matches_reference_slices():
     from datou_gomoku_muzero_b200.trajectory import (DeviceSliceStore, TrajectoryStore, build_game_record,
                                                      cut_training_slices)
     z = np.load(os.path.join(GOLDEN_DIR, "selfplay_az_9_100.npz"))
-    N, nir, S, K, seed, U, n_steps, version = (int(x) for x in z["params"])
+    N, nir, S, K, seed, U, n_steps, version = (int(x) for x in z["params"][:8])
     A = N * N
     saved = (config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS)
     config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS = float(z["discount"]), n_steps, U
@@ -164,8 +164,9 @@ def test_device_batch_d4_augmentation_matches_reference_loss_path():
     from oracle import oracle
     z = np.load(os.path.join(GOLDEN_DIR, "selfplay_az_6_36.npz"))
     g = np.load(os.path.join(GOLDEN_DIR, "augment_kat.npz"))
-    N, nir, S, K, seed, U, n_steps, version = (int(x) for x in z["params"])
-    pick = [0, 3, 7, 18, 29, 31, 33, 35]
+    N, nir, S, K, seed, U, n_steps, version = (int(x) for x in z["params"][:8])
+    T = len(z["actions"])
+    pick = [0, 3, 7, T // 2, T - 7, T - 5, T - 3, T - 1]            # as tests/golden/make_golden.py gen_augment
     saved = (config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS)
     config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS = float(z["discount"]), n_steps, U
     try:

@@ -10,14 +10,15 @@ from _golden_util import GOLDEN_DIR
 import pytest
 
 
-@pytest.mark.parametrize("name", ["selfplay_az_9_100", "selfplay_az_6_36", "selfplay_mz_6_50"])
+@pytest.mark.parametrize("name", ["selfplay_az_9_100", "selfplay_az_6_36", "selfplay_mz_6_50", "selfplay_az_9_64_dense_f32",
+                                  "selfplay_mz_6_50_dense_f32"])
 def test_game_record_and_slices_match_reference_golden(name):
     """Host post-processing (final rewards, n-step targets, slice cutting) against the GameRecord /
     TrainingSlices the reference's universal_worker produced (tests/golden/selfplay_*.npz)."""
     from datou_gomoku_muzero_b200.config import config
     from datou_gomoku_muzero_b200.trajectory import build_game_record, cut_training_slices
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
-    N, nir, S, K, seed, U, n_steps, version = (int(x) for x in z["params"])
+    N, nir, S, K, seed, U, n_steps, version = (int(x) for x in z["params"][:8])
     saved = (config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS)
     config.DISCOUNT, config.N_STEPS, config.NUM_UNROLL_STEPS = float(z["discount"]), n_steps, U
     try:
