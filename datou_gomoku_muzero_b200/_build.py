@@ -34,14 +34,20 @@ def _stale(so=SO) -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, verify: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, verify: bool = False, variant: str = "", defines=()) -> str:
+    """variant / defines: development builds with extra -D flags into build_variants/libgmz_<variant>.so
+    (loaded through the GMZ_LIB override by tools/kbench.py; never by the package itself)."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     so = SO_VERIFY if verify else SO
+    if variant:
+        os.makedirs(os.path.join(os.path.dirname(HERE), "build_variants"), exist_ok=True)
+        so = os.path.join(os.path.dirname(HERE), "build_variants", f"libgmz_{variant}.so")
     if not force and not _stale(so):
         return so
-    objdir = os.path.join(HERE, "build", "verify" if verify else "release")
+    objdir = os.path.join(HERE, "build", variant or ("verify" if verify else "release"))
     os.makedirs(objdir, exist_ok=True)
-    common = [nvcc, *NVCC_FLAGS, *(["-DGMZ_VERIFY_FAST"] if verify else []), *(["-Xptxas", "-v"] if verbose else [])]
+    common = [nvcc, *NVCC_FLAGS, *(["-DGMZ_VERIFY_FAST"] if verify else []), *(["-Xptxas", "-v"] if verbose else []),
+              *[f"-D{d}" for d in defines]]
     jobs = []
     for s in SOURCES:
         jobs.append((common + ["-c", os.path.join(CSRC, s), "-o", os.path.join(objdir, s[:-3] + ".o")]))

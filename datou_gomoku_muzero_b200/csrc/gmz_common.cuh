@@ -72,12 +72,12 @@ struct Params {
     double *nW;      // [G*S]      node.value_sum
     double *nR;      // [G*S]      node.reward (MuZero mode only)
     u64 *nH;         // [G*S]      E0 hidden state of a node (MuZero mode + fixed evaluator only)
-    short *path;     // [G][S+2]   node ids root..leaf-parent of the pending simulation
+    int2 *path;      // [G][S+2]   (node id, mirror word) root..leaf-parent of the pending simulation (see PathReg)
     short *pyset;    // [ceil(G/4)*4][4096] scratch for the CPython-set tie-break (rare path)
     char *sel_overflow;   // [ceil(G/4)*4][128*NC*20 B] select scratch for nodes with > 64 visited children
     struct PlayCtl *ctl;   // play-kernel ticket counter + statistics
-    int4 *nHdr;      // [G*S]      summary of a node's unvisited actions + number of children (see gmz_tree.cuh)
-    int2 *nList;     // [G*S][32]  a node's children in creation order: ((action << 16) | child id, logit bits)
+    char *nBlk;      // [G*S][1 KiB]  per node: summary of its unvisited actions + its children with their edge
+                     //               statistics mirrored in, 32 slots of 32 bytes (see gmz_tree.cuh)
 };
 
 // Device-side control block of the play kernel (+ select statistics).
@@ -155,6 +155,13 @@ __device__ __forceinline__ float warp_sum_f32(float v)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(GMZ_FULL, v, o));
     return v;
+}
+// Sum of non-negative terms (each <= ~400, at least one == 1 up to rounding) in 2^-23 fixed point: ONE integer
+// REDUX instead of a five-step shuffle tree.  Absolute error <= 32 * 2^-24 on a sum >= 1 (certified select only).
+__device__ __forceinline__ float warp_sum_fx(float v)
+{
+    const unsigned q = __float2uint_rn(__fmul_rn(v, 8388608.0f));
+    return __fmul_rn((float)__reduce_add_sync(GMZ_FULL, q), 1.1920928955078125e-07f);
 }
 // 1/x for x in the float range, to ~1e-15: float reciprocal + two Newton steps (the certified select
 // path only needs ~1e-9; the exact path keeps the correctly rounded division).

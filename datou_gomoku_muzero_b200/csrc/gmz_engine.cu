@@ -183,13 +183,13 @@ k_select(const __grid_constant__ Params p, T *leaf_obs, int32_t *out_a, int32_t 
     }
     wg_valid_bits<NC>(p, w, lane);
     __shared__ SelSmem s_sel[WARPS_PER_CTA];
-    short *path = p.path + (size_t)g * (p.S + 2);
+    int2 *path = p.path + (size_t)g * (p.S + 2);
     u64 P = w.P, M = w.M; int colour = w.to_move;
     int lp, la;
-    int mypath;
-    const int depth = descend<NC, MZ, F32>(p, w, path, mypath, s_sel[threadIdx.x >> 5], blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane,
+    PathReg pr;
+    const int depth = descend<NC, MZ, F32>(p, w, path, pr, s_sel[threadIdx.x >> 5], blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane,
                                       lp, la, P, M, colour);
-    if (lane < min(depth, 32)) path[lane] = (short)mypath;      // hand the path to k_expand_backup
+    if (lane < min(depth, 32)) path[lane] = make_int2(pr.node, pr.mir);      // hand the path to k_expand_backup
     if (!MZ && leaf_obs)   // colour is now the player to move at the leaf; last move = la
         obs_write<NC, T>(leaf_obs + (size_t)g * 3 * p.A, p.A, colour > 0 ? P : M, colour > 0 ? M : P, la, lane);
     if (lane == 0) {
@@ -216,7 +216,7 @@ k_expand_backup(const __grid_constant__ Params p, const float *logits, const voi
     if (!s->active || depth <= 0) return;
     WG w; wg_load(p, g, lane, w);
     const int lp = s->leaf_parent, la = s->leaf_action, reps = s->leaf_reps;
-    const short *path = p.path + (size_t)g * (p.S + 2);
+    const int2 *path = p.path + (size_t)g * (p.S + 2);
     float lg[4 * NC];
     load_lane_logits<NC>(logits + (size_t)g * p.A, p.A, lane, lg);
     const double value = load_value(values, vdtype, g);
@@ -225,11 +225,16 @@ k_expand_backup(const __grid_constant__ Params p, const float *logits, const voi
     wg_valid_bits<NC>(p, w, lane);
     node_write_row<NC>(p, w, nn, lg, lane);
     node_init_hdr<NC>(p, w, nn, lg, lane);
-    node_link<NC>(p, w, lp, la, nn, lane);
+    const int nmir = node_link<NC>(p, w, lp, la, nn, lane);
     w.num_nodes = nn + 1;
-    const int mypath = lane < min(depth, 32) ? (int)path[lane] : 0;
-    backup<MZ, F32>(p, w, path, mypath, depth, nn, value, reward, reps, lane);
-    survivor_visit(w, depth, mypath, nn, la, reps, lane);
+    PathReg pr; pr.node = 0; pr.mir = 0; pr.n = 0; pr.W = 0.0; pr.R = 0.0;
+    if (lane < min(depth, 32)) {        // the statistics the fused kernel keeps in registers: re-read them here
+        const int2 t = path[lane]; pr.node = t.x; pr.mir = t.y;
+        const size_t li = w.nbase + (size_t)t.x;
+        pr.n = p.nN[li]; pr.W = p.nW[li]; if (MZ) pr.R = p.nR[li];
+    }
+    backup<MZ, F32>(p, w, path, pr, depth, nn, nmir, value, reward, reps, lane);
+    survivor_visit(w, depth, pr.node, nn, la, reps, lane);
     w.sim_count += reps;
     __syncwarp();
     if (halving_ready(p, w)) sequential_halving<MZ, F32>(p, w, lane);
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_game_step(Params p, const int32
 // ---------------------------------------------------------------------------------------------
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct Layout { size_t gs, logits, child, nN, nW, nR, nH, path, pyset, selov, ctl, hdr, list, total; };
+struct Layout { size_t gs, logits, child, nN, nW, nR, nH, path, pyset, selov, ctl, blk, total; };
 
 static int validate(const gmz_config *c)
 {
@@ -415,12 +420,11 @@ static Layout make_layout(const gmz_config *c)
     L.nW = o; o = align_up(o + G * S * sizeof(double), 256);
     L.nR = o; if (c->mode == GMZ_MODE_MUZERO) o = align_up(o + G * S * sizeof(double), 256);
     L.nH = o; if (c->mode == GMZ_MODE_MUZERO) o = align_up(o + G * S * sizeof(u64), 256);
-    L.path = o; o = align_up(o + G * (S + 2) * sizeof(short), 256);
+    L.path = o; o = align_up(o + G * (S + 2) * sizeof(int2), 256);
     L.pyset = o; o = align_up(o + ((G + 3) / 4 * 4) * 4096 * sizeof(short), 256);
     L.selov = o; o = align_up(o + ((G + 3) / 4 * 4) * AP * 20, 256);
     L.ctl = o; o = align_up(o + sizeof(PlayCtl), 256);
-    L.hdr = o; o = align_up(o + G * S * sizeof(int4), 256);
-    L.list = o; o = align_up(o + G * S * kListCap * sizeof(int2), 256);
+    L.blk = o; o = align_up(o + G * S * (size_t)kBlkBytes, 1024);
     L.total = o;
     return L;
 }
@@ -471,9 +475,9 @@ extern "C" int gmz_create(const gmz_config *cfg, void *workspace, size_t workspa
     p.nN = (int *)(base + L.nN); p.nW = (double *)(base + L.nW);
     p.nR = cfg->mode == GMZ_MODE_MUZERO ? (double *)(base + L.nR) : nullptr;
     p.nH = cfg->mode == GMZ_MODE_MUZERO ? (u64 *)(base + L.nH) : nullptr;
-    p.path = (short *)(base + L.path);
+    p.path = (int2 *)(base + L.path);
     p.pyset = (short *)(base + L.pyset); p.sel_overflow = base + L.selov; p.ctl = (PlayCtl *)(base + L.ctl);
-    p.nHdr = (int4 *)(base + L.hdr); p.nList = (int2 *)(base + L.list);
+    p.nBlk = base + L.blk;
     cudaError_t err = cudaMemsetAsync(base + L.gs, 0, (size_t)p.G * sizeof(GState), (cudaStream_t)stream);
     if (err == cudaSuccess) err = cudaMemsetAsync(base + L.ctl, 0, sizeof(PlayCtl), (cudaStream_t)stream);
     if (err != cudaSuccess) { free(e); return fail("cudaMemsetAsync: %s", cudaGetErrorString(err)); }

@@ -290,7 +290,7 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
         }
         __threadfence();                    // acquire: everything the previous owner wrote is visible
         GState *s = p.gs + g;
-        short *path = p.path + (size_t)g * (p.S + 2);   // root..leaf-parent node ids (global, L1-resident)
+        int2 *path = p.path + (size_t)g * (p.S + 2);    // descent path past depth 31 (rare)
 
         if (a.do_step && s->winner != GMZ_WINNER_NONE) {   // finished earlier, could not restart then
             game_reset(p, s, lane);
@@ -308,8 +308,9 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
             while (w.sim_count < p.S) {
                 u64 P = w.P, M = w.M; int colour = w.to_move;
                 int lp, la;
-                int mypath;
-                const int depth = descend<NC, MZ, F32>(p, w, path, mypath, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
+                PathReg pr;
+                const int depth = descend<NC, MZ, F32>(p, w, path, pr, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
+                path_root_stats<MZ>(p, w, depth, pr, lane);
                 prefetch_parent_rows<NC>(p, w, lp, lane);
                 // AlphaZero mode: evaluate the replayed board (mcts.py:251-253).  MuZero mode: the learned
                 // dynamics, here E0's recurrent half on the parent's hidden state (mcts.py:336-343).
@@ -325,7 +326,7 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                         for (int i = 0; i < 4 * NC; ++i) {
                             const int off = 128 * (i >> 2) + (i & 3);
                             const unsigned x = e0_action_hash(xb + (unsigned)off * E0_GOLD32);
-                            lg[i] = off + 4 * lane < p.A ? __fmul_rn((float)((int)(x >> a.e0.lshift) - a.e0.lbias), a.e0.lmul) : 0.0f;
+                            lg[i] = __fmul_rn((float)((int)(x >> a.e0.lshift) - a.e0.lbias), a.e0.lmul);   // (padding past A: never read, the valid mask covers it)
                         }
                     } else {
 #pragma unroll 1
@@ -337,7 +338,7 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                     node_write_row<NC>(p, w, nn, lg, lane);
                     node_init_hdr<NC>(p, w, nn, lg, lane);
                 }
-                node_link<NC>(p, w, lp, la, nn, lane);
+                const int nmir = node_link<NC>(p, w, lp, la, nn, lane);
                 if (MZ && lane == 0) p.nH[w.nbase + (size_t)nn] = h;
                 if ((a.trace_a != nullptr || a.trace_d != nullptr) && lane == 0) {      // parity tests only
                     if (a.trace_a) a.trace_a[(size_t)g * p.S + ev] = la;
@@ -345,8 +346,8 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                 }
                 w.num_nodes = nn + 1; ++ev;
                 __syncwarp();
-                backup<MZ, F32>(p, w, path, mypath, depth, nn, e0_value(h, a.e0.dense), MZ ? e0_reward(h, a.e0.dense) : 0.0, reps, lane);
-                survivor_visit(w, depth, mypath, nn, la, reps, lane);
+                backup<MZ, F32>(p, w, path, pr, depth, nn, nmir, e0_value(h, a.e0.dense), MZ ? e0_reward(h, a.e0.dense) : 0.0, reps, lane);
+                survivor_visit(w, depth, pr.node, nn, la, reps, lane);
                 w.sim_count += reps;
                 __syncwarp();
                 if (halving_ready(p, w)) sequential_halving<MZ, F32>(p, w, lane);

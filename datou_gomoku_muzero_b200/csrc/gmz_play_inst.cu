@@ -14,6 +14,7 @@
 // grid = what fits on the GPU at once (persistent), capped by the game count.  The occupancy is a
 // property of (device, NC) for this translation unit's (MZ, F32): cached per device, filled under a mutex.
 #include <mutex>
+#include <stdlib.h>
 template <int NC>
 static int launch_t(gmz_engine *e, const PlayArgs &a, cudaStream_t st)
 {
@@ -36,6 +37,7 @@ static int launch_t(gmz_engine *e, const PlayArgs &a, cudaStream_t st)
     }
     int grid = (e->p.G + GMZ_PLAY_WARPS - 1) / GMZ_PLAY_WARPS;
     if (grid > resident) grid = resident;
+    if (const char *cap = getenv("GMZ_PLAY_GRID_CAP")) { const int c = atoi(cap); if (c > 0 && c < grid) grid = c; }   // development: occupancy sweeps
     if (cudaMemsetAsync(&e->p.ctl->next_ticket, 0, 2 * sizeof(unsigned long long), st) != cudaSuccess) return gmz_fail("cudaMemsetAsync(ctl)");
     k_play_e0<NC, MZ, F32><<<grid, 32 * GMZ_PLAY_WARPS, 0, st>>>(e->p, a);
     return gmz_check_launch("k_play_e0");

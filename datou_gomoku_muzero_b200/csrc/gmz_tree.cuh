@@ -485,18 +485,34 @@ __device__ __noinline__ int select_interior_exact(const Params &p, const SelCtx 
 // node therefore carries a 16-byte summary of its unvisited set,
 //     ub  = that best unvisited action,  lub = its logit,
 //     U   = sum over the unvisited valid actions of exp(logit - lub)       (float32, in [1, A])
-// and the list of its children in creation order.  The candidates of a select are then the <= 31
-// visited children plus `ub`: one per lane, no pass over the A logits, and the softmax denominator is
+// and the list of its children in creation order WITH THEIR EDGE STATISTICS MIRRORED IN: one 1 KiB block per
+// node (Params::nBlk) of 32 slots x 32 bytes -- slot 0 the summary, slot j (1..31) child j-1 as
+//     { (action << 16) | child id,  logit,  N(child),  -,  W(child) f64,  reward(child) f64 }.
+// The candidates of a select are then the <= 31 visited children plus `ub`: one per lane, no pass over the A
+// logits, ONE memory round trip per tree level (lane j reads its own slot while every lane reads slot 0; the
+// canonical per-node arrays nN / nW / nR are only read by the exact path, the root and the halving), and the
+// softmax denominator is
 //     sum_visited exp(x_c - mx) + exp(x_ub - mx) * U.
+// The backup keeps the mirror current: it already holds each path node's statistics in registers (handed
+// over by the descent that read them), so it needs no loads at all -- it stores N / W to the node's own
+// arrays and to its slot in the parent's block.
 // The summary is float32 (relative error ~3e-6 on the probabilities), so the decision is CERTIFIED:
 // it is taken only if the best score clears every other candidate by more than that error, or ties
 // with candidates whose inputs are bit-identical (then the lowest action wins, as np.argmax); otherwise
 // the exact float64 path above decides.  Visit counts stay bit-exact; the summary is rebuilt (one pass
 // over the parent's logits, float32 exp) once per simulation, when a child is added.
-constexpr int kListCap = 32;          // list entries per node (Params::nList)
-constexpr int kListSpec = 8;          // entries loaded speculatively with the header
-constexpr int kFastMaxVisited = 31;   // visited children + the best unvisited action fit one warp
-constexpr double kCertEps = 2e-5;     // > 6x the float32 error bound of a probability
+constexpr int kBlkBytes = 1024;       // per-node block (Params::nBlk): 32 slots of 32 bytes
+constexpr int kSlotBytes = 32;
+constexpr int kListSpec = 8;          // slots loaded speculatively with the header (one per lane; 5 of 6 nodes have < 8 children)
+constexpr int kFastMaxVisited = 31;   // visited children (slots 1..31) + the best unvisited action fit one warp
+
+// Per-lane view of the descent path: lane d holds the node at depth d (depths >= 32 spill to Params::path) with
+// the statistics the descent read for it, i.e. BEFORE this simulation's backup.  mir = (parent node << 5) | slot
+// of this node in the parent's block (slot 0 = not mirrored: root children, children past the 31st).
+struct PathReg { int node, mir, n; double W, R; };
+__device__ __forceinline__ char *blk_of(const Params &p, size_t ni) { return p.nBlk + ni * (size_t)kBlkBytes; }
+constexpr double kCertEps = 3e-5;     // > 6x the error bound of a probability on this path (float32 exp / summary ~3e-6,
+                                      //  fixed-point softmax denominator ~2e-6)
 
 // ub / lub / U / "ambiguous" for the candidate set `cand` (bit i = this lane's action i).  Ambiguous:
 // two different unvisited logits closer than 1e-6 -- float64 rounding of logit + sigma could merge
@@ -541,18 +557,19 @@ __device__ __forceinline__ void node_init_hdr(const Params &p, const WG &w, int 
 {
     int ub; float lub, U; bool amb;
     unvisited_summary<NC, false>(lg, w.vb, lane, ub, lub, U, amb);
-    if (lane == 0) p.nHdr[w.nbase + (size_t)node] = hdr_pack(U, lub, ub, 0, amb ? 1 : 0);
+    if (lane == 0) *reinterpret_cast<int4 *>(blk_of(p, w.nbase + (size_t)node)) = hdr_pack(U, lub, ub, 0, amb ? 1 : 0);
 }
 
 // node.children[action] = new_node (mcts.py:27-30, 109): the child-row link, and for a non-root parent
-// the list entry + the refreshed summary of what is still unvisited.
+// the block slot (key + logit; the backup fills in N / W / reward) + the refreshed summary of what is still
+// unvisited.  Returns the new node's mirror word (parent << 5) | slot, slot 0 = not mirrored.
 template <int NC>
-__device__ __forceinline__ void node_link(const Params &p, const WG &w, int parent, int action, int new_node, int lane)
+__device__ __forceinline__ int node_link(const Params &p, const WG &w, int parent, int action, int new_node, int lane)
 {
     constexpr int E = 4 * NC;
     const size_t pi = w.nbase + (size_t)parent;
     short *crow = p.child + pi * (size_t)p.AP;
-    if (parent == 0) { if (lane == 0) crow[action] = (short)new_node; return; }
+    if (parent == 0) { if (lane == 0) crow[action] = (short)new_node; return 0; }
     const float *lrow = p.logits + pi * (size_t)p.AP;
     float lg[E]; unsigned vm = 0;
 #pragma unroll
@@ -562,7 +579,8 @@ __device__ __forceinline__ void node_link(const Params &p, const WG &w, int pare
         lg[4 * j + 0] = t.x; lg[4 * j + 1] = t.y; lg[4 * j + 2] = t.z; lg[4 * j + 3] = t.w;
         vm |= ((c.x >= 0 ? 1u : 0u) | (c.y >= 0 ? 2u : 0u) | (c.z >= 0 ? 4u : 0u) | (c.w >= 0 ? 8u : 0u)) << (4 * j);
     }
-    const int4 h = p.nHdr[pi];
+    char *blk = blk_of(p, pi);
+    const int4 h = *reinterpret_cast<const int4 *>(blk);
     const int owner = (action & 127) >> 2, idx = 4 * (action >> 7) + (action & 3);
     if (lane == owner) vm |= 1u << idx;
     float la = __int_as_float(h.y);                       // the new child is normally the summary's best unvisited action
@@ -576,37 +594,48 @@ __device__ __forceinline__ void node_link(const Params &p, const WG &w, int pare
     }
     __syncwarp();
     const int nvis = (h.z >> 16) + 1;
+    const int slot = nvis <= kFastMaxVisited ? nvis : 0;
     if (lane == 0) {
         crow[action] = (short)new_node;
-        if (nvis <= kListCap) p.nList[pi * kListCap + (nvis - 1)] = make_int2((action << 16) | new_node, __float_as_int(la));
+        if (slot) *reinterpret_cast<int2 *>(blk + kSlotBytes * slot) = make_int2((action << 16) | new_node, __float_as_int(la));
     }
     int ub; float lub, U; bool amb;
     unvisited_summary<NC, true>(lg, w.vb & ~vm, lane, ub, lub, U, amb);
-    if (lane == 0) p.nHdr[pi] = hdr_pack(U, lub, ub, min(nvis, 32767), (amb || nvis > kFastMaxVisited) ? 1 : 0);
+    if (lane == 0) *reinterpret_cast<int4 *>(blk) = hdr_pack(U, lub, ub, min(nvis, 32767), (amb || nvis > kFastMaxVisited) ? 1 : 0);
+    return (parent << 5) | slot;
 }
 
+// One slot of a node's block: the first 16 bytes (key, logit, N) and the statistics behind them.
+template <bool MZ>
+__device__ __forceinline__ void slot_load(const char *slot, int4 &e, double &W, double &R)
+{
+    e = *reinterpret_cast<const int4 *>(slot);
+    if (MZ) { const double2 t = *reinterpret_cast<const double2 *>(slot + 16); W = t.x; R = t.y; }
+    else { W = *reinterpret_cast<const double *>(slot + 16); R = 0.0; }
+}
+
+// Returns the chosen action, the child it leads to (-1 = not created yet) and -- for an existing child --
+// its slot in this node's block (0 = not mirrored) and its statistics N / W / reward as of now.
 template <int NC, bool MZ, bool F32>
 __device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
-                                                double mn, double rden, int &action, int &child)
+                                                double mn, double rden, int &action, int &child, int &slot, int &cn, double &cW, double &cR)
 {
     const size_t ni = w.nbase + (size_t)node;
-    const int4 h = p.nHdr[ni];
-    // the first 8 list entries (two sectors) are fetched alongside the header: 5 of 6 nodes have <= 8 children
-    const int2 *le = p.nList + ni * kListCap + lane;
-    int2 e = make_int2(0, 0);
-    if (lane < kListSpec) e = *le;
+    const char *blk = blk_of(p, ni);
+    const char *mine = blk + kSlotBytes * lane;
+    const int4 h = *reinterpret_cast<const int4 *>(blk);
+    // slots 1..7 are fetched alongside the summary: one round trip for 5 of 6 nodes
+    int4 e = make_int4(0, 0, 0, 0); double eW = 0.0, eR = 0.0;
+    if (lane >= 1 && lane < kListSpec) slot_load<MZ>(mine, e, eW, eR);
+    const int nvis = h.z >> 16, ub = (int)(short)(h.z & 0xffff);
+    bool loaded_all = false;
     if (h.w == 0) {
-        const int nvis = h.z >> 16, ub = (int)(short)(h.z & 0xffff);
-        if (nvis == 0) { action = ub; child = -1; return; }            // nothing visited: the highest logit wins outright
-        const bool vis = lane < nvis, un = lane == nvis && ub >= 0, cand = vis || un;
+        if (nvis == 0) { action = ub; child = -1; slot = 0; cn = 0; cW = 0.0; cR = 0.0; return; }   // nothing visited: the highest logit wins outright
+        const bool vis = lane >= 1 && lane <= nvis, un = lane == 0 && ub >= 0, cand = vis || un;
+        if (vis && lane >= kListSpec) slot_load<MZ>(mine, e, eW, eR);
+        loaded_all = true;
         int key = (ub << 16) | 0xffff, nn = 0; float slg = __int_as_float(h.y); double W = 0.0, rew = 0.0;
-        if (vis) {
-            if (lane >= kListSpec) e = *le;
-            key = e.x; slg = __int_as_float(e.y);
-            const size_t ci = w.nbase + (size_t)(key & 0xffff);
-            nn = p.nN[ci]; W = p.nW[ci];
-            if (MZ) rew = p.nR[ci];
-        }
+        if (vis) { key = e.x; slg = __int_as_float(e.y); nn = e.z; W = eW; rew = MZ ? eR : 0.0; }
         const int maxN = __reduce_max_sync(GMZ_FULL, nn), sumN = __reduce_add_sync(GMZ_FULL, nn);
         const double scale = (p.c_visit + (double)maxN) * p.c_scale;
         double xs = -INFINITY;
@@ -621,7 +650,7 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         // any common shift near the maximum will do on this path: take it in float32 (one REDUX)
         const double mx = (double)f32_unkey(__reduce_max_sync(GMZ_FULL, f32_key(cand ? (float)xs : -INFINITY)));
         const float ef = cand ? exp_approx((float)(xs - mx)) : 0.0f;
-        const float sum = warp_sum_f32(un ? __fmul_rn(ef, __int_as_float(h.x)) : ef);
+        const float sum = warp_sum_fx(un ? __fmul_rn(ef, __int_as_float(h.x)) : ef);
         const float pf = __fmul_rn(ef, rcp_approx(sum));
         const double s = (double)pf - (double)nn * rcp_newton((double)(1 + sumN));
         const u64 k64 = cand ? f64_key(s) : 0ull;
@@ -641,51 +670,86 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         if (!near) {
             const int wkey = __shfl_sync(GMZ_FULL, key, bl);
             action = a; child = (wkey & 0xffff) == 0xffff ? -1 : (wkey & 0xffff);
+            slot = bl;                                            // lane j scored slot j; lane 0 (the unvisited candidate) -> no slot
+            cn = __shfl_sync(GMZ_FULL, nn, bl); cW = __shfl_sync(GMZ_FULL, W, bl);
+            cR = MZ ? __shfl_sync(GMZ_FULL, rew, bl) : 0.0;
 #ifdef GMZ_VERIFY_FAST
             int ea, ec;
             sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w), node, lane, sm, warp_slot), ea, ec);
-            if (lane == 0) {
-                atomicAdd(&p.ctl->sel_fast, 1ull);
-                if (ea != action || ec != child) atomicAdd(&p.ctl->sel_mismatch, 1ull);
-            }
-            action = ea; child = ec;
-#endif
+            if (lane == 0) atomicAdd(&p.ctl->sel_fast, 1ull);
+            if (ea == action && ec == child) return;
+            if (lane == 0) atomicAdd(&p.ctl->sel_mismatch, 1ull);
+            action = ea; child = ec;                              // the exact decision stands; locate it below
+#else
             return;
+#endif
+        } else {
+            if (lane == 0) atomicAdd(&p.ctl->sel_fallback, 1ull);
+            sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w), node, lane, sm, warp_slot), action, child);
         }
-        if (lane == 0) atomicAdd(&p.ctl->sel_fallback, 1ull);
+    } else sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w), node, lane, sm, warp_slot), action, child);
+    // the exact path decided: find the child among the mirrored slots (or read its own arrays)
+    slot = 0; cn = 0; cW = 0.0; cR = 0.0;
+    if (child >= 0) {
+        const bool vis = lane >= 1 && lane <= min(nvis, kFastMaxVisited);
+        if (vis && !loaded_all && lane >= kListSpec) slot_load<MZ>(mine, e, eW, eR);
+        const unsigned hit = __ballot_sync(GMZ_FULL, vis && (e.x >> 16) == action);
+        if (hit) {
+            slot = __ffs(hit) - 1;
+            cn = __shfl_sync(GMZ_FULL, e.z, slot); cW = __shfl_sync(GMZ_FULL, eW, slot);
+            cR = MZ ? __shfl_sync(GMZ_FULL, eR, slot) : 0.0;
+        } else {
+            const size_t ci = w.nbase + (size_t)child;
+            cn = p.nN[ci]; cW = p.nW[ci]; cR = MZ ? p.nR[ci] : 0.0;
+        }
     }
-    sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w), node, lane, sm, warp_slot), action, child);
 }
 
 // _select_leaf (mcts.py:88-104): root = first least-visited survivor (strict <, list order),
 // then interior selection until an unexpanded child is reached.  In AlphaZero mode the path
 // is replayed on the bitboards while descending (mcts.py:236-248).  Returns depth (edges).
+// pr: lane d <- the node at depth d and its statistics (lane 0 = the root).
 template <int NC, bool MZ, bool F32>
-__device__ __forceinline__ int descend(const Params &p, const WG &w, short *path, int &mypath, SelSmem &sc, int warp_slot, int lane,
+__device__ __forceinline__ int descend(const Params &p, const WG &w, int2 *path, PathReg &pr, SelSmem &sc, int warp_slot, int lane,
                                        int &leaf_parent, int &leaf_action, u64 &P, u64 &M, int &colour)
 {
     const unsigned key = lane < w.n_surv ? (((unsigned)w.s_n << 5) | (unsigned)lane) : 0xffffffffu;
     const int bl = (int)(__reduce_min_sync(GMZ_FULL, key) & 31u);
     int a = __shfl_sync(GMZ_FULL, w.s_act, bl);
     int node = __shfl_sync(GMZ_FULL, w.s_child, bl);
+    int cn = 0, slot = 0;
+    double cW = 0.0, cR = 0.0;
+    // (lanes 0 and 1 -- the root and the chosen root child -- get their statistics from path_root_stats() after
+    //  the descent: only the backup consumes them, and loading them here would stall the first level on them)
+    pr.node = 0; pr.mir = 0; pr.n = 0; pr.W = 0.0; pr.R = 0.0;
     int parent = 0, depth = 1;
-    // the path root..leaf-parent lives in registers: lane d holds the node at depth d (depths >= 32 -- never seen
-    // at 400 simulations -- spill to the global `path`)
-    mypath = 0;
     if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
     // MinMaxStats only change in the backup: 1 / (max - min + delta) is the same at every level of this descent
     const bool rng = w.mm_max > w.mm_min;
     const double rden = rng ? rcp_newton(F32 ? mm_denom<true>(p, w.mm_min, w.mm_max) : (w.mm_max - w.mm_min) + p.delta) : 0.0, mn = rng ? w.mm_min : 0.0;
     while (node >= 0) {
-        if (depth < 32) mypath = lane == depth ? node : mypath;
-        else if (lane == 0) path[depth] = (short)node;
+        const int mir = (parent << 5) | slot;
+        if (depth < 32) { if (lane == depth) { pr.node = node; pr.mir = mir; pr.n = cn; pr.W = cW; pr.R = cR; } }
+        else if (lane == 0) path[depth] = make_int2(node, mir);
         int c;
-        select_interior<NC, MZ, F32>(p, w, node, lane, sc, warp_slot, mn, rden, a, c);
+        select_interior<NC, MZ, F32>(p, w, node, lane, sc, warp_slot, mn, rden, a, c, slot, cn, cW, cR);
         if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
         parent = node; node = c; ++depth;
     }
     leaf_parent = parent; leaf_action = a;
     return depth;
+}
+
+// Statistics of the root (lane 0) and of the root child on the path (lane 1): they have no slot in a parent's
+// block, so they come from the nodes' own arrays.  Issued right after the descent, consumed by the backup.
+template <bool MZ>
+__device__ __forceinline__ void path_root_stats(const Params &p, const WG &w, int depth, PathReg &pr, int lane)
+{
+    if (lane == 0 || (lane == 1 && depth > 1)) {
+        const size_t li = w.nbase + (size_t)pr.node;
+        pr.n = p.nN[li]; pr.W = p.nW[li];
+        if (MZ) pr.R = p.nR[li];
+    }
 }
 
 // The leaf's parent is refreshed (node_link) after the evaluation: start pulling its logits / child rows
@@ -715,36 +779,39 @@ __device__ __forceinline__ void node_write_row(const Params &p, const WG &w, int
 }
 
 // _backpropagate for one leaf, `reps` times in sequence (mcts.py:119-138; MuZero applies the
-// same value len(selected) times, mcts.py:345).  Positions 0..depth-1 are path[], position
-// `depth` is the new node.  Lane l of a 32-wide segment owns position hi - l.  Also maintains
-// the survivor visit counts and the MinMaxStats (min/max are order-independent).
+// same value len(selected) times, mcts.py:345).  Positions 0..depth-1 are the descent path, position
+// `depth` is the new node.  Lane l owns position 32 c + l of chunk c; chunk 0 comes from the descent's
+// registers (no loads), deeper chunks (paths longer than a warp) from Params::path and the nodes' own arrays.
+// Also maintains the mirrored statistics in the parents' blocks and the MinMaxStats (min/max are
+// order-independent).
 template <bool MZ, bool F32>
-__device__ __forceinline__ void backup(const Params &p, WG &w, const short *path, int mypath, int depth, int new_node,
+__device__ __forceinline__ void backup(const Params &p, WG &w, const int2 *path, const PathReg &pr, int depth, int new_node, int new_mir,
                                        double value, double reward, int reps, int lane)
 {
     double v = dclip1(value);
     double qmin = INFINITY, qmax = -INFINITY;
     const bool noclip = p.discount <= 1.0 && p.discount >= -1.0;      // (float32(discount) then is in [-1, 1] too)
 
-    for (int hi = depth; hi >= 0; hi -= 32) {
-        const int pos = hi - lane;
-        const bool act = pos >= 0;
+    for (int c = depth >> 5; c >= 0; --c) {
+        const int base = c << 5, top = min(depth, base + 31);
+        const int pos = base + lane;
+        const bool act = pos <= top;
         const bool is_new = pos == depth;
-        const int pn = __shfl_sync(GMZ_FULL, mypath, pos & 31);
-        const int node = act ? (is_new ? new_node : (pos < 32 ? pn : (int)path[pos])) : 0;
-        const size_t ni = w.nbase + (size_t)node;
-        int n = 0; double W = 0.0, R = 0.0;
-        if (act && !is_new) { n = p.nN[ni]; W = p.nW[ni]; if (MZ) R = p.nR[ni]; }
-        if (act && is_new && MZ) R = reward;
+        int node = pr.node, mir = pr.mir, n = pr.n; double W = pr.W, R = MZ ? pr.R : 0.0;
+        if (c > 0 && act && !is_new) {
+            const int2 t = path[pos]; node = t.x; mir = t.y;
+            const size_t li = w.nbase + (size_t)node;
+            n = p.nN[li]; W = p.nW[li]; if (MZ) R = p.nR[li];
+        }
+        if (is_new) { node = new_node; mir = new_mir; n = 0; W = 0.0; R = MZ ? reward : 0.0; }
         double myv = 0.0;
-        const int cnt = min(32, hi + 1);
         if (!MZ && noclip) {            // no rewards, |discount| <= 1: after the first clip |v| can only shrink
-            for (int l = 0; l < cnt; ++l) {
+            for (int l = top - base; l >= 0; --l) {
                 if (lane == l) myv = v;
                 v = F32 ? (double)__fmul_rn(p.discf, (float)v) : __dadd_rn(0.0, __dmul_rn(p.discount, v));
             }
         } else {
-            for (int l = 0; l < cnt; ++l) {
+            for (int l = top - base; l >= 0; --l) {
                 const double Rl = MZ ? __shfl_sync(GMZ_FULL, R, l) : 0.0;
                 if (lane == l) myv = v;
                 v = dclip1(F32 ? (double)__fadd_rn((float)Rl, __fmul_rn(p.discf, (float)v))
@@ -759,8 +826,15 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const short *path
                     qmin = dmin2(qmin, q); qmax = dmax2(qmax, q);
                 }
             }
+            const size_t ni = w.nbase + (size_t)node;
             p.nN[ni] = n; p.nW[ni] = W;
             if (MZ && is_new) p.nR[ni] = R;
+            if (mir & 31) {              // the copy the parent's selects read
+                char *e = blk_of(p, w.nbase + (size_t)(mir >> 5)) + kSlotBytes * (mir & 31);
+                *reinterpret_cast<int *>(e + 8) = n;
+                *reinterpret_cast<double *>(e + 16) = W;
+                if (MZ && is_new) *reinterpret_cast<double *>(e + 24) = R;
+            }
         }
     }
     if (__any_sync(GMZ_FULL, qmin < w.mm_min || qmax > w.mm_max)) {      // rare once the range has settled
@@ -821,9 +895,9 @@ __device__ __forceinline__ void sequential_halving(const Params &p, WG &w, int l
 
 // After a backup through root child `first_node` (depth-1 node on the path): bump the
 // survivor's visit count (and record the child id if it was just created).
-__device__ __forceinline__ void survivor_visit(WG &w, int depth, int mypath, int new_node, int leaf_action, int reps, int lane)
+__device__ __forceinline__ void survivor_visit(WG &w, int depth, int path_node, int new_node, int leaf_action, int reps, int lane)
 {
-    const int first = __shfl_sync(GMZ_FULL, mypath, 1);        // every lane takes part: no shuffle behind a short-circuit
+    const int first = __shfl_sync(GMZ_FULL, path_node, 1);     // every lane takes part: no shuffle behind a short-circuit
     bool hit;
     if (depth == 1) hit = lane < w.n_surv && w.s_act == leaf_action;
     else hit = lane < w.n_surv && w.s_child == first;

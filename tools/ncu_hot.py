@@ -5,13 +5,19 @@ the hot footprint and the dynamic instructions per simulation.
 import collections, csv, io, os, re, subprocess, sys, tempfile
 
 rep, sims = sys.argv[1], float(sys.argv[2])
-kern = sys.argv[3] if len(sys.argv) > 3 else "_Z9k_play_e0ILi2ELb0EEv6Params8PlayArgs"
-so = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "datou_gomoku_muzero_b200", "libgmz.so")
+kern = sys.argv[3] if len(sys.argv) > 3 else "_Z9k_play_e0ILi2ELb0ELb0EEv6Params8PlayArgs"
+# the four play-kernel cubins inside libgmz.so share one file name, so read the object of the instantiation instead
+so = sys.argv[4] if len(sys.argv) > 4 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "datou_gomoku_muzero_b200",
+                                                       "build", "release", "gmz_play_mz0_f0.o")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-cub = [f for f in os.listdir(tmp) if f.startswith("gmz_engine.") and f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.split("\n")
-start = next(i for i, l in enumerate(dis) if l.startswith(".text." + kern + ":"))
+dis, start = [], None
+for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):      # the cubin that holds the kernel
+    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.split("\n")
+    start = next((i for i, l in enumerate(dis) if l.startswith(".text." + kern + ":")), None)
+    if start is not None:
+        break
+assert start is not None, f"{kern} not found in {so}"
 end = next((i for i in range(start + 1, len(dis)) if dis[i].startswith("//--------------------- .text.")), len(dis))
 cur, insts = ("?", 0), {}
 for l in dis[start:end]:
@@ -29,7 +35,7 @@ base = int(data[0][0], 16)
 src_lines = {}
 def text_of(f, l):
     if f not in src_lines:
-        path = os.path.join(os.path.dirname(so), "csrc", f)
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "datou_gomoku_muzero_b200", "csrc", f)
         src_lines[f] = open(path).read().split("\n") if os.path.exists(path) else []
     return src_lines[f][l - 1].strip()[:90] if 0 < l <= len(src_lines[f]) else ""
 # component = enclosing function of the source line (nearest preceding line that looks like a function header)
