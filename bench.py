@@ -6,8 +6,10 @@ self-play, 400 simulations per move, 4096 concurrent games per GPU (BASELINE.jso
 
 A "step" is one self-play move for every game on the GPU: Gumbel noise, one full 400-simulation
 search per game, decision, do_move + win/draw detection, restart of finished games.  Rank 0
-prints ONE JSON line.  `--impl reference` times the CPU oracle port (oracle/, the reference is
-pure Python and cannot travel to the GPU box) on all host threads on the same config.
+prints ONE JSON line.  `--impl reference` times the UNMODIFIED reference (baseline/_ref, installed by
+baseline/install_reference.py; its own AlphaZeroMCTS.search in one process per host core, plus its production
+topology universal_worker x W + inference_server_worker at N = 1) on the same config; the C port of the search
+(oracle/) is timed beside it as a second figure, and stands in alone if baseline/_ref is absent.
 """
 from __future__ import annotations
 
@@ -55,6 +57,25 @@ def staggered_positions(G, rank, rs=None):
 
 WORKLOAD = ("AlphaZero-mode 15x15 Gomoku self-play, 400 sims/move, 4096 concurrent games per GPU "
             "(BASELINE configs[1]), E0 fixed deterministic evaluator")
+
+
+def bench_config(games):
+    """The workload object both arms (`--impl ours` / `--impl reference`) print, byte for byte; what differs
+    between the arms (how a step is carried out) is reported under `notes`."""
+    return {"workload": WORKLOAD, "games_per_gpu": games, "board": N, "n_in_row": N_IN_ROW, "num_simulations": S,
+            "num_top_actions": K_TOP, "evaluator": "E0 seed %d, quantised logits k/%d" % (E0_SEED, LOGIT_DIV),
+            "roots": "staggered synthetic mid-game positions (0..159 stones)",
+            "l2": "GPU arm: node pools (4 GB per GPU) exceed the 126 MB L2, no explicit flush; CPU arm: n/a"}
+
+
+def kernel_source_sha():
+    """Hash of the CUDA sources: stamps `roofline.traffic` (an ncu measurement) with the kernel it was taken on."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "datou_gomoku_muzero_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler(threading.Thread):
@@ -121,49 +142,93 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
-def run_reference(args):
-    """CPU arm: the oracle port (C restatement of the reference search, pinned to the reference's
-    golden vectors) on every host thread; each step = one search for `games` games of the same workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def port_leg(budget_s, threads=None):
+    """The C port of the reference search (oracle/gmz_oracle.c, OpenMP over games) on the host threads: a bounded
+    sample of the workload, `budget_s` seconds of searches."""
     from oracle import oracle
-    threads = host_threads()
-    games = args.cpu_games or threads * 8
+    threads = threads or host_threads()
+    games = threads * 8
     cfg = oracle.make_config(board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP,
                              eval_seed=E0_SEED, logit_div=LOGIT_DIV)
     boards, players, last, mc = staggered_positions(games, 0)
     rs = np.random.RandomState(7)
-    for _ in range(args.warmup):
+    oracle.search_batch(cfg, boards, players, last, mc, rs.gumbel(0, 1, (games, A)), n_threads=threads, want_visits=False)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
         oracle.search_batch(cfg, boards, players, last, mc, rs.gumbel(0, 1, (games, A)), n_threads=threads, want_visits=False)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle.search_batch(cfg, boards, players, last, mc, rs.gumbel(0, 1, (games, A)), n_threads=threads, want_visits=False)
+        n += 1
     dt = time.perf_counter() - t0
-    sims = games * S * args.steps / dt
-    sample = f"{args.steps} steps x {games} searches of 15x15/400 sims (E0 evaluator) on {threads} threads"
-    print(json.dumps({
-        "impl": "reference", "metric": "mcts_sims_per_sec", "value": sims, "unit": "sims/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+    return {"value": games * S * n / dt, "unit": "sims/s", "cores": threads, "kind": "port",
+            "sample": f"{n} batches x {games} searches of 15x15/400 sims (E0) on {threads} threads, {dt:.1f} s"}
+
+
+def reference_leg(steps, warmup, threads=None, with_config1=True):
+    """The unmodified reference (baseline/_ref): one process per host thread, each running AlphaZeroMCTS.search
+    with E0 behind the reference's own queue protocol.  None if baseline/_ref is absent."""
+    from baseline import ref_runner
+    if not ref_runner.available():
+        return None
+    threads = threads or host_threads()
+    r = ref_runner.tree_only(threads, steps, warmup=warmup, N=N, S=S, K=K_TOP, e0_seed=E0_SEED, logit_div=LOGIT_DIV)
+    out = {"value": r["sims_per_sec"], "unit": "sims/s", "cores": threads, "kind": "reference", "cpu_model": cpu_model(),
+           "moves_per_sec": r["moves_per_sec"], "ms_per_step": r["ms_per_step"],
+           "per_process_sims_per_sec": r["per_process_sims_per_sec"],
+           "sample": "%d steps x %d processes x 1 search of 15x15/400 sims: unmodified reference AlphaZeroMCTS.search "
+                     "(baseline/_ref/mcts.py), E0 in-process, %.1f s" % (steps, threads, r["seconds"])}
+    if with_config1:
+        c1 = ref_runner.tree_only(1, 30, warmup=2, N=9, S=100, K=K_TOP, e0_seed=E0_SEED, logit_div=LOGIT_DIV)
+        out["config1"] = {"workload": "BASELINE configs[0]: 9x9, 100 sims, ONE reference worker process (E0 in-process)",
+                          "sims_per_sec": c1["sims_per_sec"], "moves_per_sec": c1["moves_per_sec"]}
+    return out
+
+
+def run_reference(args):
+    """CPU arm (rank 0 only).  `value` = the unmodified reference on every host thread when baseline/_ref is
+    present (kind "reference"), else the C port (kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    ref = None
+    try:
+        ref = reference_leg(args.steps, max(1, min(args.warmup, 2)), threads)
+    except Exception as ex:
+        ref = None
+        print("reference arm: baseline/_ref failed (%r); falling back to the C port" % (ex,), file=sys.stderr)
+    port = port_leg(5.0 if ref is not None else max(5.0, args.cpu_seconds), threads)
+    port["cpu_model"] = cpu_model()
+    main = ref if ref is not None else port
+    line = {
+        "impl": "reference", "metric": "mcts_sims_per_sec", "value": main["value"], "unit": "sims/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main.get("ms_per_step"), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "moves_per_sec": games * args.steps / dt,
-        "config": {"workload": WORKLOAD, "games_per_gpu": args.games, "board": N, "num_simulations": S, "num_top_actions": K_TOP,
-                   "roots": "staggered synthetic mid-game positions (0..159 stones)",
-                   "step": "bounded sample of the workload: one 400-simulation search for each of %d games per step, "
-                           "CPU port of the reference search (oracle/gmz_oracle.c, OpenMP over games)" % games},
-        "cpu_baseline": {"value": sims, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample,
-                         "cpu_model": cpu_model()},
-        "e2e": {"value": sims, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "moves_per_sec": main["value"] / S,
+        "config": bench_config(args.games),
+        "notes": "each step is a bounded sample of the workload: one 400-simulation search per host process "
+                 "(the reference is one Python process per core); float64 tree arithmetic (E0 hands Python floats)",
+        "cpu_baseline": dict(main, port=port) if ref is not None else port,
+        "e2e": {"value": main["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}
+    if ref is not None and args.gpus == 1 and args.ref_topology_seconds > 0:
+        try:        # the reference's production topology, with its own network on the GPU (reported, not the headline)
+            from baseline import ref_runner
+            line["reference_topology"] = ref_runner.topology(seconds=args.ref_topology_seconds, n_workers=max(1, threads - 2),
+                                                             N=N, S=S, K=K_TOP)
+        except Exception as ex:
+            line["reference_topology"] = {"error": repr(ex)[:300]}
+    print(json.dumps(line))
 
 
 def host_threads():
     """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm ignores that:
     only rank 0 runs it, so it gets the whole box)."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = max(1, len(os.sched_getaffinity(0)))
     except Exception:
-        return max(1, os.cpu_count() or 1)
+        n = max(1, os.cpu_count() or 1)
+    cap = int(os.environ.get("GMZ_BENCH_MAX_PROCS", "0") or 0)          # tests only
+    return min(n, cap) if cap > 0 else n
 
 
 def cpu_model():
@@ -176,9 +241,9 @@ def cpu_model():
     return "unknown"
 
 
-def config1_leg():
+def config1_port_leg():
     """BASELINE configs[0]: 9x9, N_IN_ROW=5, 100 simulations, ONE self-play worker (single host thread of
-    the CPU port) -- the reference's own CPU-runnable case, timed for context."""
+    the CPU port), timed for context beside the reference's own figure."""
     from oracle import oracle
     n, s = 9, 100
     cfg = oracle.make_config(board_size=n, n_in_row=5, num_simulations=s, num_top_actions=K_TOP, eval_seed=E0_SEED)
@@ -196,22 +261,18 @@ def config1_leg():
 
 
 def cpu_baseline_leg(budget_s=10.0):
-    from oracle import oracle
+    """Reported on rank 0 at N = 1: the unmodified reference on the host cores (bounded sample), the C port as a
+    second figure."""
     threads = host_threads()
-    games = threads * 8
-    cfg = oracle.make_config(board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP,
-                             eval_seed=E0_SEED, logit_div=LOGIT_DIV)
-    boards, players, last, mc = staggered_positions(games, 0)
-    rs = np.random.RandomState(7)
-    oracle.search_batch(cfg, boards, players, last, mc, rs.gumbel(0, 1, (games, A)), n_threads=threads, want_visits=False)
-    n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s:
-        oracle.search_batch(cfg, boards, players, last, mc, rs.gumbel(0, 1, (games, A)), n_threads=threads, want_visits=False)
-        n += 1
-    dt = time.perf_counter() - t0
-    return {"value": games * S * n / dt, "unit": "sims/s", "cores": threads, "kind": "port", "cpu_model": cpu_model(),
-            "sample": f"{n} batches x {games} searches of 15x15/400 sims (E0) on {threads} threads, {dt:.1f} s",
-            "config1": config1_leg()}
+    ref = None
+    try:
+        ref = reference_leg(max(2, int(budget_s // 1.5)), 1, threads)
+    except Exception as ex:
+        print("cpu_baseline: baseline/_ref failed (%r)" % (ex,), file=sys.stderr)
+    port = port_leg(5.0 if ref is not None else budget_s, threads)
+    port["cpu_model"] = cpu_model()
+    port["config1"] = config1_port_leg()
+    return dict(ref, port=port) if ref is not None else port
 
 
 def own_bytes_per_sim(d, n_vis=3.2):
@@ -222,16 +283,19 @@ def own_bytes_per_sim(d, n_vis=3.2):
     return (d - 1) * (16 + 20 * n_vis) + (4 * A + 2 * A + 16) + (4 * A + 2 * A + 16 + 16 + 8 + 2) + 24 * (d + 1)
 
 
-def net_leg(eng, dev, peaks):
+def net_leg(eng, dev, peaks, dtype_name="bf16"):
     """Same workload with the REAL network as evaluator (E1): GomokuNetEZ 8 blocks x 128 filters,
-    random init (torch.manual_seed(0)), bf16, BatchNorm folded, cuDNN fused conv ops, CUDA graph;
-    one full 400-simulation search for all G games through the stepwise kernels."""
+    random init (torch.manual_seed(0)), BatchNorm folded, cuDNN fused conv ops, CUDA graph;
+    one full 400-simulation search for all G games through the stepwise kernels.  dtype_name "bf16", or
+    "tf32" = fp32 tensors with TF32 convolutions -- the precision the reference's own server runs at on this
+    GPU (workers.py:318, 350-352: fp32 model, PyTorch's default cudnn.allow_tf32)."""
     import torch
     from datou_gomoku_muzero_b200.config import Config
     from datou_gomoku_muzero_b200.network import DeviceEvaluator, GomokuNetEZ
     torch.manual_seed(0)
     cfg = Config(BOARD_SIZE=N, ACTION_SPACE_SIZE=A, NUM_RES_BLOCKS=8, NUM_FILTERS=128, HEAD_HIDDEN_DIM=64)
-    ev = DeviceEvaluator(GomokuNetEZ(cfg), eng.leaf_obs, dtype=torch.bfloat16, graph=True)
+    torch.backends.cudnn.allow_tf32 = True
+    ev = DeviceEvaluator(GomokuNetEZ(cfg), eng.leaf_obs, dtype=torch.bfloat16 if dtype_name == "bf16" else torch.float32, graph=True)
     G = eng.G
     gum = torch.empty((G, A), dtype=torch.float64, device=dev)
     eng.fill_gumbel(gum, 4242, 0)
@@ -255,11 +319,13 @@ def net_leg(eng, dev, peaks):
     net_ms = n0.elapsed_time(n1) / 10
     tf = 1.064e9 * G / (net_ms * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
-    return {"evaluator": "GomokuNetEZ 8x128 bf16 (random init, BN folded, cuDNN fused conv+bias+relu, CUDA graph)",
+    return {"evaluator": "GomokuNetEZ 8x128 %s (random init, BN folded, cuDNN fused conv+bias+relu, CUDA graph)" % dtype_name,
+            "accum_dtype": eng.accum_dtype,
             "sims_per_sec": G * S / (ms * 1e-3), "moves_per_sec": G / (ms * 1e-3), "ms_per_search": ms,
             "net_forward_ms": net_ms, "tree_and_glue_ms_per_sim_step": ms / S - net_ms,
             "tensor": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                       "flop_per_eval": 1.064e9, "note": "algorithmic conv FLOPs (SURVEY 8d) / measured cuBLAS bf16 burst peak"}}
+                       "flop_per_eval": 1.064e9, "note": "algorithmic conv FLOPs (SURVEY 8d) / measured cuBLAS bf16 burst peak "
+                                                         "(also for the tf32 leg: there is no measured tf32 peak)"}}
 
 
 def muzero_leg(dev, peaks, G):
@@ -324,6 +390,84 @@ def muzero_leg(dev, peaks, G):
                               "unit": "GB/s", "frac": gather_bytes / gather_ms / 1e6 / peak, "bytes": gather_bytes},
             "hidden_scatter": {"bound": "hbm", "ms": scatter_ms, "achieved": scatter_bytes / scatter_ms / 1e6, "peak": peak,
                                "unit": "GB/s", "frac": scatter_bytes / scatter_ms / 1e6 / peak, "bytes": scatter_bytes}}
+
+
+def per_leg(dev, peaks, rounds=400):
+    """BASELINE configs[4], first half: PER `sample(360)` + `update_priorities(360)` on a full capacity-1M sum tree
+    resident on the device (replay_buffer.py:57-103), CUDA-event timed; the reference's own InMemoryReplayBuffer on
+    one host core beside it.  Algorithmic bytes: 168 B per sample, 320 B per update."""
+    import ctypes as C
+    import torch
+    from datou_gomoku_muzero_b200 import replay_buffer as rb
+    cap, B = 1_000_000, 360
+    rs = np.random.RandomState(0)
+    tree = rb.SumTree(cap, device=dev)
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(); tree.add_many(np.abs(rs.randn(cap)) + 1e-6); f1.record(); torch.cuda.synchronize()
+    u = torch.from_numpy(rs.random_sample((rounds, B))).to(dev)
+    newp = torch.from_numpy(np.abs(rs.randn(rounds, B)) + 1e-6).to(dev)
+    idx = torch.empty(B, dtype=torch.int64, device=dev); pr = torch.empty(B, dtype=torch.float64, device=dev)
+    w = torch.empty(B, dtype=torch.float32, device=dev)
+    lib, st, P = tree.lib, tree._stream(), (lambda t: C.c_void_p(t.data_ptr()))
+
+    def step(i):
+        lib.gmz_per_sample(P(tree.tree), cap, cap, P(u[i]), B, 0.4, P(idx), P(pr), P(w), st)
+        lib.gmz_per_update(P(tree.tree), cap, P(idx), P(newp[i]), B, st)
+    for i in range(10):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(10, rounds):
+        step(i)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (rounds - 10)
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    nbytes = B * (168 + 320)
+    out = {"workload": "PER sample(360) + update_priorities(360), capacity 1M, full tree (BASELINE configs[4])",
+           "us_per_batch": ms * 1e3, "samples_per_sec": B / (ms * 1e-3), "fill_1M_adds_ms": f0.elapsed_time(f1),
+           "roofline": {"bound": "hbm", "kernel": "k_per_sample + k_per_update", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak,
+                        "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_batch": nbytes,
+                        "note": "360 dependent 20-level descents per launch: latency bound by construction, not bandwidth bound"}}
+    try:
+        from baseline import ref_runner
+        if ref_runner.available():
+            r = ref_runner.per(cap, B, rounds=60)
+            out["cpu_reference"] = {"kind": "reference", "cores": 1, "us_per_batch": r["us_per_batch"], "samples_per_sec": r["samples_per_sec"],
+                                    "sample": "60 x (sample(360) + update_priorities) of the reference InMemoryReplayBuffer, capacity 1M"}
+    except Exception as ex:
+        out["cpu_reference"] = {"error": repr(ex)[:200]}
+    return out
+
+
+def reanalysis_leg(dev, positions=1_000_000, depth=4):
+    """BASELINE configs[4], second half: Surge re-analysis (workers.py:243-305) of `positions` stored positions with
+    the latest evaluator, through the public re-analysis driver: host boards -> pinned staging -> H2D -> search ->
+    D2H policies / values, `depth` batches of G in flight."""
+    import torch
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.reanalysis import reanalyse_positions
+    G = 4096
+    engs = [SearchEngine(G, board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP, device=dev) for _ in range(depth)]
+    base = staggered_positions(16 * G, 3)          # 65 536 distinct stored positions, cycled to `positions`
+    reps = (positions + 16 * G - 1) // (16 * G)
+    boards = np.tile(base[0], (reps, 1))[:positions]; players = np.tile(base[1], reps)[:positions]
+    last = np.tile(base[2], reps)[:positions]; mc = np.tile(base[3], reps)[:positions]
+    reanalyse_positions(engs, boards[:depth * G], players[:depth * G], last[:depth * G], mc[:depth * G], eval_seed=E0_SEED + 1,
+                        logit_div=LOGIT_DIV, noise_seed=77)          # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pol, val = reanalyse_positions(engs, boards, players, last, mc, eval_seed=E0_SEED + 1, logit_div=LOGIT_DIV, noise_seed=78,
+                                   want_policies="checksum")
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    del engs
+    return {"workload": "Surge re-analysis of %d stored positions, 15x15 / 400 sims, E0 (BASELINE configs[4])" % positions,
+            "positions": positions, "seconds": dt, "positions_per_sec": positions / dt, "sims_per_sec": positions * S / dt,
+            "h2d_bytes": int(boards.nbytes + players.nbytes + last.nbytes + mc.nbytes), "d2h_bytes": int(positions * (A * 8 + 8)),
+            "pipeline_depth": depth, "api": "reanalysis.reanalyse_positions(engines, host boards/players/last_moves/move_counts)",
+            "value_mean": float(np.mean(val)), "policy_checksum": float(pol)}
 
 
 def weight_broadcast_leg(dev, rank, world):
@@ -432,7 +576,11 @@ def run_ours(args):
     moves_done, finished = m1 - m0, f1 - f0
     kernel_ms = elapsed_ms / args.steps               # the play kernel IS the timed region
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [elapsed_ms / args.steps]
     if world > 1:
+        allms = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allms, t)
+        per_rank_ms = [float(x.item()) / args.steps for x in allms]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     md = torch.tensor([moves_done], dtype=torch.float64, device=dev)
@@ -486,9 +634,13 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     bytes_per_launch = algorithmic_bytes_per_sim(mean_depth) * (moves_done / args.steps) * (S - 1)   # per step
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_play_e0_bytes_per_step")
+    traffic, traffic_note = None, "no ncu measurement on record"
+    try:        # ncu dram__bytes_read.sum + dram__bytes_write.sum per bench step, valid only for the kernel it was taken on
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("kernel_source_sha") == kernel_source_sha():
+            traffic, traffic_note = tj.get("k_play_e0_bytes_per_step"), "ncu, " + str(tj.get("source", ""))
+        else:
+            traffic_note = "stale: measured on kernel sources %s, current %s" % (tj.get("kernel_source_sha"), kernel_source_sha())
     except Exception:
         pass
     out = {
@@ -496,12 +648,11 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "moves_per_sec": moves_total / (elapsed_ms * 1e-3),
-        "config": {"workload": WORKLOAD,
-                   "games_per_gpu": G, "board": N, "num_simulations": S, "num_top_actions": K_TOP,
-                   "roots": "staggered synthetic mid-game positions (0..159 stones), finished games restarted in-kernel",
-                   "step": "G self-play moves; the K timed steps run as one persistent ticketed launch of K*G moves (K <= 48; longer runs: one launch per 48 steps)",
-                   "l2": "node pools (2.6 GB per GPU) exceed the 126 MB L2; no explicit flush",
-                   "mean_leaf_depth": mean_depth},
+        "config": bench_config(G),
+        "notes": "a step = G self-play moves (noise, 400-sim search, decision, trajectory record, do_move, win/draw check, in-kernel "
+                 "restart of finished games); the K timed steps run as one persistent ticketed launch of K*G moves (one launch "
+                 "per 48 steps on longer runs); float64 tree arithmetic (E0 hands Python floats)",
+        "ms_per_step_per_rank": per_rank_ms,
         "e2e": {"value": sims_per_step * e2e_steps / e2e_s, "unit": "sims/s",
                 "h2d_bytes_per_step": int(hb.nbytes + hp.nbytes + hl.nbytes + hm.nbytes + hgums[0].nbytes),
                 "d2h_bytes_per_step": int(pol.nbytes + val.nbytes + act.nbytes), "steps": e2e_steps,
@@ -510,7 +661,8 @@ def run_ours(args):
         "gpu_launches": launches,
         "games_finished_in_timed_region": int(finished), "games_harvested": harvested,
         "roofline": {"bound": "hbm", "kernel": "k_play_e0<2>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel_ms_per_step": kernel_ms,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "kernel_ms_per_step": kernel_ms,
+                     "mean_leaf_depth": mean_depth,
                      "algorithmic_bytes_per_sim": algorithmic_bytes_per_sim(mean_depth),
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "own_bytes_per_sim": own_bytes_per_sim(mean_depth),
@@ -525,7 +677,11 @@ def run_ours(args):
     if not args.no_net and world == 1:          # single-GPU context measurement
         try:
             torch.cuda.empty_cache()
-            out["net"] = net_leg(eng, dev, peaks)
+            neng = SearchEngine(G, board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP, device=dev,
+                                accum_dtype="float32")       # float32 accumulation: what the reference does with network values
+            out["net"] = net_leg(neng, dev, peaks, "bf16")
+            out["net_tf32"] = net_leg(neng, dev, peaks, "tf32")
+            del neng
         except Exception as ex:      # the headline (fixed evaluator) stands on its own
             out["net"] = {"error": repr(ex)[:200]}
     if not args.no_net and world == 1:
@@ -536,6 +692,17 @@ def run_ours(args):
             out["muzero"] = muzero_leg(dev, peaks, G)
         except Exception as ex:
             out["muzero"] = {"error": repr(ex)[:200]}
+    if not args.no_config5 and world == 1:
+        try:
+            import gc
+            gc.collect(); torch.cuda.empty_cache()
+            out["per"] = per_leg(dev, peaks)
+        except Exception as ex:
+            out["per"] = {"error": repr(ex)[:200]}
+        try:
+            out["reanalysis"] = reanalysis_leg(dev, args.reanalysis_positions)
+        except Exception as ex:
+            out["reanalysis"] = {"error": repr(ex)[:200]}
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         out["cpu_baseline"] = cpu_baseline_leg(args.cpu_seconds)
     print(json.dumps(out))
@@ -555,6 +722,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-net", action="store_true", help="skip the real-network (E1) leg")
     ap.add_argument("--e2e-depth", type=int, default=6, help="host batches in flight in the end-to-end leg")
+    ap.add_argument("--no-config5", action="store_true", help="skip the PER and re-analysis legs (BASELINE configs[4])")
+    ap.add_argument("--reanalysis-positions", type=int, default=1_000_000)
+    ap.add_argument("--ref-topology-seconds", type=float, default=40.0,
+                    help="--impl reference at N = 1: seconds of the reference's universal_worker + inference_server topology (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -133,23 +133,29 @@ class _GumbelEngineMCTS(MCTS):
         b = self._batch
         return b["o_policy"].numpy(), b["o_value"].numpy(), b["o_action"].numpy()
 
-    def enqueue_batch(self, boards, players, last_moves, move_counts, gumbel=None):
+    def enqueue_batch(self, boards, players, last_moves, move_counts, gumbel=None, device_noise=None):
         """Asynchronous half of search_batch: stages the inputs in pinned memory and enqueues H2D copies,
         the search, the decision and the D2H copies on the current stream.  The pinned output arrays
-        (`_batch["o_*"]`) are valid once that stream has been synchronised."""
+        (`_batch["o_*"]`) are valid once that stream has been synchronised.  device_noise = (seed, counter):
+        draw the Gumbel noise on the device (gmz_fill_gumbel) instead of shipping a host array."""
         b = self._batch
         if b is None:
             raise RuntimeError("search_batch needs an instance made with for_engine()")
         eng = b["engine"]
         G, A = eng.G, eng.A
-        if gumbel is None:
+        if gumbel is None and device_noise is None:
             gumbel = np.random.gumbel(0, 1, (G, A))
         b["h_boards"].numpy()[...] = np.asarray(boards, dtype=np.int8).reshape(G, A)
         b["h_players"].numpy()[...] = np.asarray(players, dtype=np.int8)
         b["h_last"].numpy()[...] = np.asarray(last_moves, dtype=np.int32)
         b["h_mc"].numpy()[...] = np.asarray(move_counts, dtype=np.int32)
-        b["h_gumbel"].numpy()[...] = np.asarray(gumbel, dtype=np.float64).reshape(G, A)
-        for k in ("boards", "players", "last", "mc", "gumbel"):
+        keys = ("boards", "players", "last", "mc")
+        if device_noise is None:
+            b["h_gumbel"].numpy()[...] = np.asarray(gumbel, dtype=np.float64).reshape(G, A)
+            keys += ("gumbel",)
+        else:
+            eng.fill_gumbel(b["d_gumbel"], int(device_noise[0]), int(device_noise[1]))
+        for k in keys:
             b["d_" + k].copy_(b["h_" + k], non_blocking=True)
         eng.set_roots(b["d_boards"], b["d_players"], b["d_last"], b["d_mc"])
         if b["evaluator"] == "e0":
@@ -185,13 +191,13 @@ class PipelinedBatchSearch:
         self.events = [None] * len(engines)
         self.n = 0
 
-    def submit(self, boards, players, last_moves, move_counts, gumbel=None):
+    def submit(self, boards, players, last_moves, move_counts, gumbel=None, device_noise=None):
         import torch
         i = self.n % len(self.lanes)
         if self.events[i] is not None:
             self.events[i].synchronize()           # the lane's pinned buffers are about to be overwritten
         with torch.cuda.stream(self.streams[i]):
-            self.lanes[i].enqueue_batch(boards, players, last_moves, move_counts, gumbel)
+            self.lanes[i].enqueue_batch(boards, players, last_moves, move_counts, gumbel, device_noise)
             ev = torch.cuda.Event()
             ev.record(self.streams[i])
         self.events[i] = ev

@@ -57,3 +57,54 @@ def reanalyse(game_records, batch_search, board_size=None, gumbel_fn=None):
         out.append((pol[off:off + T].copy(), targets))
         off += T
     return out
+
+
+def reanalyse_positions(engines, boards, players, last_moves, move_counts, evaluator="e0", eval_seed=0, logit_div=16,
+                        noise_seed=0, gumbel=None, want_policies=True, cls=None):
+    """Re-search `n` stored positions (host arrays: boards int8 [n, A], players [n], last_moves [n], move_counts [n])
+    with the latest evaluator -- the inner loop of the reference's re-analysis mode (workers.py:254-266) for any number of
+    positions.  They stream through `len(engines)` engines in flight (PipelinedBatchSearch: pinned staging, H2D, search,
+    D2H), G positions per batch; the last batch is padded with inactive (full-board) roots.  Noise: `gumbel` float64
+    [n, A] from the host, or drawn on the device from `noise_seed` (position i uses counters i*A .. i*A + A - 1).
+    Returns (policies float64 [n, A], values float64 [n]); want_policies=False returns (None, values),
+    "checksum" returns (sum of all policy entries, values) without materialising the [n, A] array."""
+    from .mcts import PipelinedBatchSearch
+    eng0 = engines[0]
+    G, A = eng0.G, eng0.A
+    boards = np.asarray(boards, dtype=np.int8).reshape(-1, A)
+    n = boards.shape[0]
+    pipe = PipelinedBatchSearch(list(engines), cls=cls, evaluator=evaluator, eval_seed=eval_seed, logit_div=logit_div)
+    keep = want_policies is True
+    pol = np.zeros((n, A), np.float64) if keep else None
+    checksum = 0.0
+    val = np.zeros(n, np.float64)
+    pad_b = np.ones((G, A), np.int8); pad_p = np.ones(G, np.int8); pad_l = np.full(G, -1, np.int32); pad_m = np.zeros(G, np.int32)
+    inflight = []
+
+    def collect():
+        nonlocal checksum
+        ticket, s0, k = inflight.pop(0)
+        p, v, _ = pipe.result(ticket)
+        if keep:
+            pol[s0:s0 + k] = p[:k]
+        elif want_policies == "checksum":
+            checksum += float(p[:k].sum())
+        val[s0:s0 + k] = v[:k]
+    for s0 in range(0, n, G):
+        k = min(G, n - s0)
+        if k == G:
+            b, pl, lm, m = boards[s0:s0 + G], players[s0:s0 + G], last_moves[s0:s0 + G], move_counts[s0:s0 + G]
+        else:
+            b, pl, lm, m = pad_b.copy(), pad_p.copy(), pad_l.copy(), pad_m.copy()
+            b[:k], pl[:k], lm[:k], m[:k] = boards[s0:s0 + k], players[s0:s0 + k], last_moves[s0:s0 + k], move_counts[s0:s0 + k]
+        if gumbel is not None:
+            g = np.zeros((G, A), np.float64); g[:k] = np.asarray(gumbel[s0:s0 + k], np.float64)
+            t = pipe.submit(b, pl, lm, m, g)
+        else:
+            t = pipe.submit(b, pl, lm, m, device_noise=(noise_seed, s0 * A))
+        inflight.append((t, s0, k))
+        if len(inflight) >= len(engines):
+            collect()
+    while inflight:
+        collect()
+    return (pol if keep else (checksum if want_policies == "checksum" else None)), val

@@ -1,5 +1,6 @@
-"""The bench line contract, as far as it can be checked without a GPU: the reference arm (CPU port of the
-reference search on the host cores) runs here and must print ONE JSON line with the agreed keys."""
+"""The bench line contract, as far as it can be checked without a GPU: the reference arm runs here (the
+unmodified reference from baseline/_ref when installed, the C port otherwise) and must print ONE JSON line with
+the agreed keys; both arms print the same `config` object."""
 import json
 import os
 import subprocess
@@ -9,8 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_contract_line():
+    env = dict(os.environ, GMZ_BENCH_MAX_PROCS="2")           # keep the CPU suite short: two reference processes
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--cpu-games", "8"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                        "--ref-topology-seconds", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -20,15 +22,33 @@ def test_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["metric"] == "mcts_sims_per_sec" and d["unit"] == "sims/s"
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    cb = d["cpu_baseline"]
+    sys.path.insert(0, ROOT)
+    from baseline import ref_runner
+    if ref_runner.available():          # the real reference is the headline, the port the second figure
+        assert cb["kind"] == "reference" and cb["port"]["kind"] == "port" and cb["port"]["value"] > cb["value"]
+        assert "config1" in cb
+    else:
+        assert cb["kind"] == "port"
+    assert cb["cores"] >= 1 and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    import bench
+    assert d["config"] == bench.bench_config(4096)            # byte-identical to what the GPU arm prints
 
 
-def test_both_arms_share_the_workload_name():
+def test_both_arms_share_the_config_object():
     sys.path.insert(0, ROOT)
     import bench
     src = open(os.path.join(ROOT, "bench.py")).read()
-    assert src.count('"workload": WORKLOAD') == 2          # our arm and the reference arm
+    assert src.count('"config": bench_config(') == 2          # our arm and the reference arm
     assert "15x15" in bench.WORKLOAD and "400 sims" in bench.WORKLOAD and "4096" in bench.WORKLOAD
     assert bench.own_bytes_per_sim(3.8) < bench.algorithmic_bytes_per_sim(3.8)
+
+
+def test_reference_install_is_unmodified():
+    """baseline/_ref (when present) holds byte-identical copies of the reference modules (SHA-256 manifest)."""
+    sys.path.insert(0, ROOT)
+    from baseline import install_reference, ref_runner
+    if ref_runner.available():
+        assert install_reference.verify()
