@@ -470,6 +470,75 @@ def reanalysis_leg(dev, positions=1_000_000, depth=4):
             "value_mean": float(np.mean(val)), "policy_checksum": float(pol)}
 
 
+def selfplay_e2e_leg(dev, rank, world, G, steps):
+    """Self-play END TO END on the device: play -> finished games packed into move records (observations, policies,
+    boards, rewards, n-step targets) -> appended to the device replay ring + PER tree -> one training batch of 360
+    slices sampled per chunk (workers.py:162-230 + 399-433 with no host object in between).  Wall-clock moves/s
+    including every kernel and the one small D2H read (the finished-game table) per chunk.  At N > 1 it is followed by
+    the trajectory gather: every rank's last packed chunk -> rank 0 with NCCL (replaces data_queue)."""
+    import torch
+    import torch.distributed as dist
+    from datou_gomoku_muzero_b200.config import config
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.parallel import gather_packed_games
+    from datou_gomoku_muzero_b200.replay_buffer import DeviceReplayBuffer
+    from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+    from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
+    eng = SearchEngine(G, board_size=N, n_in_row=N_IN_ROW, num_simulations=S, num_top_actions=K_TOP, device=dev)
+    sp = SelfPlayEngine(eng, "e0", seed=E0_SEED, logit_div=LOGIT_DIV, noise_seed=2000 + rank)
+    eng.set_roots(*staggered_positions(G, rank))
+    traj = TrajectoryStore(eng, extra_slots=G // 2)
+    buf = DeviceReplayBuffer(400_000, N, device=dev)             # 1.9 GB of records
+    state = {"packed": None, "batches": 0, "d2h": 0, "records": 0}
+
+    def sink(pg):
+        buf.add_packed(pg)
+        state["packed"], state["records"] = pg, state["records"] + pg.n_moves
+        state["d2h"] += pg.table.nbytes + 4
+        if len(buf) >= 360:
+            batch, idx, w = buf.sample(360, rot_k=state["batches"] % 4, flip=bool(state["batches"] & 1))
+            buf.update_priorities(idx, batch[4][:, 0] - 0.5)     # stand-in TD errors (device)
+            state["batches"] += 1
+    sp.play(moves_per_game=8, traj=traj, sink=sink)              # warm-up
+    m0, f0 = eng.play_counters()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sp.play(moves_per_game=steps, traj=traj, sink=sink)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    m1, f1 = eng.play_counters()
+    out = {"what": "play (persistent kernel) -> gmz_traj_pack -> DeviceReplayBuffer.add_packed -> sample(360) + update_priorities "
+                   "per chunk, all on the device", "moves": m1 - m0, "seconds": dt, "moves_per_sec": (m1 - m0) / dt,
+           "sims_per_sec": (m1 - m0) * S / dt, "games_finished": f1 - f0, "records_packed": state["records"],
+           "record_bytes": int(buf.stride), "batches_sampled": state["batches"], "d2h_bytes_total": int(state["d2h"]),
+           "h2d_bytes_total": 0, "replay_len": len(buf)}
+    pg = state["packed"]
+    if pg is not None:                                           # the host-facing form of the same bytes
+        t0 = time.perf_counter()
+        items = pg.data_queue_items(0)
+        dt2 = time.perf_counter() - t0
+        out["host_objects"] = {"what": "last chunk: D2H of the records + GameRecord / TrainingSlice views (workers.py:230 tuples)",
+                               "games": len(items), "moves": pg.n_moves, "seconds": dt2, "moves_per_sec": pg.n_moves / dt2,
+                               "d2h_bytes": int(pg.n_moves * buf.stride)}
+    if world > 1:
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gather_packed_games(pg, N, dst=0, device=dev)            # warm-up (NCCL channels)
+        torch.cuda.synchronize(); dist.barrier()
+        e0.record(); got = gather_packed_games(pg, N, dst=0, device=dev); e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            nbytes = got.n_moves * buf.stride if got is not None else 0
+            out["trajectory_gather"] = {"what": "every rank's last packed chunk -> rank 0: all_gather(counts) + gather(records) + "
+                                                "gather(game tables), NCCL", "games": 0 if got is None else len(got),
+                                        "moves": 0 if got is None else got.n_moves, "bytes": int(nbytes), "ms": float(t.item()),
+                                        "gb_per_s": nbytes / (float(t.item()) * 1e-3) / 1e9 if nbytes else 0.0}
+    return out
+
+
 def weight_broadcast_leg(dev, rank, world):
     """BASELINE configs[3]: the trainer rank publishes GomokuNetEZ's weights to every self-play rank
     (`model_update_queue` in the reference, workers.py:587-593) as one NCCL broadcast of a flat buffer."""
@@ -620,6 +689,15 @@ def run_ours(args):
     sampler.join(timeout=2)
 
     bcast = weight_broadcast_leg(dev, rank, world) if world > 1 else None
+    sp_e2e = None
+    if not args.no_selfplay_e2e:
+        del pipe, engs
+        import gc
+        gc.collect(); torch.cuda.empty_cache()
+        try:
+            sp_e2e = selfplay_e2e_leg(dev, rank, world, G, max(args.steps, 24))
+        except Exception as ex:
+            sp_e2e = {"error": repr(ex)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -674,6 +752,8 @@ def run_ours(args):
     }
     if bcast is not None:
         out["weight_broadcast"] = bcast
+    if sp_e2e is not None:
+        out["selfplay_e2e"] = sp_e2e
     if not args.no_net and world == 1:          # single-GPU context measurement
         try:
             torch.cuda.empty_cache()
@@ -722,6 +802,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-net", action="store_true", help="skip the real-network (E1) leg")
     ap.add_argument("--e2e-depth", type=int, default=6, help="host batches in flight in the end-to-end leg")
+    ap.add_argument("--no-selfplay-e2e", action="store_true", help="skip the device-side self-play -> replay -> batch leg")
     ap.add_argument("--no-config5", action="store_true", help="skip the PER and re-analysis legs (BASELINE configs[4])")
     ap.add_argument("--reanalysis-positions", type=int, default=1_000_000)
     ap.add_argument("--ref-topology-seconds", type=float, default=40.0,

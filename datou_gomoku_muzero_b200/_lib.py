@@ -66,6 +66,9 @@ SIGNATURES = {
     "gmz_build_batch": (C.c_int, [C.POINTER(GmzTraj), C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "gmz_build_batch_aug": (C.c_int, [C.POINTER(GmzTraj), C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                       _P, _P, _P, _P, _P, _P]),
+    "gmz_move_record_bytes": (C.c_size_t, [C.c_int]),
+    "gmz_traj_pack": (C.c_int, [C.POINTER(GmzTraj), C.c_int, _P, C.c_int, _P, _P, C.c_int, _P, _P]),
+    "gmz_records_batch": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "gmz_tactics_classify": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "gmz_per_update": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, _P]),
     "gmz_per_add": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, _P, _P]),

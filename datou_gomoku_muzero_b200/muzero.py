@@ -62,6 +62,22 @@ class MuZeroDeviceSearch:
         self.fused = hasattr(recurrent_fn, "forward_fused") and getattr(recurrent_fn, "embed", None) is not None
         self._root_slot = (torch.arange(engine.G, dtype=torch.int32, device=engine.device) * engine.S).contiguous()
 
+    def set_recurrent_fn(self, recurrent_fn):
+        """Swap the dynamics evaluator (e.g. after a model update that built a new FoldedRecurrentInference): the
+        captured CUDA graph holds the old one's weight pointers, so it is dropped and re-captured on the next search.
+        (FoldedRecurrentInference.update_weights refreshes the weights in place instead and needs no re-capture.)"""
+        self.recurrent_fn = recurrent_fn
+        self.fused = hasattr(recurrent_fn, "forward_fused") and getattr(recurrent_fn, "embed", None) is not None
+        self.graph = None
+        if self.pool is not None:                       # same hidden-state shape assumed: keep the pool, refresh the embedding
+            had = self.embed is not None
+            if self.fused and len(self.hshape) == 3:
+                self.embed = recurrent_fn.embed.detach().to(self.pool.dtype).to(self.pool.device).contiguous()
+            else:
+                self.embed = None
+            if had != (self.embed is not None):
+                self.pool = None                        # the gathered batch changes width: start over
+
     # ---- pool layout
     @staticmethod
     def _rows(h):
@@ -259,26 +275,65 @@ class FoldedRecurrentInference:
     NHWC flatten order so the [B, C*N*N] view of the hidden state is free.  Library kernels."""
 
     def __init__(self, net: GomokuNetEZ, dtype=torch.bfloat16):
-        d, p = net.dynamics_net, net.prediction_net
         self.dtype = dtype
-        self.embed = d.action_embed_conv.weight.detach().to(dtype).reshape(-1)           # [16]
+        self.fused = True
+        self._fold_from(net)
+        self.v_sup, self.r_sup = net.v_sup, net.r_sup
+        self.n = net.board_size
+        try:        # the fused cuDNN entry points do not cover every dtype / build: fall back to conv2d + relu
+            dev = self.stem[0].device
+            self._cr(torch.zeros((1, self.stem[0].shape[1], self.n, self.n), dtype=dtype, device=dev)
+                     .contiguous(memory_format=torch.channels_last), self.stem, 1)
+        except RuntimeError:
+            self.fused = False
+
+    def _tensors(self):
+        return [self.stem, *sum(([a, b] for a, b in self.blocks), []), self.r1, self.r2, self.pv, self.policy_fc,
+                self.value_fc1, self.value_fc2]
+
+    def update_weights(self, net: GomokuNetEZ):
+        """Refold from `net` (fp32 weights) INTO the existing tensors, so a CUDA graph captured over this object
+        (MuZeroDeviceSearch) keeps replaying against the same buffers -- the MuZero-mode counterpart of
+        DeviceEvaluator.update_weights (ModelWeightsUpdate, workers.py:331-335)."""
+        old = self._tensors(); old_embed = self.embed
+        self._fold_from(net)
+        new = self._tensors()
+        with torch.no_grad():
+            for (ow, ob), (nw, nb) in zip(old, new):
+                ow.copy_(nw); ob.copy_(nb)
+            old_embed.copy_(self.embed)
+        self.embed = old_embed
+        (self.stem, *rest) = old
+        nb = len(self.blocks)
+        self.blocks = [(rest[2 * i], rest[2 * i + 1]) for i in range(nb)]
+        self.r1, self.r2, self.pv, self.policy_fc, self.value_fc1, self.value_fc2 = rest[2 * nb:]
+
+    def _fold_from(self, net):
+        d, p = net.dynamics_net, net.prediction_net
+        dtype = self.dtype
+        self.embed = d.action_embed_conv.weight.detach().to(dtype).reshape(-1).clone()           # [16]
         self.stem = _fold(d.conv, d.bn, dtype)
         self.blocks = [(_fold(b.conv1, b.bn1, dtype), _fold(b.conv2, b.bn2, dtype)) for b in d.resblocks]
         n, C = net.board_size, d.conv.out_channels
         w1 = d.reward_fc[0].weight.detach()                                                # [hid, C*n*n] in CHW order
-        self.r1 = (w1.reshape(-1, C, n, n).permute(0, 2, 3, 1).reshape(w1.shape[0], -1).to(dtype).contiguous(),
-                   d.reward_fc[0].bias.detach().to(dtype))
-        self.r2 = (d.reward_fc[2].weight.detach().to(dtype), d.reward_fc[2].bias.detach().to(dtype))
+        self.r1 = (w1.reshape(-1, C, n, n).permute(0, 2, 3, 1).reshape(w1.shape[0], -1).to(dtype).contiguous(), None)
+        own = lambda t: t.detach().to(dtype).clone()      # never alias the module's parameters (update_weights writes in place)
+        self.r1 = (self.r1[0], own(d.reward_fc[0].bias))
+        self.r2 = (own(d.reward_fc[2].weight), own(d.reward_fc[2].bias))
         self.pv = _fold_heads(p, dtype)
-        self.policy_fc = (p.policy_fc.weight.detach().to(dtype), p.policy_fc.bias.detach().to(dtype))
-        self.value_fc1 = (p.value_fc1.weight.detach().to(dtype), p.value_fc1.bias.detach().to(dtype))
-        self.value_fc2 = (p.value_fc2.weight.detach().to(dtype), p.value_fc2.bias.detach().to(dtype))
-        self.v_sup, self.r_sup = net.v_sup, net.r_sup
-        self.n = n
+        self.policy_fc = (own(p.policy_fc.weight), own(p.policy_fc.bias))
+        self.value_fc1 = (own(p.value_fc1.weight), own(p.value_fc1.bias))
+        self.value_fc2 = (own(p.value_fc2.weight), own(p.value_fc2.bias))
 
-    @staticmethod
-    def _cr(x, wb, pad):
-        return torch.cudnn_convolution_relu(x, wb[0], wb[1], (1, 1), (pad, pad), (1, 1), 1)
+    def _cr(self, x, wb, pad):
+        if self.fused:
+            return torch.cudnn_convolution_relu(x, wb[0], wb[1], (1, 1), (pad, pad), (1, 1), 1)
+        return F.relu(F.conv2d(x, wb[0], wb[1], padding=pad))
+
+    def _car(self, x, wb, z):
+        if self.fused:
+            return torch.cudnn_convolution_add_relu(x, wb[0], z, 1.0, wb[1], (1, 1), (1, 1), (1, 1), 1)
+        return F.relu(F.conv2d(x, wb[0], wb[1], padding=1) + z)
 
     @torch.no_grad()
     def __call__(self, hidden, actions):
@@ -294,7 +349,7 @@ class FoldedRecurrentInference:
         B = x.shape[0]
         h = self._cr(x, self.stem, 1)
         for c1, c2 in self.blocks:
-            h = torch.cudnn_convolution_add_relu(self._cr(h, c1, 1), c2[0], h, 1.0, c2[1], (1, 1), (1, 1), (1, 1), 1)
+            h = self._car(self._cr(h, c1, 1), c2, h)
         flat = h.permute(0, 2, 3, 1).reshape(B, -1)
         rew = _support_scalar(F.linear(F.relu(F.linear(flat, *self.r1)), *self.r2).float(), *self.r_sup)
         pv = self._cr(h, self.pv, 0)

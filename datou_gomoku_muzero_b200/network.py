@@ -240,11 +240,14 @@ class DeviceEvaluator:
     def update_weights(self, state_dict):
         """Hot-swap the evaluator's weights (the reference's ModelWeightsUpdate message,
         workers.py:331-335, ipc_messages.py:75-77): load the full state_dict and refold IN PLACE,
-        so a captured CUDA graph keeps replaying against the same buffers."""
-        self.net.load_state_dict({k: v.to(self.dtype) if v.is_floating_point() else v for k, v in state_dict.items()})
+        so a captured CUDA graph keeps replaying against the same buffers.  Folding starts from an fp32
+        copy of the new weights -- exactly what __init__ does -- so update_weights(sd) gives the same folded
+        tensors as DeviceEvaluator(net_with_sd) (no double rounding through the inference dtype)."""
+        master = copy.deepcopy(self.net).float()
+        master.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in state_dict.items()})
+        self.net.load_state_dict({k: v.to(self.dtype) if v.is_floating_point() else v for k, v in master.state_dict().items()})
         if self.folded is not None:
-            fresh = FoldedInitialInference(self.net.float(), self.dtype)
-            self.net.to(self.dtype)
+            fresh = FoldedInitialInference(master.to(self.obs.device).eval(), self.dtype)
             old, new = self.folded, fresh
             with torch.no_grad():
                 for a, b in zip([old.stem, *sum(([x, y] for x, y in old.blocks), []), old.pv,

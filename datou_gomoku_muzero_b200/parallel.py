@@ -5,7 +5,7 @@ only for the two exchanges the reference does through multiprocessing queues:
   * trainer -> workers weight publication (`model_update_queue`, workers.py:587-593, 331-335)
     -> `broadcast_weights`: one flattened-buffer broadcast from the trainer rank;
   * workers -> data loader trajectories (`data_queue`, workers.py:230, 399)
-    -> `gather_finished_games`: counts all-gathered, records sent to the collecting rank.
+    -> `gather_packed_games`: counts all-gathered, fixed-stride move records gathered as raw bytes.
 """
 from __future__ import annotations
 
@@ -91,9 +91,51 @@ def sum_over_ranks(value: float, device=None, group=None) -> float:
     return float(t.item())
 
 
+def gather_packed_games(packed, board_size, dst: int = 0, group=None, device=None):
+    """The reference's `data_queue` (workers.py:230, 399) across ranks: every rank's finished games, as packed move
+    records (trajectory.PackedGames, fixed stride ~4.7 KB per move at 15x15), gathered on rank `dst` with tensor
+    collectives -- `all_gather` of the (moves, games) counts, then one `gather` of the record bytes and one of the
+    game tables, each padded to the largest rank.  No pickling, no per-game Python objects; with NCCL the records go
+    GPU -> GPU.  `packed` may be None (this rank has nothing).  Returns a PackedGames on `dst` whose table has a
+    fifth column = source rank; None elsewhere."""
+    from .trajectory import PackedGames
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    stride = (64 + 21 * board_size * board_size + 15) // 16 * 16
+    if device is None:
+        device = packed.records.device if packed is not None and torch.is_tensor(packed.records) else torch.device("cpu")
+    m = 0 if packed is None else packed.n_moves
+    n = 0 if packed is None else len(packed)
+    mine = torch.tensor([m, n], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(counts, mine, group=group)
+    counts = torch.stack(counts).cpu().numpy()
+    M, Nn = int(counts[:, 0].max()), int(counts[:, 1].max())
+    if M == 0:
+        return None
+    rec = torch.zeros((M, stride), dtype=torch.uint8, device=device)
+    tab = torch.zeros((Nn, 4), dtype=torch.int32, device=device)
+    if m:
+        rec[:m].copy_(torch.as_tensor(packed.records).reshape(m, stride))
+        tab[:n].copy_(torch.as_tensor(np.ascontiguousarray(packed.table[:, :4], dtype=np.int32)))
+    recs = [torch.empty_like(rec) for _ in range(world)] if rank == dst else None
+    tabs = [torch.empty_like(tab) for _ in range(world)] if rank == dst else None
+    dist.gather(rec, recs, dst=dst, group=group)
+    dist.gather(tab, tabs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out_rec = torch.cat([recs[r][:counts[r, 0]] for r in range(world)])
+    tables, offs, base = [], [0], 0
+    for r in range(world):
+        t = tabs[r][:counts[r, 1]].cpu().numpy()
+        tables.append(np.concatenate([t, np.full((len(t), 1), r, np.int32)], axis=1))
+        for L in t[:, 2]:
+            base += int(L); offs.append(base)
+    return PackedGames(out_rec, np.concatenate(tables), np.asarray(offs, np.int64), board_size)
+
+
 def gather_finished_games(records, dst: int = 0, group=None):
-    """Harvested games (list of dicts from TrajectoryStore.harvest) of every rank -> `dst`.
-    Fixed-stride packing: one int64 header row + float64 payload per game, counts all-gathered first."""
+    """Harvested games as Python dicts (TrajectoryStore.harvest) of every rank -> `dst`, through
+    `gather_object` (pickle).  Convenience for small jobs and tests; the tensor path is gather_packed_games."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     counts = [None] * world
     dist.all_gather_object(counts, len(records), group=group)

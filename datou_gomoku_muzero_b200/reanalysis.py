@@ -27,7 +27,8 @@ def positions_of(game_record, board_size):
 def reanalyse(game_records, batch_search, board_size=None, gumbel_fn=None):
     """game_records: list of GameRecord.  batch_search: an `AlphaZeroMCTS.for_engine(...)`-style object
     (search_batch over exactly G roots).  Returns, per game, (new_policies [T,A] float64,
-    new_value_targets list[float]) -- what `finish_reanalysis_for_game` is handed (workers.py:292-294).
+    new_value_targets list[float], search_values float64 [T]) -- the first two are what
+    `finish_reanalysis_for_game` is handed (workers.py:292-294).
     gumbel_fn(n, A) supplies the noise rows (default: np.random.gumbel like each reference search)."""
     N = board_size or config.BOARD_SIZE
     A = N * N
@@ -54,7 +55,7 @@ def reanalyse(game_records, batch_search, board_size=None, gumbel_fn=None):
         T = len(gr.actions)
         rewards = np.array(gr.rewards, dtype=np.float32)          # workers.py:291: float32 here, unlike self-play
         targets = compute_n_step_returns(rewards, [np.float64(x) for x in val[off:off + T]], config.DISCOUNT, config.N_STEPS)
-        out.append((pol[off:off + T].copy(), targets))
+        out.append((pol[off:off + T].copy(), targets, val[off:off + T].copy()))
         off += T
     return out
 

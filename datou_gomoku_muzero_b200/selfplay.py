@@ -68,14 +68,35 @@ class SelfPlayEngine:
         self.moves_played += e.G
         return winner
 
-    def play(self, moves_per_game=1, traj=None, restart=True):
-        """Persistent-kernel self-play (fixed evaluator only): G * moves_per_game moves in one launch,
-        games advancing independently; returns nothing -- harvest finished games from `traj`."""
+    def play(self, moves_per_game=1, traj=None, restart=True, sink=None, chunk=None):
+        """Persistent-kernel self-play (fixed evaluator only): G * moves_per_game moves, games advancing
+        independently.  Without `sink` it is ONE launch and the caller harvests finished games from `traj`
+        (games that finish when no trajectory slot is free park until slots are released).  With `sink` -- a
+        callable taking a trajectory.PackedGames, e.g. `DeviceReplayBuffer.add_packed` -- the run is cut into
+        launches of `chunk` moves per game (default: what the store's spare slots absorb, at most 48) and after
+        each one the finished games are packed on the device, handed to the sink and their slots recycled, so a
+        run of any length never parks a game."""
         if self.evaluator != "e0":
             raise NotImplementedError("the persistent self-play kernel runs the fixed evaluator E0")
         e = self.e
-        e.selfplay_e0(e.G * int(moves_per_game), self.seed, self.logit_div, self.noise_seed, traj, restart)
-        self.moves_played += e.G * int(moves_per_game)
+        total = int(moves_per_game)
+        if sink is None or traj is None:
+            e.selfplay_e0(e.G * total, self.seed, self.logit_div, self.noise_seed, traj, restart)
+            self.moves_played += e.G * total
+            return
+        if chunk is None:          # a game ends about every A/3 moves at the earliest in practice; spare slots absorb the finishes
+            spare = max(1, traj.n_slots - e.G)
+            chunk = int(max(4, min(48, spare * (e.A // 3) // max(1, e.G))))
+        done = 0
+        while done < total:
+            n = min(int(chunk), total - done)
+            e.selfplay_e0(e.G * n, self.seed, self.logit_div, self.noise_seed, traj, restart)
+            done += n
+            packed = traj.pack_finished(recycle=True)
+            if packed is not None:
+                sink(packed)
+                self.games_finished += len(packed)
+        self.moves_played += e.G * total
 
     def count_finished(self, winner):
         n = int((winner != 2).sum().item())

@@ -17,12 +17,81 @@ from .config import config
 from .data_structures import GameRecord, TrainingSlice
 
 
+def record_dtype(board_size):
+    """numpy view of one packed move record (include/gmz.h gmz_move_record + payload)."""
+    N = int(board_size)
+    A = N * N
+    stride = (64 + 21 * A + 15) // 16 * 16
+    names = ["game_seq", "t", "length", "winner", "action", "to_move", "last_move", "move_count", "reward", "value_target",
+             "search_value", "game", "slot", "policy", "obs", "board"]
+    formats = ["<i4"] * 8 + ["<f4", "<f4", "<f8", "<i4", "<i4", ("<f8", (A,)), ("<f4", (3, N, N)), ("i1", (N, N))]
+    offsets = [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 48, 52, 64, 64 + 8 * A, 64 + 20 * A]
+    return np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": stride})
+
+
+class PackedGames:
+    """Finished games as packed move records (csrc/gmz_records.cu): `records` uint8 [M, stride] (device or host
+    tensor), `table` int32 [n, 4] = (slot, game, length, winner) per game, `offsets` int64 [n + 1] = first record of
+    each game.  What the reference puts on data_queue per game -- (GameRecord, [TrainingSlice], version),
+    workers.py:230 -- is a set of numpy views of these bytes."""
+
+    def __init__(self, records, table, offsets, board_size):
+        self.records, self.table, self.offsets, self.N = records, np.asarray(table), np.asarray(offsets, np.int64), int(board_size)
+        self._host = None
+
+    def __len__(self):
+        return len(self.table)
+
+    @property
+    def n_moves(self):
+        return int(self.offsets[-1])
+
+    def host(self):
+        """Structured numpy array [M] over the record bytes (one D2H copy, cached)."""
+        if self._host is None:
+            raw = self.records.cpu().numpy() if torch.is_tensor(self.records) else np.asarray(self.records)
+            self._host = np.ascontiguousarray(raw).view(record_dtype(self.N)).reshape(-1)
+        return self._host
+
+    def game(self, i):
+        return self.host()[self.offsets[i]:self.offsets[i + 1]]
+
+    def game_record(self, i):
+        """GameRecord of game i (data_structures.py:9-16): lists of per-move array views / Python scalars."""
+        r = self.game(i)
+        return GameRecord(list(r["obs"]), r["action"].tolist(), r["reward"].tolist(), list(r["policy"]),
+                          r["value_target"].tolist(), list(r["board"]))
+
+    def training_slices(self, i):
+        """[TrainingSlice] of game i (workers.py:208-222): windows of U+1 moves over the zero / -1 padded arrays."""
+        r, U = self.game(i), int(config.NUM_UNROLL_STEPS)
+        T = len(r)
+        if T == 0:
+            return []
+        win = np.lib.stride_tricks.sliding_window_view
+        obs = np.concatenate([r["obs"], np.zeros((U + 1,) + r["obs"].shape[1:], np.float32)])
+        pol = np.concatenate([r["policy"], np.zeros((U + 1, r["policy"].shape[1]), np.float64)])
+        act = np.concatenate([r["action"].astype(np.int32), np.full(U, -1, np.int32)])
+        rew = np.concatenate([r["reward"].astype(np.float32), np.zeros(U, np.float32)])
+        val = np.concatenate([r["value_target"].astype(np.float32), np.zeros(U + 1, np.float32)])
+        ow, pw = win(obs, U + 1, axis=0), win(pol, U + 1, axis=0)             # window axis comes last
+        ow, pw = np.moveaxis(ow, -1, 1), np.moveaxis(pw, -1, 1)
+        aw, rw, vw = (win(act, U) if U else np.zeros((T + 1, 0), np.int32)), (win(rew, U) if U else np.zeros((T + 1, 0), np.float32)), win(val, U + 1)
+        return [TrainingSlice(ow[t], aw[t], rw[t], pw[t], vw[t]) for t in range(T)]
+
+    def data_queue_items(self, model_version=0):
+        """The tuples universal_worker puts on data_queue (workers.py:230), one per game."""
+        return [(self.game_record(i), self.training_slices(i), model_version) for i in range(len(self))]
+
+
 class TrajectoryStore:
     def __init__(self, engine, extra_slots=None, max_moves=None):
         e = self.e = engine
         G, A = e.G, e.A
         self.n_slots = G + (max(64, G // 4) if extra_slots is None else int(extra_slots))
         self.max_moves = A if max_moves is None else int(max_moves)
+        if self.max_moves < 1:
+            raise ValueError("max_moves must be >= 1")
         dev = e.device
         n, T = self.n_slots, self.max_moves
         self.policy = torch.zeros((n, T, A), dtype=torch.float64, device=dev)
@@ -40,16 +109,21 @@ class TrajectoryStore:
         check(e.lib.gmz_traj_init(e.handle, C.byref(self.c), e._stream()), "gmz_traj_init")
         e.launches += 1
 
-    def harvest(self, copy_policies=True, recycle=True):
+    def harvest(self, copy_policies=True, recycle=True, unpark=True):
         """Finished games since the last harvest -> list of dicts (host arrays).  With `recycle` their
-        slots go back on the free stack and parked games restart; a DeviceSliceStore keeps the slots
-        (the games stay resident for sampling) and recycles them itself when it evicts."""
+        slots go back on the free stack and (with `unpark`) parked games restart -- pass unpark=False after
+        play(restart=False) to leave finished games finished; a DeviceSliceStore keeps the slots (the games stay
+        resident for sampling) and recycles them itself when it evicts.  A game that recorded more moves than the
+        store's `max_moves` (only possible with a user-supplied max_moves below the remaining plies) comes back with
+        `length` clamped to what was recorded and `truncated` = True."""
         e = self.e
         n = int(self.fin_count.item())
         if n == 0:
             return []
         q = self.fin_queue[:n].cpu().numpy()
         slots = torch.as_tensor(q[:, 0].astype(np.int64), device=e.device)
+        full_len = q[:, 2].copy()
+        q[:, 2] = np.minimum(q[:, 2], self.max_moves)
         Tmax = int(q[:, 2].max())
         act = self.action[slots, :Tmax].cpu().numpy()
         val = self.value[slots, :Tmax].cpu().numpy()
@@ -64,14 +138,43 @@ class TrajectoryStore:
             out.append(dict(slot=int(q[i, 0]), game=int(q[i, 1]), length=T, winner=int(q[i, 3]), actions=act[i, :T].copy(),
                             values=val[i, :T].copy(), policies=None if pol is None else pol[i, :T].copy(),
                             start_board=board.reshape(e.N, e.N), start_player=int(si[i, 0]),
-                            start_move_count=int(si[i, 1]), start_last_move=int(si[i, 2])))
+                            start_move_count=int(si[i, 1]), start_last_move=int(si[i, 2]),
+                            truncated=bool(full_len[i] > self.max_moves)))
         self.fin_count.zero_()
         if recycle:
-            self.release(slots)
+            self.release(slots, unpark=unpark)
         return out
 
-    def release(self, slots):
-        """Push slots back on the free stack and restart games that were parked waiting for one."""
+    def pack_finished(self, recycle=True):
+        """Finished games since the last harvest / pack -> PackedGames on the DEVICE (None if there are none): one
+        kernel expands every finished slot into fixed-stride move records (observations, policies, boards, final
+        rewards, n-step value targets); nothing is computed per move on the host.  With `recycle` the slots go back
+        on the free stack and parked games restart."""
+        e = self.e
+        n = int(self.fin_count.item())
+        if n == 0:
+            return None
+        q = self.fin_queue[:n].cpu().numpy()
+        lens = np.minimum(q[:, 2], self.max_moves).astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        stride = int(e.lib.gmz_move_record_bytes(e.N))
+        rec = torch.empty((int(off[-1]), stride), dtype=torch.uint8, device=e.device)
+        off_d = torch.as_tensor(off[:-1].copy(), device=e.device)
+        dpow = torch.tensor([config.DISCOUNT ** i for i in range(config.N_STEPS + 1)], dtype=torch.float64, device=e.device)
+        check(e.lib.gmz_traj_pack(C.byref(self.c), e.N, self.fin_queue.data_ptr(), n, off_d.data_ptr(), dpow.data_ptr(),
+                                  int(config.N_STEPS), rec.data_ptr(), e._stream()), "gmz_traj_pack")
+        e.launches += 1
+        self.fin_count.zero_()
+        if recycle:
+            self.release(torch.as_tensor(q[:, 0].astype(np.int32), device=e.device))
+        return PackedGames(rec, q, off, e.N)
+
+    def free_slots_left(self):
+        return int(self.free_top.item())
+
+    def release(self, slots, unpark=True):
+        """Push slots back on the free stack and (unless unpark=False) restart every parked game that can get one --
+        including games parked by play(restart=False)."""
         e = self.e
         slots = torch.as_tensor(slots, device=e.device).to(torch.int32).reshape(-1)
         n = int(slots.numel())
@@ -80,8 +183,9 @@ class TrajectoryStore:
         top = int(self.free_top.item())
         self.free_slots[top:top + n] = slots
         self.free_top.fill_(top + n)
-        check(e.lib.gmz_selfplay_unpark(e.handle, C.byref(self.c), e._stream()), "gmz_selfplay_unpark")
-        e.launches += 1
+        if unpark:
+            check(e.lib.gmz_selfplay_unpark(e.handle, C.byref(self.c), e._stream()), "gmz_selfplay_unpark")
+            e.launches += 1
 
 
 class DeviceSliceStore:

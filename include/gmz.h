@@ -228,6 +228,45 @@ int gmz_build_batch_aug(const gmz_traj *traj, int board_size, const float *targe
                         int unroll, int rot_k, int flip, float *obs, int32_t *act, float *rew, double *pi, float *val,
                         gmz_stream stream);
 
+/* ---- packed move records: the device-side trajectory hand-off (workers.py:172-230, 399-433) ---- */
+/* One fixed-stride record per move of a finished game: everything the reference's self-play loop emits for
+ * that move.  Layout (stride = gmz_move_record_bytes(board_size), a multiple of 16):
+ *   bytes 0..63   gmz_move_record header (below)
+ *   then          policy f64 [A]   the search policy (policies.append, workers.py:174)
+ *   then          obs    f32 [3A]  game.get_board_state before the move (workers.py:173)
+ *   then          board  i8  [A]   np.copy(game.board) before the move (workers.py:177)
+ * The same bytes are (a) viewed as GameRecord / TrainingSlice arrays on the host, (b) gathered across ranks
+ * as raw bytes, (c) appended to the device replay ring gmz_records_batch samples from. */
+typedef struct gmz_move_record {
+    int32_t game_seq;     /* index of the game in the gmz_traj_pack call */
+    int32_t t;            /* move number within the recorded game, 0-based */
+    int32_t length;       /* moves recorded for the game */
+    int32_t winner;       /* get_game_ended(): +-1, 0 = draw */
+    int32_t action;       /* the move played */
+    int32_t to_move;      /* current_player before the move */
+    int32_t last_move;    /* last_move before the move, -1 = None */
+    int32_t move_count;   /* move_count before the move */
+    float reward;         /* final_rewards[t], workers.py:183-187 */
+    float value_target;   /* compute_n_step_returns(...)[t], workers.py:144-152, 205 */
+    double search_value;  /* root value of the search for this move */
+    int32_t game;         /* engine game index that played it */
+    int32_t slot;         /* trajectory slot it was recorded in */
+    int32_t reserved[2];
+} gmz_move_record;
+size_t gmz_move_record_bytes(int board_size);
+/* Expand n_games finished games into records.  fin int32 [n_games][4] = (slot, game, length, winner) rows of the
+ * store's fin_queue; move_offset int64 [n_games] = record index of each game's first move (exclusive prefix sum of
+ * min(length, max_moves)); discount_pow f64 [n_steps+1] = discount**i as the host computes them;
+ * out_records = total_moves * stride bytes.  All pointers are device pointers. */
+int gmz_traj_pack(const gmz_traj *traj, int board_size, const int32_t *fin, int n_games, const int64_t *move_offset,
+                  const double *discount_pow, int n_steps, void *out_records, gmz_stream stream);
+/* A training batch (workers.py:430-433) gathered from a RING of `capacity` records: sample b is the record at
+ * ring position positions[b] (the reference's data index, replay_buffer.py:80) plus the next `unroll` records of
+ * the same game, padded past its end like workers.py:208-222; rot_k / flip = the trainer's D4 augmentation
+ * (loss.py:37-51).  Outputs as gmz_build_batch. */
+int gmz_records_batch(const void *ring, int64_t capacity, int board_size, const int64_t *positions, int batch, int unroll,
+                      int rot_k, int flip, float *obs, int32_t *act, float *rew, double *pi, float *val, gmz_stream stream);
+
 /* ---- tactics classifier (find_winning_moves_rebuilt, workers.py:49-123) ---- */
 /* boards int8 [B,A], players int8 [B] (the side to move) -> out_cls int8 [B,A]: per empty cell
  * 1 = 'five', 2 = 'open_four', 3 = 'combo', 0 = none (occupied cells: 0).  Feeds the missed-win

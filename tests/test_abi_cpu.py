@@ -35,7 +35,7 @@ def test_config_validation_without_gpu():
     lib = _lib.load()
     ok = _lib.GmzConfig(15, 5, 400, 16, 0, 4096, 0, 0, 30.0, 1.0, 1e-3, 0.997)
     nbytes = lib.gmz_workspace_bytes(ctypes.byref(ok))
-    assert 2.8e9 < nbytes < 3.3e9          # 4096 games x 400 nodes x (1 KiB logits + 512 B children + 256 B child list + headers)
+    assert 4.1e9 < nbytes < 4.5e9          # 4096 games x 400 nodes x (1 KiB logits + 512 B children + 1 KiB node block + own stats)
     for bad in (_lib.GmzConfig(20, 5, 400, 16, 0, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997),      # board too large
                 _lib.GmzConfig(15, 5, 0, 16, 0, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997),        # no simulations
                 _lib.GmzConfig(15, 5, 400, 33, 0, 1, 0, 0, 30.0, 1.0, 1e-3, 0.997),      # too many top actions

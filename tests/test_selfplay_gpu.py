@@ -89,12 +89,21 @@ def test_reanalysis_matches_oracle_per_position():
     allnoise = np.concatenate(noise)
     cfg = oracle.make_config(board_size=N, num_simulations=S, eval_seed=new_seed)
     off = 0
-    for gr, (pol, targets) in zip(games, out):
+    for gr, (pol, targets, vals) in zip(games, out):
         b, pl, lm, mc = positions_of(gr, N)
         T = len(gr.actions)
         opol, oval, oact, _ = oracle.search_batch(cfg, b, pl, lm, mc, allnoise[off:off + T])
         np.testing.assert_allclose(pol, opol, rtol=1e-5, atol=1e-12)
+        assert np.array_equal(vals, oval)                       # the re-searched root values, bit for bit
         assert len(targets) == T and all(isinstance(t, float) for t in targets)
+        # the new value targets: workers.py:291-292 restated (float32 rewards there, unlike self-play: float32 sums)
+        rew = np.array(gr.rewards, dtype=np.float32); v32 = np.array(oval, dtype=np.float32)
+        exp = np.zeros(T, np.float32)
+        for t in range(T):
+            acc = sum((config.DISCOUNT ** i) * rew[t + i] for i in range(config.N_STEPS) if t + i < T)
+            boot = v32[t + config.N_STEPS] * (config.DISCOUNT ** config.N_STEPS) if t + config.N_STEPS < T else 0.0
+            exp[t] = acc + boot
+        assert np.array_equal(np.array(targets, np.float32), exp)
         off += T
 
 
