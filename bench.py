@@ -291,38 +291,42 @@ def net_leg(eng, dev, peaks, dtype_name="bf16"):
     GPU (workers.py:318, 350-352: fp32 model, PyTorch's default cudnn.allow_tf32)."""
     import torch
     from datou_gomoku_muzero_b200.config import Config
-    from datou_gomoku_muzero_b200.network import DeviceEvaluator, GomokuNetEZ
+    from datou_gomoku_muzero_b200.network import GomokuNetEZ, NetworkSearch
     torch.manual_seed(0)
     cfg = Config(BOARD_SIZE=N, ACTION_SPACE_SIZE=A, NUM_RES_BLOCKS=8, NUM_FILTERS=128, HEAD_HIDDEN_DIM=64)
     torch.backends.cudnn.allow_tf32 = True
-    ev = DeviceEvaluator(GomokuNetEZ(cfg), eng.leaf_obs, dtype=torch.bfloat16 if dtype_name == "bf16" else torch.float32, graph=True)
+    ns = NetworkSearch(eng, GomokuNetEZ(cfg), dtype=torch.bfloat16 if dtype_name == "bf16" else torch.float32, graph=True)
     G = eng.G
     gum = torch.empty((G, A), dtype=torch.float64, device=dev)
     eng.fill_gumbel(gum, 4242, 0)
     eng.set_roots(*staggered_positions(G, 0))
-
-    def search(n_sims):
-        lg, v = ev(eng.root_obs()); eng.root_expand(lg, v, gum)
-        for _ in range(n_sims - 1):
-            lg, v = ev(eng.select()); eng.expand_backup(lg, v)
-    search(8)                                   # warm-up (partial search)
+    ns.search(gum, num_simulations=8)           # warm-up (partial search): cuDNN plans + graph capture
+    # the tree kernels of one simulation step on their own (select -> expand/backup with the last network outputs)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(20):
+        eng.select(out=ns.obs); eng.expand_backup(ns.ev.logits, ns.ev.values)
+    t1.record(); torch.cuda.synchronize()
+    tree_ms = t0.elapsed_time(t1) / 20
     eng.set_roots(*staggered_positions(G, 0))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); search(S); eng.finalize(want_visits=False); e1.record(); torch.cuda.synchronize()
+    e0.record(); ns.search(gum); eng.finalize(want_visits=False); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0.record()
     for _ in range(10):
-        ev(eng.leaf_obs)
+        ns.ev._forward()
     n1.record(); torch.cuda.synchronize()
     net_ms = n0.elapsed_time(n1) / 10
     tf = 1.064e9 * G / (net_ms * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
-    return {"evaluator": "GomokuNetEZ 8x128 %s (random init, BN folded, cuDNN fused conv+bias+relu, CUDA graph)" % dtype_name,
+    return {"evaluator": "GomokuNetEZ 8x128 %s (random init, BN folded, cuDNN fused conv+bias+relu); one CUDA graph per simulation "
+                         "step {select -> network -> expand/backup}" % dtype_name,
             "accum_dtype": eng.accum_dtype,
             "sims_per_sec": G * S / (ms * 1e-3), "moves_per_sec": G / (ms * 1e-3), "ms_per_search": ms,
-            "net_forward_ms": net_ms, "tree_and_glue_ms_per_sim_step": ms / S - net_ms,
+            "net_forward_ms": net_ms, "tree_kernels_ms_per_sim_step": tree_ms,
+            "step_minus_standalone_forward_ms": ms / S - net_ms,
             "tensor": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
                        "flop_per_eval": 1.064e9, "note": "algorithmic conv FLOPs (SURVEY 8d) / measured cuBLAS bf16 burst peak "
                                                          "(also for the tf32 leg: there is no measured tf32 peak)"}}

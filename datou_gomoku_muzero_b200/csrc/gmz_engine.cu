@@ -108,6 +108,13 @@ k_get_roots(Params p, int8_t *boards, int8_t *players, int32_t *last_moves, int3
     }
 }
 
+// T = float: NCHW float32 planes; T = unsigned short: NHWC bf16 (channels_last), see obs_write_nhwc_bf16
+template <int NC, typename T>
+__device__ __forceinline__ void obs_emit(T *obs, int A, u64 own, u64 opp, int last, int lane)
+{
+    if constexpr (sizeof(T) == 2) obs_write_nhwc_bf16<NC>((unsigned short *)obs, A, own, opp, last, lane);
+    else obs_write<NC, T>(obs, A, own, opp, last, lane);
+}
 template <int NC, typename T>
 __global__ void __launch_bounds__(CTA_THREADS) k_root_obs(Params p, T *obs)
 {
@@ -116,7 +123,7 @@ __global__ void __launch_bounds__(CTA_THREADS) k_root_obs(Params p, T *obs)
     const GState *s = p.gs + g;
     const u64 P = lane < GMZ_WORDS ? s->p1[lane] : 0ull, M = lane < GMZ_WORDS ? s->m1[lane] : 0ull;
     const int tm = s->to_move;
-    obs_write<NC, T>(obs + (size_t)g * 3 * p.A, p.A, tm > 0 ? P : M, tm > 0 ? M : P, s->last_move, lane);
+    obs_emit<NC, T>(obs + (size_t)g * 3 * p.A, p.A, tm > 0 ? P : M, tm > 0 ? M : P, s->last_move, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -191,7 +198,7 @@ k_select(const __grid_constant__ Params p, T *leaf_obs, int32_t *out_a, int32_t 
                                       lp, la, P, M, colour);
     if (lane < min(depth, 32)) path[lane] = make_int2(pr.node, pr.mir);      // hand the path to k_expand_backup
     if (!MZ && leaf_obs)   // colour is now the player to move at the leaf; last move = la
-        obs_write<NC, T>(leaf_obs + (size_t)g * 3 * p.A, p.A, colour > 0 ? P : M, colour > 0 ? M : P, la, lane);
+        obs_emit<NC, T>(leaf_obs + (size_t)g * 3 * p.A, p.A, colour > 0 ? P : M, colour > 0 ? M : P, la, lane);
     if (lane == 0) {
         GState *s = p.gs + g;
         s->leaf_parent = lp; s->leaf_action = la; s->leaf_depth = depth; s->leaf_reps = MZ ? w.n_surv : 1;
@@ -542,8 +549,9 @@ extern "C" int gmz_root_obs(gmz_engine *e, void *obs, int obs_dtype, gmz_stream 
 {
     LIVE(e, "gmz_root_obs");
     if (!obs) return fail("gmz_root_obs: null argument");
-    if (obs_dtype != GMZ_F32) return fail("gmz_root_obs: only GMZ_F32 observations are supported");
-    DISPATCH_NC(e, k_root_obs<NC, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)obs));
+    if (obs_dtype == GMZ_F32) { DISPATCH_NC(e, k_root_obs<NC, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)obs)); }
+    else if (obs_dtype == GMZ_BF16) { DISPATCH_NC(e, k_root_obs<NC, unsigned short><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (unsigned short *)obs)); }
+    else return fail("gmz_root_obs: obs_dtype must be GMZ_F32 (NCHW float32) or GMZ_BF16 (NHWC bfloat16)");
     return check_launch("k_root_obs");
 }
 extern "C" int gmz_root_expand(gmz_engine *e, const float *logits, const void *values, int value_dtype,
@@ -560,14 +568,13 @@ extern "C" int gmz_select(gmz_engine *e, void *leaf_obs, int obs_dtype, int32_t 
 {
     LIVE(e, "gmz_select");
     if (e->p.mode != GMZ_MODE_ALPHAZERO) return fail("gmz_select: engine is in MuZero mode, use gmz_select_mz");
-    if (obs_dtype != GMZ_F32) return fail("gmz_select: only GMZ_F32 observations are supported");
-    if (e->p.f32acc) {
-        DISPATCH_NC(e, k_select<NC, false, true, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)leaf_obs, out_leaf_action,
-                                                                                            nullptr, nullptr, out_leaf_depth, nullptr));
-    } else {
-        DISPATCH_NC(e, k_select<NC, false, false, float><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (float *)leaf_obs, out_leaf_action,
-                                                                                             nullptr, nullptr, out_leaf_depth, nullptr));
-    }
+    if (obs_dtype != GMZ_F32 && obs_dtype != GMZ_BF16)
+        return fail("gmz_select: obs_dtype must be GMZ_F32 (NCHW float32) or GMZ_BF16 (NHWC bfloat16)");
+#define GMZ_SEL(F, T) DISPATCH_NC(e, k_select<NC, false, F, T><<<GRID(e), 0, (cudaStream_t)stream>>>(e->p, (T *)leaf_obs, out_leaf_action, \
+                                                                                           nullptr, nullptr, out_leaf_depth, nullptr))
+    if (obs_dtype == GMZ_F32) { if (e->p.f32acc) { GMZ_SEL(true, float); } else { GMZ_SEL(false, float); } }
+    else { if (e->p.f32acc) { GMZ_SEL(true, unsigned short); } else { GMZ_SEL(false, unsigned short); } }
+#undef GMZ_SEL
     return check_launch("k_select");
 }
 extern "C" int gmz_select_mz(gmz_engine *e, int32_t *out_parent_slot, int32_t *out_action, int32_t *out_child_slot,

@@ -952,6 +952,32 @@ __device__ __forceinline__ void root_init(const Params &p, WG &w, const float *l
     w.n_init = cnt; w.n_surv = cnt;
 }
 
+// The same planes as bf16 in NHWC order ([cell][own, opp, last]): what the network's first convolution reads
+// (channels_last), written by the select itself so no cast / re-layout kernel sits between tree and network.
+// Lane l writes the 4 cells x 3 channels x 2 bytes = 24 contiguous bytes of each chunk: adjacent lanes, adjacent bytes.
+template <int NC>
+__device__ __forceinline__ void obs_write_nhwc_bf16(unsigned short *obs, int A, u64 own_w, u64 opp_w, int last, int lane)
+{
+    constexpr unsigned short ONE = 0x3F80;      // bf16(1.0)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        const u64 ow = shfl_u64(own_w, 2 * j + (lane >> 4)) >> ((lane & 15) * 4);
+        const u64 pw = shfl_u64(opp_w, 2 * j + (lane >> 4)) >> ((lane & 15) * 4);
+        const int a0 = 128 * j + 4 * lane;
+        unsigned short v[12];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            v[3 * t + 0] = ((ow >> t) & 1ull) ? ONE : 0;
+            v[3 * t + 1] = ((pw >> t) & 1ull) ? ONE : 0;
+            v[3 * t + 2] = (a0 + t == last) ? ONE : 0;
+        }
+        // 16-bit stores: a game's block starts at g * 3A * 2 bytes, which is only 2-byte aligned for odd 3A
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (a0 + t < A) { obs[(size_t)(a0 + t) * 3] = v[3 * t]; obs[(size_t)(a0 + t) * 3 + 1] = v[3 * t + 1]; obs[(size_t)(a0 + t) * 3 + 2] = v[3 * t + 2]; }
+    }
+}
+
 // Observation planes of a position (game.py:12-17) for this lane's actions, from the
 // lane-distributed bitboards: own / opp relative to `to_move`, last-move one-hot.
 template <int NC, typename T>

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import GMZ_ACCUM_F32, GMZ_ACCUM_F64, GMZ_F32, GMZ_F64, GMZ_MODE_ALPHAZERO, GMZ_MODE_MUZERO, GmzConfig, check
+from ._lib import GMZ_ACCUM_F32, GMZ_ACCUM_F64, GMZ_BF16, GMZ_F32, GMZ_F64, GMZ_MODE_ALPHAZERO, GMZ_MODE_MUZERO, GmzConfig, check
 
 
 def _ptr(t):
@@ -118,9 +118,21 @@ class SearchEngine:
         self.launches += 1
         return b, pl, lm, mc
 
+    def obs_buffer_bf16(self):
+        """An observation buffer the kernels can fill directly in the network's input format: bfloat16, logical
+        shape [G,3,N,N] with channels_last strides (memory [G,N,N,3])."""
+        return torch.zeros((self.G, self.N, self.N, 3), dtype=torch.bfloat16, device=self.device).permute(0, 3, 1, 2)
+
+    def _obs_kind(self, out):
+        if out.dtype == torch.float32 and out.is_contiguous():
+            return GMZ_F32
+        if out.dtype == torch.bfloat16 and out.permute(0, 2, 3, 1).is_contiguous():
+            return GMZ_BF16
+        raise TypeError("observation buffer must be contiguous float32 [G,3,N,N] or channels_last bfloat16 [G,3,N,N]")
+
     def root_obs(self, out=None):
         out = self.leaf_obs if out is None else out
-        check(self.lib.gmz_root_obs(self.handle, _ptr(out), GMZ_F32, self._stream()), "gmz_root_obs")
+        check(self.lib.gmz_root_obs(self.handle, _ptr(out), self._obs_kind(out), self._stream()), "gmz_root_obs")
         self.launches += 1
         return out
 
@@ -142,13 +154,15 @@ class SearchEngine:
               "gmz_root_expand")
         self.launches += 1
 
-    def select(self, trace=False):
-        """AlphaZero mode: returns the leaf observations [G,3,N,N] (engine-owned buffer)."""
-        check(self.lib.gmz_select(self.handle, _ptr(self.leaf_obs), GMZ_F32,
+    def select(self, trace=False, out=None):
+        """AlphaZero mode: returns the leaf observations [G,3,N,N] (engine-owned float32 buffer, or `out`: a float32
+        NCHW or channels_last bfloat16 buffer, see obs_buffer_bf16)."""
+        out = self.leaf_obs if out is None else out
+        check(self.lib.gmz_select(self.handle, _ptr(out), self._obs_kind(out),
                                   _ptr(self.leaf_action) if trace else None,
                                   _ptr(self.leaf_depth) if trace else None, self._stream()), "gmz_select")
         self.launches += 1
-        return self.leaf_obs
+        return out
 
     def select_mz(self, with_reps=False):
         """MuZero mode: (parent_slot, action, child_slot, depth[, reps]) int32 [G]; -1 where nothing to evaluate."""

@@ -232,7 +232,9 @@ class DeviceEvaluator:
 
     @torch.no_grad()
     def _forward(self):
-        x = self.obs.to(self.dtype).contiguous(memory_format=torch.channels_last)
+        x = self.obs                 # already the network's input format when the select wrote bf16 NHWC: no cast, no re-layout
+        if x.dtype != self.dtype or not x.is_contiguous(memory_format=torch.channels_last):
+            x = x.to(self.dtype).contiguous(memory_format=torch.channels_last)
         p, v, _ = self.folded(x) if self.folded is not None else self.net.initial_inference(x)
         self.logits.copy_(p)
         self.values.copy_(v.reshape(-1))
@@ -264,3 +266,60 @@ class DeviceEvaluator:
         else:
             self._forward()
         return self.logits, self.values
+
+
+class NetworkSearch:
+    """AlphaZeroMCTS.search (mcts.py:197-280) for the engine's G games with a NETWORK evaluator, one CUDA graph per
+    simulation step: { gmz_select -> folded network -> gmz_expand_backup } -- the reference's per-simulation round trip
+    (mcts.py:253 -> workers.py:339-355: pickle, queue, H2D, forward, D2H, queue, unpickle) collapsed into one graph
+    launch with nothing leaving the device.  With dtype = bfloat16 the select writes its leaf observations directly as
+    bf16 NHWC, the network's input format.  Create the engine with accum_dtype="float32": the network returns float32
+    values, and that is the dtype the reference's tree then accumulates in."""
+
+    def __init__(self, engine, net, dtype=torch.bfloat16, graph=True, graph_warmup=2):
+        if engine.mode != "AlphaZero":
+            raise ValueError("NetworkSearch drives an AlphaZero-mode engine (MuZero mode: muzero.MuZeroDeviceSearch)")
+        self.e = engine
+        self.obs = engine.obs_buffer_bf16() if dtype == torch.bfloat16 else engine.leaf_obs
+        self.ev = DeviceEvaluator(net, self.obs, dtype=dtype, graph=False)
+        self.use_graph, self.graph_warmup, self.graph = bool(graph), int(graph_warmup), None
+        self._launches_per_step = 0
+
+    def update_weights(self, state_dict):
+        self.ev.update_weights(state_dict)           # in place: a captured graph keeps replaying against the same buffers
+
+    def _step(self):
+        e = self.e
+        e.select(out=self.obs)
+        self.ev._forward()
+        e.expand_backup(self.ev.logits, self.ev.values)
+
+    def _capture(self):
+        e = self.e
+        n0 = e.launches
+        torch.cuda.synchronize(e.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        self._launches_per_step = e.launches - n0
+        e.launches = n0                                # capturing launched nothing
+
+    @torch.no_grad()
+    def search(self, gumbel, num_simulations=None):
+        """One search for every game from the engine's current roots; follow with engine.finalize()."""
+        e = self.e
+        e.root_obs(self.obs)
+        self.ev._forward()
+        e.root_expand(self.ev.logits, self.ev.values, gumbel)
+        steps = (e.S if num_simulations is None else int(num_simulations)) - 1
+        done = 0
+        while done < steps:
+            if self.use_graph and self.graph is None and done >= self.graph_warmup:
+                self._capture()
+            if self.graph is not None:
+                self.graph.replay()
+                e.launches += self._launches_per_step
+            else:
+                self._step()
+            done += 1
+        return done

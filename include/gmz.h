@@ -36,9 +36,9 @@ extern "C" {
 #define GMZ_MAX_TOP_ACTIONS 32
 #define GMZ_WINNER_NONE 2 /* get_game_ended() returned None (game.py:60-63) */
 
-#define GMZ_F32 0
-#define GMZ_F64 1
-#define GMZ_BF16 2
+#define GMZ_F32 0  /* values: float32;  observations: float32, NCHW [G,3,N,N] */
+#define GMZ_F64 1  /* values: float64 */
+#define GMZ_BF16 2 /* observations only: bfloat16, NHWC [G,N,N,3] (channels_last: the network's input format) */
 #define GMZ_ACCUM_F64 0 /* gmz_config.accum_dtype */
 #define GMZ_ACCUM_F32 1
 
@@ -87,7 +87,8 @@ int gmz_set_roots(gmz_engine *e, const int8_t *boards, const int8_t *players, co
                   const int32_t *move_counts, gmz_stream stream);
 /* GomokuGame.reset() (game.py:8-11) for every game with mask[g] != 0 (NULL = all). */
 int gmz_games_reset(gmz_engine *e, const uint8_t *mask, gmz_stream stream);
-/* GomokuGame.get_board_state at the roots (game.py:12-17): obs [G,3,N,N]. */
+/* GomokuGame.get_board_state at the roots (game.py:12-17): obs [G,3,N,N] float32 (GMZ_F32) or the same
+ * planes as bfloat16 in NHWC order (GMZ_BF16). */
 int gmz_root_obs(gmz_engine *e, void *obs, int obs_dtype, gmz_stream stream);
 /* Read the root positions back (boards int8 [G,A], players, last_moves, move_counts; any may be NULL). */
 int gmz_get_roots(gmz_engine *e, int8_t *boards, int8_t *players, int32_t *last_moves, int32_t *move_counts,
@@ -100,7 +101,7 @@ int gmz_get_roots(gmz_engine *e, int8_t *boards, int8_t *players, int32_t *last_
 int gmz_root_expand(gmz_engine *e, const float *logits, const void *values, int value_dtype,
                     const double *gumbel, gmz_stream stream);
 /* AlphaZero mode: _select_leaf + path replay on the real board + leaf
- * observation (mcts.py:232-251).  leaf_obs [G,3,N,N]; optional int32 [G]
+ * observation (mcts.py:232-251).  leaf_obs [G,3,N,N] (obs_dtype as gmz_root_obs); optional int32 [G]
  * out_leaf_action / out_leaf_depth for tracing.  Games whose search is
  * complete (sim_count >= S) or inactive write a zero observation. */
 int gmz_select(gmz_engine *e, void *leaf_obs, int obs_dtype, int32_t *out_leaf_action, int32_t *out_leaf_depth,

@@ -101,3 +101,114 @@ def test_network_driven_search_replayed_through_the_oracle(accum):
             np.testing.assert_allclose(pol[g], r["policy"], rtol=1e-5, atol=1e-12)
     finally:
         oracle.set_eval_callback(None)
+
+
+def test_network_search_one_graph_per_step_equals_eager_steps():
+    """NetworkSearch: the captured {select -> network -> expand/backup} graph and bf16 NHWC observations written by the
+    select give exactly what the eager float32-observation path gives (same folded network, same visit counts)."""
+    import torch
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.network import DeviceEvaluator, NetworkSearch
+    N, S, G = 9, 48, 32
+    A = N * N
+    rs = np.random.RandomState(11)
+    boards = np.zeros((G, A), np.int8); players = np.ones(G, np.int8)
+    last = np.full(G, -1, np.int32); mc = np.zeros(G, np.int32)
+    for g in range(G):
+        p = 1
+        for a in rs.permutation(A)[: 2 * g]:
+            boards[g, a] = p; last[g] = a; p = -p; mc[g] += 1
+        players[g] = p
+    gum = torch.from_numpy(rs.gumbel(0, 1, (G, A))).cuda()
+    net = _net(7)
+    out = {}
+    for name in ("graph", "eager", "f32obs"):
+        eng = SearchEngine(G, board_size=N, num_simulations=S, accum_dtype="float32")
+        eng.set_roots(boards, players, last, mc)
+        if name == "f32obs":                                  # round 1's path: float32 NCHW observations, cast by torch
+            ev = DeviceEvaluator(net, eng.leaf_obs, dtype=torch.bfloat16, graph=False)
+            lg, v = ev(eng.root_obs()); eng.root_expand(lg, v, gum)
+            for _ in range(S - 1):
+                lg, v = ev(eng.select()); eng.expand_backup(lg, v)
+        else:
+            ns = NetworkSearch(eng, net, dtype=torch.bfloat16, graph=(name == "graph"))
+            assert ns.obs.dtype == torch.bfloat16 and ns.obs.is_contiguous(memory_format=torch.channels_last)
+            assert ns.search(gum) == S - 1
+            if name == "graph":
+                assert ns.graph is not None
+        pol, val, act, vis = (t.cpu().numpy().copy() for t in eng.finalize())
+        out[name] = (vis, act, val)
+        assert (vis.sum(1) == S - 1).all()
+    for name in ("eager", "f32obs"):
+        assert np.array_equal(out["graph"][0], out[name][0]) and np.array_equal(out["graph"][1], out[name][1]), name
+        assert np.array_equal(out["graph"][2], out[name][2]), name
+    # the bf16 NHWC observation the kernels write == the float32 planes, re-laid out
+    eng = SearchEngine(G, board_size=N, num_simulations=S)
+    eng.set_roots(boards, players, last, mc)
+    o16 = eng.root_obs(eng.obs_buffer_bf16())
+    assert torch.equal(o16.float(), eng.root_obs().clone())
+
+
+def test_bf16_network_against_fp32_network_at_8x128():
+    """The bench's network legs run the 8x128 GomokuNetEZ in bf16; the reference's server runs it in fp32
+    (workers.py:318).  Bound the difference on 15x15 positions: logits, softmax policy, value -- and what it does
+    to the searches (same noise, same roots): agreement of the chosen moves and of the visit distributions.  The
+    measured numbers go to gpurun_out/bf16_vs_fp32.json (copied to profiles/ by hand)."""
+    import json
+    import os
+    import torch
+    from datou_gomoku_muzero_b200.config import Config
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.network import GomokuNetEZ, NetworkSearch
+    N, S, G = 15, 64, 256
+    A = N * N
+    torch.manual_seed(0)
+    net = GomokuNetEZ(Config(BOARD_SIZE=N, ACTION_SPACE_SIZE=A, NUM_RES_BLOCKS=8, NUM_FILTERS=128, HEAD_HIDDEN_DIM=64))
+    with torch.no_grad():                                     # trained-like statistics: non-trivial BN, non-zero residual gains
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.8, 1.2); m.weight.normal_(0.5, 0.1); m.bias.normal_(0, 0.1)
+    rs = np.random.RandomState(2)
+    boards = np.zeros((G, A), np.int8); players = np.ones(G, np.int8)
+    last = np.full(G, -1, np.int32); mc = np.zeros(G, np.int32)
+    for g in range(G):
+        k = int(rs.randint(0, 120)); p = 1
+        for a in rs.permutation(A)[:k]:
+            boards[g, a] = p; last[g] = a; p = -p
+        players[g] = p; mc[g] = k
+    gum = torch.from_numpy(rs.gumbel(0, 1, (G, A))).cuda()
+    res = {}
+    saved = torch.backends.cudnn.allow_tf32
+    try:
+        for name, dt, tf32 in (("fp32", torch.float32, False), ("tf32", torch.float32, True), ("bf16", torch.bfloat16, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            eng = SearchEngine(G, board_size=N, num_simulations=S, accum_dtype="float32")
+            eng.set_roots(boards, players, last, mc)
+            ns = NetworkSearch(eng, net, dtype=dt, graph=False)
+            eng.root_obs(ns.obs); ns.ev._forward()
+            lg0, v0 = ns.ev.logits.clone(), ns.ev.values.clone()
+            ns.search(gum)
+            pol, val, act, vis = (t.cpu().numpy().copy() for t in eng.finalize())
+            res[name] = dict(logits=lg0.cpu().numpy(), values=v0.cpu().numpy(), act=act, vis=vis)
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+    valid = boards == 0
+
+    def softmax(l):
+        l = np.where(valid, l, -np.inf); e = np.exp(l - l.max(1, keepdims=True)); return e / e.sum(1, keepdims=True)
+    rep = {}
+    for name in ("tf32", "bf16"):
+        a, b = res["fp32"], res[name]
+        rep[name] = dict(max_abs_dlogit=float(np.abs(a["logits"] - b["logits"]).max()),
+                         max_abs_dpolicy=float(np.abs(softmax(a["logits"]) - softmax(b["logits"])).max()),
+                         max_abs_dvalue=float(np.abs(a["values"] - b["values"]).max()),
+                         move_agreement=float((a["act"] == b["act"]).mean()),
+                         visit_count_identical=float((a["vis"] == b["vis"]).all(1).mean()),
+                         mean_visit_l1=float(np.abs(a["vis"] - b["vis"]).sum(1).mean() / (2 * (S - 1))))
+    rep["config"] = dict(board=N, sims=S, games=G, net="GomokuNetEZ 8x128, seeded, perturbed BN statistics", reference="fp32 (allow_tf32 off)")
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(rep, open(os.path.join("gpurun_out", "bf16_vs_fp32.json"), "w"), indent=1)
+    print(json.dumps(rep))
+    assert rep["bf16"]["max_abs_dpolicy"] < 0.02 and rep["bf16"]["max_abs_dvalue"] < 0.05, rep
+    assert rep["tf32"]["max_abs_dpolicy"] <= rep["bf16"]["max_abs_dpolicy"] + 1e-3, rep
+    assert rep["bf16"]["move_agreement"] > 0.5 and rep["bf16"]["mean_visit_l1"] < 0.35, rep
