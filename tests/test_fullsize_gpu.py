@@ -87,3 +87,44 @@ def test_full_size_selfplay_bookkeeping():
         assert r["winner"] in (-1, 0, 1) and (r["winner"] != 0 or T == A)
         if r["winner"] != 0:
             assert r["winner"] == (1 if T % 2 == 1 else -1)              # the side that moved last won
+
+
+@pytest.mark.parametrize("div,accum", [(16, "float64"), (0, "float32")])
+def test_full_size_games_move_for_move_against_the_oracle(div, accum):
+    """The bench configuration itself -- 15x15, 400 simulations, the persistent multi-move launch with in-kernel
+    restart -- compared MOVE FOR MOVE with the CPU oracle's game loop: every move, root value and the winner of the
+    first finished games, policies within 1e-5 (quantised float64 and dense-logit float32-accumulation evaluators)."""
+    import torch
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+    from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
+    from oracle import oracle
+    Gs, S_, seed, nseed = 96, 400, 21, 22
+    eng = SearchEngine(Gs, board_size=N, num_simulations=S_, num_top_actions=K, accum_dtype=accum)
+    sp = SelfPlayEngine(eng, "e0", seed=seed, logit_div=div, noise_seed=nseed)
+    traj = TrajectoryStore(eng, extra_slots=Gs)
+    finished = []
+    for _ in range(8):                                       # several multi-move launches: games cross launch boundaries
+        sp.play(moves_per_game=16, traj=traj)
+        finished += traj.harvest()
+        if len({r["game"] for r in finished}) >= 10:
+            break
+    first = {}
+    for r in finished:                                       # the first game of each index starts at noise counter 0
+        first.setdefault(r["game"], r)
+    assert len(first) >= 8, len(first)
+    cfg = oracle.make_config(board_size=N, num_simulations=S_, num_top_actions=K, eval_seed=seed, logit_div=div,
+                             accum_dtype=int(accum == "float32"))
+    checked = 0
+    for g, r in sorted(first.items())[:10]:
+        T = r["length"]
+        gum = torch.empty((T, A), dtype=torch.float64, device="cuda")
+        for k in range(T):
+            eng.fill_gumbel(gum[k], nseed, (k * Gs + g) * A)
+        o = oracle.selfplay_game(cfg, np.concatenate([gum.cpu().numpy(), np.zeros((1, A))]))
+        assert o["T"] == T and o["winner"] == r["winner"], (g, o["T"], T)
+        assert np.array_equal(o["actions"], r["actions"]), g
+        assert np.array_equal(o["values"], r["values"]), g
+        np.testing.assert_allclose(r["policies"], o["policies"], rtol=1e-5, atol=1e-12)
+        checked += 1
+    assert checked >= 8
