@@ -227,7 +227,9 @@ template <int NC>
 __device__ __noinline__ u64 play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane)
 {
     const int g = w.g;
-    const u64 h = e0_hash_planes(a.e0.h0, w.to_move > 0 ? w.P : w.M, w.to_move > 0 ? w.M : w.P, p.NW, w.last_move, lane);
+    const GState *gs = p.gs + g;
+    const u64 rP = lane < GMZ_WORDS ? gs->p1[lane] : 0ull, rM = lane < GMZ_WORDS ? gs->m1[lane] : 0ull;
+    const u64 h = e0_hash_planes(a.e0.h0, w.to_move > 0 ? rP : rM, w.to_move > 0 ? rM : rP, p.NW, w.last_move, lane);
     const u64 nctr = ((u64)noise_ctr * (u64)p.G + (u64)g) * (u64)p.A;
     float lg[4 * NC]; double gum[4 * NC];
 #pragma unroll 1
@@ -247,6 +249,7 @@ __global__ void __launch_bounds__(32 * GMZ_PLAY_WARPS, GMZ_PLAY_MIN_CTAS)
 k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
 {
     __shared__ SelSmem s_sel[GMZ_PLAY_WARPS];
+    __shared__ DescSmem s_desc[GMZ_PLAY_WARPS];
     __shared__ short s_nvis[GMZ_PLAY_WARPS][128 * NC];
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int warp_slot = blockIdx.x * GMZ_PLAY_WARPS + wi;
@@ -306,16 +309,17 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
             __syncwarp();
             int ev = 0;
             while (w.sim_count < p.S) {
-                u64 P = w.P, M = w.M; int colour = w.to_move;
-                int lp, la;
+                int colour, lp, la;
+                DescSmem &ds = s_desc[wi];
+                const int depth = descend<NC, MZ, F32>(p, w, path, ds, s_sel[wi], warp_slot, lane, lp, la, colour);
                 PathReg pr;
-                const int depth = descend<NC, MZ, F32>(p, w, path, pr, s_sel[wi], warp_slot, lane, lp, la, P, M, colour);
-                path_root_stats<MZ>(p, w, depth, pr, lane);
+                path_load<MZ>(p, w, ds, depth, pr, lane);
                 prefetch_parent_rows<NC>(p, w, lp, lane);
                 // AlphaZero mode: evaluate the replayed board (mcts.py:251-253).  MuZero mode: the learned
                 // dynamics, here E0's recurrent half on the parent's hidden state (mcts.py:336-343).
                 const u64 h = MZ ? e0_child_hidden(p.nH[w.nbase + (size_t)lp], la)
-                                 : e0_hash_planes(a.e0.h0, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la, lane);
+                                 : e0_hash_planes(a.e0.h0, lane < GMZ_WORDS ? (colour > 0 ? ds.P[lane] : ds.M[lane]) : 0ull,
+                                                  lane < GMZ_WORDS ? (colour > 0 ? ds.M[lane] : ds.P[lane]) : 0ull, p.NW, la, lane);
                 const int reps = MZ ? w.n_surv : 1;            // MuZero: len(selected) identical selections -> that many backups
                 const int nn = w.num_nodes;
                 {   // evaluate + leaf.expand fused: logits go straight into the new node's row
@@ -363,8 +367,8 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                 slot = s->traj_slot; tl = s->traj_len;
                 if (tl == 0 && w.active) {     // first recorded move of this game: remember where it started
                     if (lane < GMZ_WORDS) {
-                        a.traj.start_board[((size_t)slot * 2 + 0) * GMZ_WORDS + lane] = w.P;
-                        a.traj.start_board[((size_t)slot * 2 + 1) * GMZ_WORDS + lane] = w.M;
+                        a.traj.start_board[((size_t)slot * 2 + 0) * GMZ_WORDS + lane] = s->p1[lane];
+                        a.traj.start_board[((size_t)slot * 2 + 1) * GMZ_WORDS + lane] = s->m1[lane];
                     }
                     if (lane == 0) {
                         int32_t *si = a.traj.start_info + (size_t)slot * 4;

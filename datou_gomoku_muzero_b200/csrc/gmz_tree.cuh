@@ -10,7 +10,6 @@ struct WG {
     size_t nbase;          // U  g * S : index of this game's node 0 in the per-node arrays
     double mm_min, mm_max; // U  MinMaxStats
     int sim_count, num_nodes, phase, next_thr, n_surv, n_init, to_move, last_move, active;  // U
-    u64 P, M;              // L  lane w < NW holds word w of p1 / m1
     unsigned vb;           // L  valid bits of this lane's actions (bit 4*j + t)
     int s_act, s_child, s_n;  // L  lane i < n_init: survivor i
     // (the survivors' gumbel noise / root logits and the valid bitboard stay in GState: they are only
@@ -25,8 +24,6 @@ __device__ __forceinline__ void wg_load(const Params &p, int g, int lane, WG &w)
     w.sim_count = s->sim_count; w.num_nodes = s->num_nodes; w.phase = s->phase; w.next_thr = s->next_thr;
     w.n_surv = s->n_surv; w.n_init = s->n_init; w.to_move = s->to_move; w.last_move = s->last_move;
     w.active = s->active;
-    w.P = lane < GMZ_WORDS ? s->p1[lane] : 0ull;
-    w.M = lane < GMZ_WORDS ? s->m1[lane] : 0ull;
     w.s_act = s->surv_act[lane]; w.s_child = s->surv_child[lane]; w.s_n = s->surv_n[lane];
 }
 template <int NC>
@@ -60,6 +57,27 @@ __device__ __forceinline__ void bb_do_move(u64 &P, u64 &M, int colour, int a, in
     const u64 bp = colour > 0 ? b : 0ull, bm = b ^ bp;
     P = (P | bp) & ~bm;
     M = (M | bm) & ~bp;
+}
+
+// Per-warp shared scratch of the simulation in flight: the descent path with the statistics read on the way
+// down (handed to the backup), and -- AlphaZero mode -- the bitboards the path is replayed on.  Kept in shared
+// memory, not registers: the select needs ~30 temporaries per level, and anything live across it in registers
+// is spilled and reloaded every level.
+struct PathEntry { int node, mir, n, pad; double W, R; };      // 32 bytes, see PathReg
+struct DescSmem {
+    PathEntry path[32];
+    u64 P[GMZ_WORDS], M[GMZ_WORDS];
+};
+// GomokuGame.do_move on the shared bitboards (one lane; the others read them after the next __syncwarp)
+__device__ __forceinline__ void bb_do_move_smem(DescSmem &ds, int colour, int a, int lane)
+{
+    if (lane == 0) {
+        const int wd = a >> 6;
+        const u64 b = 1ull << (a & 63);
+        u64 P = ds.P[wd], M = ds.M[wd];
+        if (colour > 0) { P |= b; M &= ~b; } else { M |= b; P &= ~b; }
+        ds.P[wd] = P; ds.M[wd] = M;
+    }
 }
 
 // utils.MinMaxStats.normalize (utils.py:16-25) with the range test hoisted.
@@ -708,10 +726,10 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
 // _select_leaf (mcts.py:88-104): root = first least-visited survivor (strict <, list order),
 // then interior selection until an unexpanded child is reached.  In AlphaZero mode the path
 // is replayed on the bitboards while descending (mcts.py:236-248).  Returns depth (edges).
-// pr: lane d <- the node at depth d and its statistics (lane 0 = the root).
+// ds.path[d] <- the node at depth d and its statistics; ds.P / ds.M <- the replayed position (AlphaZero mode).
 template <int NC, bool MZ, bool F32>
-__device__ __forceinline__ int descend(const Params &p, const WG &w, int2 *path, PathReg &pr, SelSmem &sc, int warp_slot, int lane,
-                                       int &leaf_parent, int &leaf_action, u64 &P, u64 &M, int &colour)
+__device__ __forceinline__ int descend(const Params &p, const WG &w, int2 *path, DescSmem &ds, SelSmem &sc, int warp_slot, int lane,
+                                       int &leaf_parent, int &leaf_action, int &colour)
 {
     const unsigned key = lane < w.n_surv ? (((unsigned)w.s_n << 5) | (unsigned)lane) : 0xffffffffu;
     const int bl = (int)(__reduce_min_sync(GMZ_FULL, key) & 31u);
@@ -719,32 +737,42 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, int2 *path,
     int node = __shfl_sync(GMZ_FULL, w.s_child, bl);
     int cn = 0, slot = 0;
     double cW = 0.0, cR = 0.0;
-    // (lanes 0 and 1 -- the root and the chosen root child -- get their statistics from path_root_stats() after
-    //  the descent: only the backup consumes them, and loading them here would stall the first level on them)
-    pr.node = 0; pr.mir = 0; pr.n = 0; pr.W = 0.0; pr.R = 0.0;
+    // (the root and the chosen root child get their statistics from path_load() after the descent: only the
+    //  backup consumes them, and loading them here would stall the first level on them)
     int parent = 0, depth = 1;
-    if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
+    colour = w.to_move;
+    if (!MZ) {
+        const GState *s = p.gs + w.g;
+        if (lane < GMZ_WORDS) { ds.P[lane] = s->p1[lane]; ds.M[lane] = s->m1[lane]; }
+        __syncwarp();
+        bb_do_move_smem(ds, colour, a, lane); colour = -colour;
+    }
     // MinMaxStats only change in the backup: 1 / (max - min + delta) is the same at every level of this descent
     const bool rng = w.mm_max > w.mm_min;
     const double rden = rng ? rcp_newton(F32 ? mm_denom<true>(p, w.mm_min, w.mm_max) : (w.mm_max - w.mm_min) + p.delta) : 0.0, mn = rng ? w.mm_min : 0.0;
     while (node >= 0) {
         const int mir = (parent << 5) | slot;
-        if (depth < 32) { if (lane == depth) { pr.node = node; pr.mir = mir; pr.n = cn; pr.W = cW; pr.R = cR; } }
-        else if (lane == 0) path[depth] = make_int2(node, mir);
+        if (depth < 32) {
+            if (lane == 0) { PathEntry e; e.node = node; e.mir = mir; e.n = cn; e.pad = 0; e.W = cW; e.R = cR; ds.path[depth] = e; }
+        } else if (lane == 0) path[depth] = make_int2(node, mir);
         int c;
         select_interior<NC, MZ, F32>(p, w, node, lane, sc, warp_slot, mn, rden, a, c, slot, cn, cW, cR);
-        if (!MZ) { bb_do_move(P, M, colour, a, lane); colour = -colour; }
+        if (!MZ) { bb_do_move_smem(ds, colour, a, lane); colour = -colour; }
         parent = node; node = c; ++depth;
     }
+    __syncwarp();
     leaf_parent = parent; leaf_action = a;
     return depth;
 }
 
-// Statistics of the root (lane 0) and of the root child on the path (lane 1): they have no slot in a parent's
-// block, so they come from the nodes' own arrays.  Issued right after the descent, consumed by the backup.
+// The descent's path into registers for the backup: lane d <- position d.  The root (lane 0) and the root child
+// on the path (lane 1) have no slot in a parent's block, so their statistics come from the nodes' own arrays --
+// issued here, right after the descent, consumed by the backup after the evaluation.
 template <bool MZ>
-__device__ __forceinline__ void path_root_stats(const Params &p, const WG &w, int depth, PathReg &pr, int lane)
+__device__ __forceinline__ void path_load(const Params &p, const WG &w, const DescSmem &ds, int depth, PathReg &pr, int lane)
 {
+    const PathEntry e = ds.path[lane];                 // (lanes >= depth read stale entries; the backup ignores them)
+    pr.node = lane == 0 ? 0 : e.node; pr.mir = lane == 0 ? 0 : e.mir; pr.n = e.n; pr.W = e.W; pr.R = MZ ? e.R : 0.0;
     if (lane == 0 || (lane == 1 && depth > 1)) {
         const size_t li = w.nbase + (size_t)pr.node;
         pr.n = p.nN[li]; pr.W = p.nW[li];
