@@ -217,7 +217,7 @@ template <int NC>
 __device__ __noinline__ u64 play_root(const Params &p, const PlayArgs &a, WG &w, unsigned noise_ctr, u64 noise_mixed, int lane);
 
 #ifndef GMZ_PLAY_MIN_CTAS
-#define GMZ_PLAY_MIN_CTAS 6
+#define GMZ_PLAY_MIN_CTAS 7
 #endif
 #ifndef GMZ_PLAY_WARPS
 #define GMZ_PLAY_WARPS 4

@@ -505,7 +505,8 @@ __device__ __noinline__ int select_interior_exact(const Params &p, const SelCtx 
 //     U   = sum over the unvisited valid actions of exp(logit - lub)       (float32, in [1, A])
 // and the list of its children in creation order WITH THEIR EDGE STATISTICS MIRRORED IN: one 1 KiB block per
 // node (Params::nBlk) of 32 slots x 32 bytes -- slot 0 the summary, slot j (1..31) child j-1 as
-//     { (action << 16) | child id,  logit,  N(child),  -,  W(child) f64,  reward(child) f64 }.
+//     { (action << 16) | child id,  logit,  N(child),  -,  W(child) f64,  x f64 },   x = reward(child) in MuZero mode,
+//     x = get_qsa(child) in AlphaZero mode (exact: the backup computes it for the MinMaxStats anyway).
 // The candidates of a select are then the <= 31 visited children plus `ub`: one per lane, no pass over the A
 // logits, ONE memory round trip per tree level (lane j reads its own slot while every lane reads slot 0; the
 // canonical per-node arrays nN / nW / nR are only read by the exact path, the root and the halving), and the
@@ -521,7 +522,10 @@ __device__ __noinline__ int select_interior_exact(const Params &p, const SelCtx 
 // over the parent's logits, float32 exp) once per simulation, when a child is added.
 constexpr int kBlkBytes = 1024;       // per-node block (Params::nBlk): 32 slots of 32 bytes
 constexpr int kSlotBytes = 32;
-constexpr int kListSpec = 8;          // slots loaded speculatively with the header (one per lane; 5 of 6 nodes have < 8 children)
+#ifndef GMZ_LIST_SPEC
+#define GMZ_LIST_SPEC 8
+#endif
+constexpr int kListSpec = GMZ_LIST_SPEC;   // slots loaded speculatively with the header (one per lane; 5 of 6 nodes have < 8 children)
 constexpr int kFastMaxVisited = 31;   // visited children (slots 1..31) + the best unvisited action fit one warp
 
 // Per-lane view of the descent path: lane d holds the node at depth d (depths >= 32 spill to Params::path) with
@@ -623,13 +627,14 @@ __device__ __forceinline__ int node_link(const Params &p, const WG &w, int paren
     return (parent << 5) | slot;
 }
 
-// One slot of a node's block: the first 16 bytes (key, logit, N) and the statistics behind them.
+// One slot of a node's block: the first 16 bytes (key, logit, N) and the statistics behind them
+// (R = the child's reward in MuZero mode, its q in AlphaZero mode).
 template <bool MZ>
 __device__ __forceinline__ void slot_load(const char *slot, int4 &e, double &W, double &R)
 {
     e = *reinterpret_cast<const int4 *>(slot);
-    if (MZ) { const double2 t = *reinterpret_cast<const double2 *>(slot + 16); W = t.x; R = t.y; }
-    else { W = *reinterpret_cast<const double *>(slot + 16); R = 0.0; }
+    const double2 t = *reinterpret_cast<const double2 *>(slot + 16);
+    W = t.x; R = t.y;
 }
 
 // Returns the chosen action, the child it leads to (-1 = not created yet) and -- for an existing child --
@@ -654,12 +659,22 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         loaded_all = true;
         int key = (ub << 16) | 0xffff, nn = 0; float slg = __int_as_float(h.y); double W = 0.0, rew = 0.0;
         if (vis) { key = e.x; slg = __int_as_float(e.y); nn = e.z; W = eW; rew = MZ ? eR : 0.0; }
+#if defined(GMZ_PREFETCH_CHILD_L1) || defined(GMZ_PREFETCH_CHILD_L2)
+        if (vis) {      // the next level reads the chosen child's block: start pulling every candidate's first line now
+            const char *cb = blk_of(p, w.nbase + (size_t)(key & 0xffff));
+#ifdef GMZ_PREFETCH_CHILD_L1
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(cb));
+#else
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(cb));
+#endif
+        }
+#endif
         const int maxN = __reduce_max_sync(GMZ_FULL, nn), sumN = __reduce_add_sync(GMZ_FULL, nn);
         const double scale = (p.c_visit + (double)maxN) * p.c_scale;
         double xs = -INFINITY;
         if (cand) {
-            // float32 mode: q IS float32 arithmetic in the reference, so it is computed exactly here too
-            const double q = !vis ? 0.0 : (F32 ? q_of<true>(p, W, nn, rew) : rew + p.discount * (W * rcp_newton((double)nn)));
+            // AlphaZero mode: q comes with the slot.  MuZero mode, float32: q IS float32 arithmetic in the reference -> exact here too
+            const double q = !vis ? 0.0 : (!MZ ? eR : (F32 ? q_of<true>(p, W, nn, rew) : rew + p.discount * (W * rcp_newton((double)nn))));
             double nrm = (q - mn) * rden;                       // (mn, rden) = (0, 0) while max <= min: normalize() is 0 then
             const int hi = __double2hiint(nrm);                  // clamp to [0, 1] on the high word
             nrm = hi < 0 ? 0.0 : (hi >= 0x3ff00000 ? 1.0 : nrm);
@@ -682,7 +697,7 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
             const int nb = __shfl_sync(GMZ_FULL, nn, bl);
             const float lb = __shfl_sync(GMZ_FULL, slg, bl);
             const double Wb = __shfl_sync(GMZ_FULL, W, bl), rb = __shfl_sync(GMZ_FULL, rew, bl);
-            near = near && !(nn == nb && nn > 0 && slg == lb && W == Wb && rew == rb);
+            near = near && !(nn == nb && nn > 0 && slg == lb && W == Wb && rew == rb);      // (AlphaZero mode: W and N fix q)
             near = __any_sync(GMZ_FULL, near);
         } else near = false;
         if (!near) {
@@ -786,6 +801,9 @@ template <int NC>
 __device__ __forceinline__ void prefetch_parent_rows(const Params &p, const WG &w, int parent, int lane)
 {
     if (parent == 0) return;
+#ifdef GMZ_NO_PREFETCH
+    return;
+#endif
     const size_t pi = (w.nbase + (size_t)parent) * (size_t)(128 * NC);          // row index * AP
     const char *a = lane < 4 * NC ? (const char *)(p.logits + pi) + 128 * lane   // 4*NC lines of logits, 2*NC of child ids
                                   : (const char *)(p.child + pi) + 128 * (lane - 4 * NC);
@@ -847,11 +865,12 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const int2 *path,
             }
         }
         if (act) {
+            double myq = 0.0;
             for (int r = 0; r < reps; ++r) {
                 W = F32 ? (double)__fadd_rn((float)W, (float)myv) : __dadd_rn(W, myv); n += 1;
                 if (pos > 0) {   // min_max_stats.update(parent.get_qsa(node.action))
-                    const double q = q_of<F32>(p, W, n, R);
-                    qmin = dmin2(qmin, q); qmax = dmax2(qmax, q);
+                    myq = q_of<F32>(p, W, n, R);
+                    qmin = dmin2(qmin, myq); qmax = dmax2(qmax, myq);
                 }
             }
             const size_t ni = w.nbase + (size_t)node;
@@ -861,7 +880,8 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const int2 *path,
                 char *e = blk_of(p, w.nbase + (size_t)(mir >> 5)) + kSlotBytes * (mir & 31);
                 *reinterpret_cast<int *>(e + 8) = n;
                 *reinterpret_cast<double *>(e + 16) = W;
-                if (MZ && is_new) *reinterpret_cast<double *>(e + 24) = R;
+                if (MZ) { if (is_new) *reinterpret_cast<double *>(e + 24) = R; }
+                else *reinterpret_cast<double *>(e + 24) = myq;                     // get_qsa(child), read by the parent's selects
             }
         }
     }
