@@ -157,12 +157,86 @@ __global__ void k_per_add_idx(long long *idx, long long capacity, long long writ
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) idx[i] = (write_ptr + i) % capacity + capacity - 1;
 }
+
+// Bulk add (n <= capacity consecutive ring positions, so no leaf repeats): the same bits as n sequential add()s, on
+// the whole GPU.  A tree node's value after the batch is its old value with the `change`s of the batch leaves below
+// it added ONE BY ONE IN BATCH ORDER (replay_buffer.py:11-19) -- and for consecutive ring positions those leaves are
+// at most four runs of consecutive batch indices (two leaf levels of the heap x the ring's wrap-around).  So every
+// internal node is independent: one thread per node folds its runs in order.  The root's fold is n dependent adds
+// long (the floor bit-exactness sets); everything else hides under it.
+__global__ void k_per_add_leaves(double *tree, long long capacity, long long write_ptr, const double *prio, int n, double *change)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long j = (write_ptr + i) % capacity + capacity - 1;
+    const double p = prio[i];
+    change[i] = __dsub_rn(p, tree[j]);          // change = priority - self.tree[tree_idx]
+    tree[j] = p;
+}
+__global__ void k_per_add_nodes(double *tree, long long capacity, long long write_ptr, int n, const double *change)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= capacity - 1) return;                // internal nodes only
+    const int d = node_depth(k), Dmax = node_depth(2 * capacity - 2);
+    long long rs[4], re[4];
+    int nr = 0;
+    for (int t = max(d, Dmax - 1); t <= Dmax; ++t) {          // the (at most two) levels that hold leaves
+        long long lo = ((k + 1) << (t - d)) - 1, hi = ((k + 2) << (t - d)) - 2;
+        if (t == Dmax) { lo = max(lo, (1ll << Dmax) - 1); hi = min(hi, 2 * capacity - 2); }
+        else { lo = max(lo, capacity - 1); hi = min(hi, (1ll << Dmax) - 2); }
+        if (lo > hi) continue;
+        const long long plo = lo - (capacity - 1), phi = hi - (capacity - 1);      // ring positions under this node
+        // batch index of ring position q: q - write_ptr (first part), q + capacity - write_ptr (after the wrap)
+        const long long a0 = max(plo, write_ptr), a1 = min(phi, min(capacity - 1, write_ptr + n - 1));
+        if (a0 <= a1) { rs[nr] = a0 - write_ptr; re[nr] = a1 - write_ptr; ++nr; }
+        const long long wrapped = write_ptr + n - capacity;                        // positions 0 .. wrapped-1 come after the wrap
+        const long long b0 = plo, b1 = min(phi, wrapped - 1);
+        if (wrapped > 0 && b0 <= b1) { rs[nr] = b0 + capacity - write_ptr; re[nr] = b1 + capacity - write_ptr; ++nr; }
+    }
+    if (nr == 0) return;
+    for (int a = 1; a < nr; ++a)                  // batch order
+        for (int b = a; b > 0 && rs[b] < rs[b - 1]; --b) {
+            const long long ts = rs[b], te = re[b]; rs[b] = rs[b - 1]; re[b] = re[b - 1]; rs[b - 1] = ts; re[b - 1] = te;
+        }
+    double acc = tree[k];
+    for (int a = 0; a < nr; ++a) {
+        long long i = rs[a];
+        if (i + 15 <= re[a]) {                    // software pipeline: the next 16 changes load while these 16 are added, in order
+            double c[16], nx[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) c[u] = __ldg(change + i + u);
+            for (; i + 31 <= re[a]; i += 16) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) nx[u] = __ldg(change + i + 16 + u);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) acc = __dadd_rn(acc, c[u]);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) c[u] = nx[u];
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) acc = __dadd_rn(acc, c[u]);
+            i += 16;
+        }
+        for (; i <= re[a]; ++i) acc = __dadd_rn(acc, change[i]);   // self.tree[parent] += change
+    }
+    tree[k] = acc;
+}
+
 extern "C" int gmz_per_add(double *tree, int64_t capacity, int64_t write_ptr, const double *priorities, int n,
                            int64_t *scratch_idx, gmz_stream stream)
 {
     if (!tree || !priorities || !scratch_idx) return per_fail("gmz_per_add: null argument");
     if (n <= 0) return 0;
     if (capacity < 1 || write_ptr < 0 || write_ptr >= capacity) return per_fail("gmz_per_add: bad capacity / write_ptr");
+    if (n >= 64 && (int64_t)n <= capacity && capacity >= 2) {     // bulk path: node-parallel, whole GPU
+        double *change = reinterpret_cast<double *>(scratch_idx);  // the caller's int64 [n] scratch, reused as float64 [n]
+        k_per_add_leaves<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(tree, capacity, write_ptr, priorities, n, change);
+        const long long nodes = capacity - 1;
+        k_per_add_nodes<<<(unsigned)((nodes + 127) / 128), 128, 0, (cudaStream_t)stream>>>(tree, capacity, write_ptr, n, change);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return per_fail(cudaGetErrorString(e));
+        return 0;
+    }
     k_per_add_idx<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((long long *)scratch_idx, capacity, write_ptr, n);
     return gmz_per_update(tree, capacity, scratch_idx, priorities, n, stream);
 }

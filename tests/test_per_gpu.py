@@ -82,3 +82,28 @@ def test_per_sample_and_update_full_size_vs_oracle():
     t = gt.tree.cpu().numpy()
     leaves = t[cap - 1:]
     assert abs(t[0] - leaves.sum()) < 1e-6 * max(1.0, leaves.sum())
+
+
+@pytest.mark.parametrize("cap", [1, 2, 37, 64, 1000, 4096, 100_003])
+def test_bulk_add_is_bit_identical_to_sequential_adds(cap):
+    """gmz_per_add's node-parallel bulk path (every internal node folds its batch leaves in batch order) against the
+    oracle's one-by-one SumTree.add: non-power-of-two capacities (two leaf levels), ring wrap-around, full refills,
+    small batches (which take the chunked path)."""
+    from datou_gomoku_muzero_b200 import replay_buffer as rb
+    from oracle import oracle as O
+    rs = np.random.RandomState(cap)
+    gt, ot = rb.SumTree(cap), O.SumTree(cap)
+    sizes = [1, min(cap, 70), max(1, cap // 3), cap, max(1, cap - 1), min(cap, 200), cap]
+    for n in sizes:
+        pri = np.abs(rs.randn(n)) * rs.choice([1e-3, 1.0, 50.0]) + 1e-6
+        gt.add_many(pri)
+        for x in pri:
+            ot.add(float(x))
+        assert gt.write_ptr == ot.write_ptr and gt.count == ot.count
+        assert np.array_equal(gt.tree.cpu().numpy(), ot.tree), (cap, n)
+    if cap >= 64:          # and updates on top of bulk-added state stay exact
+        idx = rs.randint(0, cap, size=min(cap, 100)) + cap - 1
+        newp = np.abs(rs.randn(len(idx))) + 1e-6
+        gt.update_many(idx, newp)
+        ot.update_batch(idx, newp, 1.0)
+        assert np.array_equal(gt.tree.cpu().numpy(), ot.tree)
