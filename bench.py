@@ -276,11 +276,13 @@ def cpu_baseline_leg(budget_s=10.0):
 
 
 def own_bytes_per_sim(d, n_vis=3.2):
-    """Bytes one simulation of THIS kernel has to move: per interior select a 16 B header,
-    n_vis list entries (8 B) and n_vis child (N, W) pairs (12 B); the new node's logits + child rows written;
-    the parent's logits + child rows read once for its refreshed summary, header and list entry written; the
-    backup's read-modify-write of (N, W) along the path."""
-    return (d - 1) * (16 + 20 * n_vis) + (4 * A + 2 * A + 16) + (4 * A + 2 * A + 16 + 16 + 8 + 2) + 24 * (d + 1)
+    """Bytes one simulation of THIS kernel has to move: per interior select the node block's
+    16 B summary and n_vis 32 B child slots (key, logit, N, W, q -- one round trip, no gather of the children's own
+    arrays); the new node's logits + child rows and summary written; the parent's logits + child rows read once for
+    its refreshed summary, one slot key + the summary written; the backup's stores of (N, W) to each path node's
+    own arrays and of (N, W, q) to its slot in the parent's block (no loads: the statistics come down with the
+    descent); the root's and root child's (N, W) read after the descent."""
+    return (d - 1) * (16 + 32 * n_vis) + (4 * A + 2 * A + 16) + (4 * A + 2 * A + 16 + 8 + 16) + 32 * (d + 1) + 24
 
 
 def net_leg(eng, dev, peaks, dtype_name="bf16"):
