@@ -533,8 +533,8 @@ constexpr int kFastMaxVisited = 31;   // visited children (slots 1..31) + the be
 // of this node in the parent's block (slot 0 = not mirrored: root children, children past the 31st).
 struct PathReg { int node, mir, n; double W, R; };
 __device__ __forceinline__ char *blk_of(const Params &p, size_t ni) { return p.nBlk + ni * (size_t)kBlkBytes; }
-constexpr double kCertEps = 3e-5;     // > 6x the error bound of a probability on this path (float32 exp / summary ~3e-6,
-                                      //  fixed-point softmax denominator ~2e-6)
+constexpr double kCertEps = 4.5e-5;   // > 6x the error bound of a probability on this path (float32 exp / summary ~3e-6,
+                                      //  fixed-point softmax denominator ~2e-6, fixed-point summary sum U ~2e-6)
 
 // ub / lub / U / "ambiguous" for the candidate set `cand` (bit i = this lane's action i).  Ambiguous:
 // two different unvisited logits closer than 1e-6 -- float64 rounding of logit + sigma could merge
@@ -564,7 +564,7 @@ __device__ __forceinline__ void unvisited_summary(const float *lg, unsigned cand
         if (WITH_U) u = __fadd_rn(u, exp_approx(d));
         am |= (d < 0.0f) && (d > -1e-6f);
     }
-    U = WITH_U ? warp_sum_f32(u) : 0.0f;
+    U = WITH_U ? warp_sum_fx(u) : 0.0f;              // <= 8 terms per lane, each <= 1: one fixed-point REDUX (error <= 2e-6 of U >= 1)
     amb = __any_sync(GMZ_FULL, am);
 }
 
@@ -686,11 +686,14 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         const float sum = warp_sum_fx(un ? __fmul_rn(ef, __int_as_float(h.x)) : ef);
         const float pf = __fmul_rn(ef, rcp_approx(sum));
         const double s = (double)pf - (double)nn * rcp_newton((double)(1 + sumN));
-        const u64 k64 = cand ? f64_key(s) : 0ull;
-        const u64 mk = warp_max_key(k64);
-        const int a = __reduce_min_sync(GMZ_FULL, (cand && k64 == mk) ? (key >> 16) : 0x7fffffff);
-        const int bl = __ffs(__ballot_sync(GMZ_FULL, cand && k64 == mk && (key >> 16) == a)) - 1;
-        const double sb = f64_unkey(mk);
+        // the winner is FOUND in float32 (one REDUX; lowest action among float32 ties) and then CERTIFIED in float64
+        // against every other candidate: a candidate that beats it by less than float32 resolution fails the margin
+        // below like any other near-tie
+        const unsigned k32 = cand ? f32_key((float)s) : 0u;
+        const unsigned mk = __reduce_max_sync(GMZ_FULL, k32);
+        const int a = __reduce_min_sync(GMZ_FULL, (cand && k32 == mk) ? (key >> 16) : 0x7fffffff);
+        const int bl = __ffs(__ballot_sync(GMZ_FULL, cand && k32 == mk && (key >> 16) == a)) - 1;
+        const double sb = __shfl_sync(GMZ_FULL, s, bl);
         const float pb = __shfl_sync(GMZ_FULL, pf, bl);
         bool near = cand && lane != bl && !(sb - s > kCertEps * (double)(pb + pf));
         if (__any_sync(GMZ_FULL, near)) {      // a near-tie is fine only between bit-identical inputs (a true tie)

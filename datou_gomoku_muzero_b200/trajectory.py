@@ -192,7 +192,10 @@ class DeviceSliceStore:
     """Replay data resident on the GPU: finished games stay in their trajectory slots, a training
     sample is the pair (slot, t), and `batch()` builds the trainer tuple (obs, act, rew, pi, val) of
     workers.py:430-433 with one kernel.  n-step value targets are computed on the device when a game
-    is ingested (workers.py:144-152, 205).  Oldest games are evicted (slots recycled) past `capacity_games`."""
+    is ingested (workers.py:144-152, 205).  Oldest games are evicted (slots recycled) past `capacity_games`.
+    The sample index is a device tensor (`index`, int32 [n, 2]); `batch()` takes (slot, t) pairs as a sequence or as
+    a tensor.  (replay_buffer.DeviceReplayBuffer is the variant that also holds the PER tree and stores packed move
+    records instead of keeping trajectory slots resident.)"""
 
     def __init__(self, traj: "TrajectoryStore", capacity_games=None):
         self.traj, e = traj, traj.e
@@ -203,7 +206,7 @@ class DeviceSliceStore:
         self.length = torch.zeros(n, dtype=torch.int32, device=e.device)
         self.winner = torch.zeros(n, dtype=torch.int32, device=e.device)
         self.resident = []          # slots in ingestion order
-        self.index = []             # (slot, t) of every stored slice, the order add() would have produced
+        self.index = torch.zeros((0, 2), dtype=torch.int32, device=e.device)   # (slot, t) of every stored slice, in add() order
 
     def ingest(self, finished):
         """finished: records from TrajectoryStore.harvest(recycle=False).  Returns the new (slot, t) samples."""
@@ -220,16 +223,18 @@ class DeviceSliceStore:
                                       dpow.data_ptr(), int(config.N_STEPS), self.targets.data_ptr(), e._stream()),
               "gmz_value_targets")
         e.launches += 1
-        new = []
-        for r in finished:
-            self.resident.append(r["slot"])
-            new += [(r["slot"], t) for t in range(r["length"])]
-        self.index += new
-        while len(self.resident) > self.capacity_games:
-            old = self.resident.pop(0)
-            self.index = [st for st in self.index if st[0] != old]
-            self.traj.release([old])
-        return new
+        hs = np.array([r["slot"] for r in finished], np.int32)
+        hl = np.minimum(np.array([r["length"] for r in finished], np.int64), self.traj.max_moves)
+        new = np.stack([np.repeat(hs, hl), (np.arange(int(hl.sum())) - np.repeat(np.cumsum(hl) - hl, hl)).astype(np.int32)], axis=1)
+        self.resident += hs.tolist()
+        self.index = torch.cat([self.index, torch.as_tensor(new, device=e.device)])
+        if len(self.resident) > self.capacity_games:
+            n_old = len(self.resident) - self.capacity_games
+            old, self.resident = self.resident[:n_old], self.resident[n_old:]
+            old_t = torch.tensor(old, dtype=torch.int32, device=e.device)
+            self.index = self.index[~torch.isin(self.index[:, 0], old_t)]          # one mask, no host loop
+            self.traj.release(old_t)
+        return [tuple(x) for x in new.tolist()]
 
     def batch(self, samples, rot_k=0, flip=False):
         """samples: sequence of (slot, t).  Returns device tensors (obs f32 [B,U+1,3,N,N], act i32 [B,U],
@@ -238,8 +243,9 @@ class DeviceSliceStore:
         gather itself (act comes back augmented; padded entries stay -1, so the reference's `act != -1` mask,
         loss.py:85, can be taken from the returned tensor)."""
         e = self.e
-        B, U, N, A = len(samples), int(config.NUM_UNROLL_STEPS), e.N, e.A
-        st = torch.tensor(samples, dtype=torch.int32, device=e.device).reshape(B, 2)
+        st = samples.to(device=e.device, dtype=torch.int32) if torch.is_tensor(samples) else torch.tensor(samples, dtype=torch.int32, device=e.device)
+        st = st.reshape(-1, 2)
+        B, U, N, A = int(st.shape[0]), int(config.NUM_UNROLL_STEPS), e.N, e.A
         s_slot, s_t = st[:, 0].contiguous(), st[:, 1].contiguous()
         obs = torch.empty((B, U + 1, 3, N, N), dtype=torch.float32, device=e.device)
         act = torch.empty((B, U), dtype=torch.int32, device=e.device)
