@@ -689,10 +689,12 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
         // the winner is FOUND in float32 (one REDUX; lowest action among float32 ties) and then CERTIFIED in float64
         // against every other candidate: a candidate that beats it by less than float32 resolution fails the margin
         // below like any other near-tie
-        const unsigned k32 = cand ? f32_key((float)s) : 0u;
+        // (key = the score's float32 bits with the low 9 replaced by 511 - action: ONE REDUX orders by score, then by
+        //  lowest action; candidates closer than 2^-14 relative merge into a "tie" and go through the margin test)
+        const unsigned k32 = cand ? ((f32_key((float)s) & 0xFFFFFE00u) | (unsigned)(511 - (key >> 16))) : 0u;
         const unsigned mk = __reduce_max_sync(GMZ_FULL, k32);
-        const int a = __reduce_min_sync(GMZ_FULL, (cand && k32 == mk) ? (key >> 16) : 0x7fffffff);
-        const int bl = __ffs(__ballot_sync(GMZ_FULL, cand && k32 == mk && (key >> 16) == a)) - 1;
+        const int a = 511 - (int)(mk & 511u);
+        const int bl = __ffs(__ballot_sync(GMZ_FULL, cand && k32 == mk)) - 1;
         const double sb = __shfl_sync(GMZ_FULL, s, bl);
         const float pb = __shfl_sync(GMZ_FULL, pf, bl);
         bool near = cand && lane != bl && !(sb - s > kCertEps * (double)(pb + pf));
