@@ -149,7 +149,9 @@ k_root_expand(Params p, const float *logits, const void *values, int vdtype, con
 {
     const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (g >= p.G) return;
-    WG w; wg_load(p, g, lane, w);
+    __shared__ WG s_wg[WARPS_PER_CTA];
+    WG &w = s_wg[threadIdx.x >> 5];
+    wg_load(p, g, lane, w);
     if (!w.active) return;
     wg_valid_bits<NC>(p, w, lane);
     float lg[4 * NC]; double gum[4 * NC];
@@ -171,7 +173,9 @@ k_select(const __grid_constant__ Params p, T *leaf_obs, int32_t *out_a, int32_t 
     // AZ: out_a = leaf action (trace).  MZ: out_a = parent slot, out_b = action, out_c = child slot.
     const int lane = threadIdx.x & 31, g = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
     if (g >= p.G) return;
-    WG w; wg_load(p, g, lane, w);
+    __shared__ WG s_wg[WARPS_PER_CTA];
+    WG &w = s_wg[threadIdx.x >> 5];
+    wg_load(p, g, lane, w);
     const bool run = w.active && w.sim_count >= 1 && w.sim_count < p.S;
     if (!run) {
         if (!MZ && leaf_obs) {
@@ -223,7 +227,9 @@ k_expand_backup(const __grid_constant__ Params p, const float *logits, const voi
     const GState *s = p.gs + g;
     const int depth = s->leaf_depth;
     if (!s->active || depth <= 0) return;
-    WG w; wg_load(p, g, lane, w);
+    __shared__ WG s_wg[WARPS_PER_CTA];
+    WG &w = s_wg[threadIdx.x >> 5];
+    wg_load(p, g, lane, w);
     const int lp = s->leaf_parent, la = s->leaf_action, reps = s->leaf_reps;
     const int2 *path = p.path + (size_t)g * (p.S + 2);
     float lg[4 * NC];
@@ -235,7 +241,7 @@ k_expand_backup(const __grid_constant__ Params p, const float *logits, const voi
     node_write_row<NC>(p, w, nn, lg, lane);
     node_init_hdr<NC>(p, w, nn, lg, lane);
     const int nmir = node_link<NC>(p, w, lp, la, nn, lane);
-    w.num_nodes = nn + 1;
+    wg_set(w.num_nodes, nn + 1);
     PathReg pr; pr.node = 0; pr.mir = 0; pr.n = 0; pr.W = 0.0; pr.R = 0.0;
     if (lane < min(depth, 32)) {        // the statistics the fused kernel keeps in registers: re-read them here
         const int2 t = path[lane]; pr.node = t.x; pr.mir = t.y;
@@ -244,8 +250,7 @@ k_expand_backup(const __grid_constant__ Params p, const float *logits, const voi
     }
     backup<MZ, F32>(p, w, path, pr, depth, nn, nmir, value, reward, reps, lane);
     survivor_visit(w, depth, pr.node, nn, la, reps, lane);
-    w.sim_count += reps;
-    __syncwarp();
+    { const int sc = w.sim_count; wg_set(w.sim_count, sc + reps); }
     if (halving_ready(p, w)) sequential_halving<MZ, F32>(p, w, lane);
     wg_store_search(p, lane, w);
     if (lane == 0) p.gs[g].leaf_depth = 0;
@@ -258,7 +263,9 @@ k_finalize(const __grid_constant__ Params p, double *policy, double *value, int3
     __shared__ short s_nvis[WARPS_PER_CTA][128 * NC];
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5, g = blockIdx.x * WARPS_PER_CTA + wi;
     if (g >= p.G) return;
-    WG w; wg_load(p, g, lane, w);
+    __shared__ WG s_wg[WARPS_PER_CTA];
+    WG &w = s_wg[threadIdx.x >> 5];
+    wg_load(p, g, lane, w);
     double v; int a;
     finalize_root<NC, MZ, F32>(p, w, lane, policy ? policy + (size_t)g * p.A : nullptr, visits ? visits + (size_t)g * p.A : nullptr,
                           s_nvis[wi], p.pyset + ((size_t)blockIdx.x * WARPS_PER_CTA + wi) * 4096, v, a);

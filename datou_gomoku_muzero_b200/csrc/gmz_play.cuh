@@ -76,7 +76,8 @@ __device__ __noinline__ void finalize_root(const Params &p, WG &w, int lane, dou
     Row<NC> r;
     row_load<NC, MZ, F32>(p, w, 0, lane, r);
     double x[4 * NC];
-    const double inv = row_softmax<NC, F32>(p, w, r, x);
+    const double inv = row_softmax<NC, F32>(p, w, r, x, lane);
+    const unsigned wvb = w.vb[lane];
     int bn = -1, ba = 0x7fffffff;
 #pragma unroll
     for (int i = 0; i < 4 * NC; ++i) {
@@ -85,13 +86,13 @@ __device__ __noinline__ void finalize_root(const Params &p, WG &w, int lane, dou
         if (a < p.A) {
             if (policy) policy[a] = __dmul_rn(x[i], inv);
             if (visits) visits[a] = r.n[i];
-            if (((w.vb >> i) & 1u) && r.n[i] > bn) { bn = r.n[i]; ba = a; }
+            if (((wvb >> i) & 1u) && r.n[i] > bn) { bn = r.n[i]; ba = a; }
         }
     }
     const int maxn = __reduce_max_sync(GMZ_FULL, bn);
     int ties = 0;
 #pragma unroll
-    for (int i = 0; i < 4 * NC; ++i) ties += (((w.vb >> i) & 1u) && r.n[i] == maxn) ? 1 : 0;
+    for (int i = 0; i < 4 * NC; ++i) ties += (((wvb >> i) & 1u) && r.n[i] == maxn) ? 1 : 0;
     ties = __reduce_add_sync(GMZ_FULL, ties);
     int best = __reduce_min_sync(GMZ_FULL, bn == maxn ? ba : 0x7fffffff);
     __syncwarp();
@@ -250,6 +251,7 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
 {
     __shared__ SelSmem s_sel[GMZ_PLAY_WARPS];
     __shared__ DescSmem s_desc[GMZ_PLAY_WARPS];
+    __shared__ WG s_wg[GMZ_PLAY_WARPS];
     __shared__ short s_nvis[GMZ_PLAY_WARPS][128 * NC];
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int warp_slot = blockIdx.x * GMZ_PLAY_WARPS + wi;
@@ -299,12 +301,13 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
             game_reset(p, s, lane);
             __syncwarp();
         }
-        WG w; wg_load(p, g, lane, w);
+        WG &w = s_wg[wi];
+        wg_load(p, g, lane, w);
         double value = 0.0; int action = -1;
         if (w.active) {
             wg_valid_bits<NC>(p, w, lane);
             u64 h_root;
-            { WG t = w; h_root = play_root<NC>(p, a, t, s->noise_ctr, noise_mixed, lane); w = t; }   // by copy: w stays in registers
+            h_root = play_root<NC>(p, a, w, s->noise_ctr, noise_mixed, lane);
             if (MZ && lane == 0) p.nH[w.nbase] = h_root;         // root hidden state = hash of the root observation
             __syncwarp();
             int ev = 0;
@@ -348,12 +351,11 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                     if (a.trace_a) a.trace_a[(size_t)g * p.S + ev] = la;
                     if (a.trace_d) a.trace_d[(size_t)g * p.S + ev] = depth;
                 }
-                w.num_nodes = nn + 1; ++ev;
+                wg_set(w.num_nodes, nn + 1); ++ev;
                 __syncwarp();
                 backup<MZ, F32>(p, w, path, pr, depth, nn, nmir, e0_value(h, a.e0.dense), MZ ? e0_reward(h, a.e0.dense) : 0.0, reps, lane);
                 survivor_visit(w, depth, pr.node, nn, la, reps, lane);
-                w.sim_count += reps;
-                __syncwarp();
+                { const int sc = w.sim_count; wg_set(w.sim_count, sc + reps); }
                 if (halving_ready(p, w)) sequential_halving<MZ, F32>(p, w, lane);
             }
             wg_store_search(p, lane, w);
@@ -381,7 +383,7 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
             if (a.out_policy) pol = a.out_policy + (size_t)g * p.A;
             if (a.out_visits) vis = a.out_visits + (size_t)g * p.A;
         }
-        { WG t = w; finalize_root<NC, MZ, F32>(p, t, lane, pol, vis, s_nvis[wi], table, value, action); }
+        finalize_root<NC, MZ, F32>(p, w, lane, pol, vis, s_nvis[wi], table, value, action);
         if (!a.do_step) {
             if (lane == 0) { if (a.out_value) a.out_value[g] = value; if (a.out_action) a.out_action[g] = action; }
         } else if (action < 0) {

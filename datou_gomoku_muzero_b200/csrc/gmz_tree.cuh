@@ -4,17 +4,24 @@
 #pragma once
 #include "gmz_common.cuh"
 
-// Register-resident view of one game ("U" = warp-uniform, "L" = one element per lane).
-struct WG {
-    int g;                 // U
-    size_t nbase;          // U  g * S : index of this game's node 0 in the per-node arrays
+// View of the game a warp is searching, IN SHARED MEMORY (one per warp).  "U" = warp-uniform field: every lane
+// stores the same value; "L" = one element per lane.  It used to be a register struct; at 72 registers most of it
+// was spilled, and a third of those local-memory reloads missed the L1 (67 MB of stack for 4096 warps) -- in
+// shared memory the same accesses cost an LDS.  The select loop keeps what it needs (nbase, mn, rden) in registers.
+struct __align__(16) WG {
     double mm_min, mm_max; // U  MinMaxStats
+    size_t nbase;          // U  g * S : index of this game's node 0 in the per-node arrays
+    int g;                 // U
     int sim_count, num_nodes, phase, next_thr, n_surv, n_init, to_move, last_move, active;  // U
-    unsigned vb;           // L  valid bits of this lane's actions (bit 4*j + t)
-    int s_act, s_child, s_n;  // L  lane i < n_init: survivor i
+    unsigned vb[32];       // L  valid bits of this lane's actions (bit 4*j + t)
+    int s_act[32], s_child[32], s_n[32];  // L  lane i < n_init: survivor i
     // (the survivors' gumbel noise / root logits and the valid bitboard stay in GState: they are only
-    //  needed at the <= 5 halvings and at the decision, and registers decide the occupancy here)
+    //  needed at the <= 5 halvings and at the decision)
 };
+// A uniform field must not be read by one lane after another lane already stored its update: read (before the
+// call), wait for every lane, store, make the store visible.
+template <typename T>
+__device__ __forceinline__ void wg_set(T &field, T value) { __syncwarp(); field = value; __syncwarp(); }
 
 __device__ __forceinline__ void wg_load(const Params &p, int g, int lane, WG &w)
 {
@@ -24,7 +31,8 @@ __device__ __forceinline__ void wg_load(const Params &p, int g, int lane, WG &w)
     w.sim_count = s->sim_count; w.num_nodes = s->num_nodes; w.phase = s->phase; w.next_thr = s->next_thr;
     w.n_surv = s->n_surv; w.n_init = s->n_init; w.to_move = s->to_move; w.last_move = s->last_move;
     w.active = s->active;
-    w.s_act = s->surv_act[lane]; w.s_child = s->surv_child[lane]; w.s_n = s->surv_n[lane];
+    w.s_act[lane] = s->surv_act[lane]; w.s_child[lane] = s->surv_child[lane]; w.s_n[lane] = s->surv_n[lane];
+    __syncwarp();
 }
 template <int NC>
 __device__ __forceinline__ void wg_valid_bits(const Params &p, WG &w, int lane)
@@ -36,7 +44,7 @@ __device__ __forceinline__ void wg_valid_bits(const Params &p, WG &w, int lane)
         u64 word = shfl_u64(V, 2 * j + (lane >> 4));
         vb |= (unsigned)((word >> ((lane & 15) * 4)) & 0xFull) << (4 * j);
     }
-    w.vb = vb;
+    w.vb[lane] = vb;
 }
 __device__ __forceinline__ void wg_store_search(const Params &p, int lane, const WG &w)
 {
@@ -46,7 +54,7 @@ __device__ __forceinline__ void wg_store_search(const Params &p, int lane, const
         s->sim_count = w.sim_count; s->num_nodes = w.num_nodes; s->phase = w.phase; s->next_thr = w.next_thr;
         s->n_surv = w.n_surv; s->n_init = w.n_init;
     }
-    s->surv_act[lane] = (short)w.s_act; s->surv_child[lane] = (short)w.s_child; s->surv_n[lane] = w.s_n;
+    s->surv_act[lane] = (short)w.s_act[lane]; s->surv_child[lane] = (short)w.s_child[lane]; s->surv_n[lane] = w.s_n[lane];
 }
 
 // GomokuGame.do_move on the lane-distributed bitboards (game.py:20-23): the stone OVERWRITES
@@ -154,8 +162,9 @@ __device__ __forceinline__ void row_load(const Params &p, const WG &w, int node,
 // softmax over the root-valid actions of logits + sigma(q) (mcts.py:141-156): on return
 // x[i] = exp(logit + sigma - max) (0 for invalid actions) and the return value is 1/sum.
 template <int NC, bool F32>
-__device__ __forceinline__ double row_softmax(const Params &p, const WG &w, const Row<NC> &r, double *x)
+__device__ __forceinline__ double row_softmax(const Params &p, const WG &w, const Row<NC> &r, double *x, int lane)
 {
+    const unsigned wvb = w.vb[lane];
     const double scale = __dmul_rn(__dadd_rn(p.c_visit, (double)r.maxN), p.c_scale);
     const bool rng = w.mm_max > w.mm_min;
     const double denom = mm_denom<F32>(p, w.mm_min, w.mm_max);
@@ -163,7 +172,7 @@ __device__ __forceinline__ double row_softmax(const Params &p, const WG &w, cons
     double lmx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 4 * NC; ++i) {
-        if ((w.vb >> i) & 1u) {
+        if ((wvb >> i) & 1u) {
             const double sig = r.ch[i] >= 0 ? __dmul_rn(scale, mm_norm(r.q[i], rng, w.mm_min, denom)) : sig0;
             x[i] = __dadd_rn((double)r.lg[i], sig);
             lmx = dmax2(lmx, x[i]);
@@ -173,7 +182,7 @@ __device__ __forceinline__ double row_softmax(const Params &p, const WG &w, cons
     double ls = 0.0;
 #pragma unroll
     for (int i = 0; i < 4 * NC; ++i) {
-        x[i] = ((w.vb >> i) & 1u) ? exp(__dsub_rn(x[i], mx)) : 0.0;
+        x[i] = ((wvb >> i) & 1u) ? exp(__dsub_rn(x[i], mx)) : 0.0;
         ls = __dadd_rn(ls, x[i]);
     }
     const double sum = warp_sum_f64(ls);
@@ -212,7 +221,7 @@ __device__ __forceinline__ SelPtr sel_global(const Params &p, int warp_slot)
 // What the out-of-line exact select needs of the game, passed BY VALUE: a reference to the caller's WG
 // would pin the whole register-resident game view in local memory.
 struct SelCtx { size_t nbase; double mm_min, mm_max; unsigned vb; };
-__device__ __forceinline__ SelCtx sel_ctx(const WG &w) { SelCtx c; c.nbase = w.nbase; c.mm_min = w.mm_min; c.mm_max = w.mm_max; c.vb = w.vb; return c; }
+__device__ __forceinline__ SelCtx sel_ctx(const WG &w, int lane) { SelCtx c; c.nbase = w.nbase; c.mm_min = w.mm_min; c.mm_max = w.mm_max; c.vb = w.vb[lane]; return c; }
 __device__ __forceinline__ int sel_pack(int action, int child) { return (action << 16) | (child & 0xffff); }
 __device__ __forceinline__ void sel_unpack(int packed, int &action, int &child)
 {
@@ -578,7 +587,7 @@ template <int NC>
 __device__ __forceinline__ void node_init_hdr(const Params &p, const WG &w, int node, const float *lg, int lane)
 {
     int ub; float lub, U; bool amb;
-    unvisited_summary<NC, false>(lg, w.vb, lane, ub, lub, U, amb);
+    unvisited_summary<NC, false>(lg, w.vb[lane], lane, ub, lub, U, amb);
     if (lane == 0) *reinterpret_cast<int4 *>(blk_of(p, w.nbase + (size_t)node)) = hdr_pack(U, lub, ub, 0, amb ? 1 : 0);
 }
 
@@ -622,7 +631,7 @@ __device__ __forceinline__ int node_link(const Params &p, const WG &w, int paren
         if (slot) *reinterpret_cast<int2 *>(blk + kSlotBytes * slot) = make_int2((action << 16) | new_node, __float_as_int(la));
     }
     int ub; float lub, U; bool amb;
-    unvisited_summary<NC, true>(lg, w.vb & ~vm, lane, ub, lub, U, amb);
+    unvisited_summary<NC, true>(lg, w.vb[lane] & ~vm, lane, ub, lub, U, amb);
     if (lane == 0) *reinterpret_cast<int4 *>(blk) = hdr_pack(U, lub, ub, min(nvis, 32767), (amb || nvis > kFastMaxVisited) ? 1 : 0);
     return (parent << 5) | slot;
 }
@@ -640,10 +649,10 @@ __device__ __forceinline__ void slot_load(const char *slot, int4 &e, double &W, 
 // Returns the chosen action, the child it leads to (-1 = not created yet) and -- for an existing child --
 // its slot in this node's block (0 = not mirrored) and its statistics N / W / reward as of now.
 template <int NC, bool MZ, bool F32>
-__device__ __forceinline__ void select_interior(const Params &p, const WG &w, int node, int lane, SelSmem &sm, int warp_slot,
+__device__ __forceinline__ void select_interior(const Params &p, const WG &w, size_t nbase, int node, int lane, SelSmem &sm, int warp_slot,
                                                 double mn, double rden, int &action, int &child, int &slot, int &cn, double &cW, double &cR)
 {
-    const size_t ni = w.nbase + (size_t)node;
+    const size_t ni = nbase + (size_t)node;
     const char *blk = blk_of(p, ni);
     const char *mine = blk + kSlotBytes * lane;
     const int4 h = *reinterpret_cast<const int4 *>(blk);
@@ -713,7 +722,7 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
             cR = MZ ? __shfl_sync(GMZ_FULL, rew, bl) : 0.0;
 #ifdef GMZ_VERIFY_FAST
             int ea, ec;
-            sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w), node, lane, sm, warp_slot), ea, ec);
+            sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w, lane), node, lane, sm, warp_slot), ea, ec);
             if (lane == 0) atomicAdd(&p.ctl->sel_fast, 1ull);
             if (ea == action && ec == child) return;
             if (lane == 0) atomicAdd(&p.ctl->sel_mismatch, 1ull);
@@ -723,9 +732,9 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
 #endif
         } else {
             if (lane == 0) atomicAdd(&p.ctl->sel_fallback, 1ull);
-            sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w), node, lane, sm, warp_slot), action, child);
+            sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w, lane), node, lane, sm, warp_slot), action, child);
         }
-    } else sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w), node, lane, sm, warp_slot), action, child);
+    } else sel_unpack(select_interior_exact<NC, MZ, F32>(p, sel_ctx(w, lane), node, lane, sm, warp_slot), action, child);
     // the exact path decided: find the child among the mirrored slots (or read its own arrays)
     slot = 0; cn = 0; cW = 0.0; cR = 0.0;
     if (child >= 0) {
@@ -737,7 +746,7 @@ __device__ __forceinline__ void select_interior(const Params &p, const WG &w, in
             cn = __shfl_sync(GMZ_FULL, e.z, slot); cW = __shfl_sync(GMZ_FULL, eW, slot);
             cR = MZ ? __shfl_sync(GMZ_FULL, eR, slot) : 0.0;
         } else {
-            const size_t ci = w.nbase + (size_t)child;
+            const size_t ci = nbase + (size_t)child;
             cn = p.nN[ci]; cW = p.nW[ci]; cR = MZ ? p.nR[ci] : 0.0;
         }
     }
@@ -751,10 +760,11 @@ template <int NC, bool MZ, bool F32>
 __device__ __forceinline__ int descend(const Params &p, const WG &w, int2 *path, DescSmem &ds, SelSmem &sc, int warp_slot, int lane,
                                        int &leaf_parent, int &leaf_action, int &colour)
 {
-    const unsigned key = lane < w.n_surv ? (((unsigned)w.s_n << 5) | (unsigned)lane) : 0xffffffffu;
+    const unsigned key = lane < w.n_surv ? (((unsigned)w.s_n[lane] << 5) | (unsigned)lane) : 0xffffffffu;
     const int bl = (int)(__reduce_min_sync(GMZ_FULL, key) & 31u);
-    int a = __shfl_sync(GMZ_FULL, w.s_act, bl);
-    int node = __shfl_sync(GMZ_FULL, w.s_child, bl);
+    int a = w.s_act[bl];
+    int node = w.s_child[bl];
+    const size_t nbase = w.nbase;
     int cn = 0, slot = 0;
     double cW = 0.0, cR = 0.0;
     // (the root and the chosen root child get their statistics from path_load() after the descent: only the
@@ -776,7 +786,7 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, int2 *path,
             if (lane == 0) { PathEntry e; e.node = node; e.mir = mir; e.n = cn; e.pad = 0; e.W = cW; e.R = cR; ds.path[depth] = e; }
         } else if (lane == 0) path[depth] = make_int2(node, mir);
         int c;
-        select_interior<NC, MZ, F32>(p, w, node, lane, sc, warp_slot, mn, rden, a, c, slot, cn, cW, cR);
+        select_interior<NC, MZ, F32>(p, w, nbase, node, lane, sc, warp_slot, mn, rden, a, c, slot, cn, cW, cR);
         if (!MZ) { bb_do_move_smem(ds, colour, a, lane); colour = -colour; }
         parent = node; node = c; ++depth;
     }
@@ -892,17 +902,23 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const int2 *path,
     }
     if (__any_sync(GMZ_FULL, qmin < w.mm_min || qmax > w.mm_max)) {      // rare once the range has settled
         qmin = warp_min_f64(qmin); qmax = warp_max_f64(qmax);
-        w.mm_min = dmin2(w.mm_min, qmin); w.mm_max = dmax2(w.mm_max, qmax);
+        const double nmin = dmin2(w.mm_min, qmin), nmax = dmax2(w.mm_max, qmax);
+        __syncwarp();
+        w.mm_min = nmin; w.mm_max = nmax;
+        __syncwarp();
     }
 }
 
 // _ready_for_next_gumbel_phase (mcts.py:166-181), tables precomputed on the host.
 __device__ __forceinline__ bool halving_ready(const Params &p, WG &w)
 {
-    if (w.sim_count < w.next_thr) return false;
-    w.phase += 1;
-    if (w.phase > p.n_phases) { w.phase = p.n_phases + 1; return false; }   // current_num_top_actions < 1
-    w.next_thr = min(w.next_thr + p.extra_of_phase[w.phase], p.S);
+    const int thr = w.next_thr;
+    if (w.sim_count < thr) return false;
+    const int ph = w.phase + 1;
+    if (ph > p.n_phases) { wg_set(w.phase, p.n_phases + 1); return false; }   // current_num_top_actions < 1
+    __syncwarp();
+    w.phase = ph; w.next_thr = min(thr + p.extra_of_phase[ph], p.S);
+    __syncwarp();
     return true;
 }
 
@@ -913,9 +929,9 @@ __device__ __forceinline__ void sequential_halving(const Params &p, WG &w, int l
 {
     const bool mine = lane < w.n_init;
     double q = 0.0;
-    const int n = mine ? w.s_n : 0;
-    if (mine && w.s_child >= 0) {
-        const size_t ci = w.nbase + (size_t)w.s_child;
+    const int n = mine ? w.s_n[lane] : 0;
+    if (mine && w.s_child[lane] >= 0) {
+        const size_t ci = w.nbase + (size_t)w.s_child[lane];
         q = q_of<F32>(p, p.nW[ci], n, MZ ? p.nR[ci] : 0.0);
     }
     const int maxN = __reduce_max_sync(GMZ_FULL, n);
@@ -937,13 +953,16 @@ __device__ __forceinline__ void sequential_halving(const Params &p, WG &w, int l
         const int rj = __shfl_sync(GMZ_FULL, rank, j);
         if (rj == lane) src = j;
     }
-    w.s_act = __shfl_sync(GMZ_FULL, w.s_act, src);
-    w.s_child = __shfl_sync(GMZ_FULL, w.s_child, src);
-    w.s_n = __shfl_sync(GMZ_FULL, w.s_n, src);
+    {
+        const int na = w.s_act[src], nc = w.s_child[src], nn = w.s_n[src];
+        __syncwarp();
+        w.s_act[lane] = na; w.s_child[lane] = nc; w.s_n[lane] = nn;
+        __syncwarp();
+    }
     s_g = __shfl_sync(GMZ_FULL, s_g, src);
     s_logit = __shfl_sync(GMZ_FULL, s_logit, src);
     gs->surv_g[lane] = s_g; gs->surv_logit[lane] = s_logit;
-    w.n_surv = min(p.m_of_phase[w.phase], w.n_surv);
+    wg_set(w.n_surv, min(p.m_of_phase[w.phase], w.n_surv));
 }
 
 // After a backup through root child `first_node` (depth-1 node on the path): bump the
@@ -952,9 +971,10 @@ __device__ __forceinline__ void survivor_visit(WG &w, int depth, int path_node, 
 {
     const int first = __shfl_sync(GMZ_FULL, path_node, 1);     // every lane takes part: no shuffle behind a short-circuit
     bool hit;
-    if (depth == 1) hit = lane < w.n_surv && w.s_act == leaf_action;
-    else hit = lane < w.n_surv && w.s_child == first;
-    if (hit) { w.s_n += reps; if (depth == 1) w.s_child = new_node; }
+    if (depth == 1) hit = lane < w.n_surv && w.s_act[lane] == leaf_action;
+    else hit = lane < w.n_surv && w.s_child[lane] == first;
+    if (hit) { w.s_n[lane] += reps; if (depth == 1) w.s_child[lane] = new_node; }
+    __syncwarp();
 }
 
 // Root initialisation (mcts.py:217-226): expand root, first backup, halving schedule, Gumbel
@@ -970,10 +990,10 @@ __device__ __forceinline__ void root_init(const Params &p, WG &w, const float *l
     }
     w.num_nodes = 1; w.sim_count = 1; w.phase = 0; w.next_thr = p.first_thr;
     double sc[4 * NC];
-    unsigned rem = w.vb;
+    unsigned rem = w.vb[lane];
 #pragma unroll
     for (int i = 0; i < 4 * NC; ++i) sc[i] = __dadd_rn(gum[i], (double)lg[i]);
-    w.s_act = -1; w.s_child = -1; w.s_n = 0;
+    w.s_act[lane] = -1; w.s_child[lane] = -1; w.s_n[lane] = 0;
     GState *gs = p.gs + w.g;
     gs->surv_g[lane] = 0.0; gs->surv_logit[lane] = 0.f;
     __syncwarp();
@@ -999,10 +1019,11 @@ __device__ __forceinline__ void root_init(const Params &p, WG &w, const float *l
                 if (128 * (i >> 2) + 4 * lane + (i & 3) == ba) { gsel = gum[i]; lsel = lg[i]; rem &= ~(1u << i); }
         }
         gsel = __shfl_sync(GMZ_FULL, gsel, owner); lsel = __shfl_sync(GMZ_FULL, lsel, owner);
-        if (lane == r) { w.s_act = ba; gs->surv_g[r] = gsel; gs->surv_logit[r] = lsel; }
+        if (lane == r) { w.s_act[lane] = ba; gs->surv_g[r] = gsel; gs->surv_logit[r] = lsel; }
         ++cnt;
     }
     w.n_init = cnt; w.n_surv = cnt;
+    __syncwarp();
 }
 
 // The same planes as bf16 in NHWC order ([cell][own, opp, last]): what the network's first convolution reads
