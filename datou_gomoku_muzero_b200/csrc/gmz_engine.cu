@@ -197,14 +197,15 @@ k_select(const __grid_constant__ Params p, T *leaf_obs, int32_t *out_a, int32_t 
     __shared__ DescSmem s_desc[WARPS_PER_CTA];
     DescSmem &ds = s_desc[threadIdx.x >> 5];
     int2 *path = p.path + (size_t)g * (p.S + 2);
-    int colour, lp, la;
+    int lp, la;
     const int depth = descend<NC, MZ, F32>(p, w, path, ds, s_sel[threadIdx.x >> 5], blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane,
-                                      lp, la, colour);
-    if (lane < min(depth, 32)) path[lane] = lane == 0 ? make_int2(0, 0) : make_int2(ds.path[lane].node, ds.path[lane].mir);   // for k_expand_backup
-    if (!MZ && leaf_obs) { // colour is now the player to move at the leaf; last move = la
-        const u64 P = lane < GMZ_WORDS ? ds.P[lane] : 0ull, M = lane < GMZ_WORDS ? ds.M[lane] : 0ull;
+                                      lp, la);
+    if (!MZ && leaf_obs) { // the replayed position; colour = the player to move at the leaf; last move = la
+        u64 P, M;
+        const int colour = replay_path(p, w, path, ds, depth, la, lane, P, M);
         obs_emit<NC, T>(leaf_obs + (size_t)g * 3 * p.A, p.A, colour > 0 ? P : M, colour > 0 ? M : P, la, lane);
     }
+    if (lane < min(depth, 32)) path[lane] = lane == 0 ? make_int2(0, 0) : make_int2(ds.path[lane].node, ds.path[lane].mir);   // for k_expand_backup
     if (lane == 0) {
         GState *s = p.gs + g;
         s->leaf_parent = lp; s->leaf_action = la; s->leaf_depth = depth; s->leaf_reps = MZ ? w.n_surv : 1;

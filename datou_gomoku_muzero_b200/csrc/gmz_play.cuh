@@ -312,17 +312,19 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
             __syncwarp();
             int ev = 0;
             while (w.sim_count < p.S) {
-                int colour, lp, la;
+                int lp, la;
                 DescSmem &ds = s_desc[wi];
-                const int depth = descend<NC, MZ, F32>(p, w, path, ds, s_sel[wi], warp_slot, lane, lp, la, colour);
+                const int depth = descend<NC, MZ, F32>(p, w, path, ds, s_sel[wi], warp_slot, lane, lp, la);
                 PathReg pr;
                 path_load<MZ>(p, w, ds, depth, pr, lane);
                 prefetch_parent_rows<NC>(p, w, lp, lane);
+                u64 P = 0, M = 0;
+                int colour = 0;
+                if (!MZ) colour = replay_path(p, w, path, ds, depth, la, lane, P, M);
                 // AlphaZero mode: evaluate the replayed board (mcts.py:251-253).  MuZero mode: the learned
                 // dynamics, here E0's recurrent half on the parent's hidden state (mcts.py:336-343).
                 const u64 h = MZ ? e0_child_hidden(p.nH[w.nbase + (size_t)lp], la)
-                                 : e0_hash_planes(a.e0.h0, lane < GMZ_WORDS ? (colour > 0 ? ds.P[lane] : ds.M[lane]) : 0ull,
-                                                  lane < GMZ_WORDS ? (colour > 0 ? ds.M[lane] : ds.P[lane]) : 0ull, p.NW, la, lane);
+                                 : e0_hash_planes(a.e0.h0, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la, lane);
                 const int reps = MZ ? w.n_surv : 1;            // MuZero: len(selected) identical selections -> that many backups
                 const int nn = w.num_nodes;
                 {   // evaluate + leaf.expand fused: logits go straight into the new node's row
