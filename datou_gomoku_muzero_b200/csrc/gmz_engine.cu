@@ -251,8 +251,9 @@ k_expand_backup(const __grid_constant__ Params p, const float *logits, const voi
     }
     backup<MZ, F32>(p, w, path, pr, depth, nn, nmir, value, reward, reps, lane);
     survivor_visit(w, depth, pr.node, nn, la, reps, lane);
-    { const int sc = w.sim_count; wg_set(w.sim_count, sc + reps); }
-    if (halving_ready(p, w)) sequential_halving<MZ, F32>(p, w, lane);
+    const int sc = w.sim_count + reps;
+    wg_set(w.sim_count, sc);
+    if (halving_ready(p, w, sc)) sequential_halving<MZ, F32>(p, w, lane);
     wg_store_search(p, lane, w);
     if (lane == 0) p.gs[g].leaf_depth = 0;
 }

@@ -357,8 +357,9 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                 __syncwarp();
                 backup<MZ, F32>(p, w, path, pr, depth, nn, nmir, e0_value(h, a.e0.dense), MZ ? e0_reward(h, a.e0.dense) : 0.0, reps, lane);
                 survivor_visit(w, depth, pr.node, nn, la, reps, lane);
-                { const int sc = w.sim_count; wg_set(w.sim_count, sc + reps); }
-                if (halving_ready(p, w)) sequential_halving<MZ, F32>(p, w, lane);
+                const int sc = w.sim_count + reps;
+                wg_set(w.sim_count, sc);
+                if (halving_ready(p, w, sc)) sequential_halving<MZ, F32>(p, w, lane);
             }
             wg_store_search(p, lane, w);
             __syncwarp();

@@ -13,6 +13,7 @@ struct __align__(16) WG {
     size_t nbase;          // U  g * S : index of this game's node 0 in the per-node arrays
     int g;                 // U
     int sim_count, num_nodes, phase, next_thr, n_surv, n_init, to_move, last_move, active;  // U
+    u64 rP[GMZ_WORDS], rM[GMZ_WORDS];   // the root's +1 / -1 bitboards (word w at index w): every replay starts from them
     unsigned vb[32];       // L  valid bits of this lane's actions (bit 4*j + t)
     int s_act[32], s_child[32], s_n[32];  // L  lane i < n_init: survivor i
     // (the survivors' gumbel noise / root logits and the valid bitboard stay in GState: they are only
@@ -32,6 +33,7 @@ __device__ __forceinline__ void wg_load(const Params &p, int g, int lane, WG &w)
     w.n_surv = s->n_surv; w.n_init = s->n_init; w.to_move = s->to_move; w.last_move = s->last_move;
     w.active = s->active;
     w.s_act[lane] = s->surv_act[lane]; w.s_child[lane] = s->surv_child[lane]; w.s_n[lane] = s->surv_n[lane];
+    if (lane < GMZ_WORDS) { w.rP[lane] = s->p1[lane]; w.rM[lane] = s->m1[lane]; }
     __syncwarp();
 }
 template <int NC>
@@ -793,9 +795,8 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, int2 *path,
 __device__ __forceinline__ int replay_path(const Params &p, const WG &w, const int2 *path, const DescSmem &ds, int depth, int leaf_action,
                                            int lane, u64 &P, u64 &M)
 {
-    const GState *s = p.gs + w.g;
-    P = lane < GMZ_WORDS ? s->p1[lane] : 0ull;
-    M = lane < GMZ_WORDS ? s->m1[lane] : 0ull;
+    P = lane < GMZ_WORDS ? w.rP[lane] : 0ull;
+    M = lane < GMZ_WORDS ? w.rM[lane] : 0ull;
     int colour = w.to_move;
     for (int d = 1; d < depth; ++d) {
         const int a = d < 32 ? ds.path[d].act : (path[d].y >> 20);
@@ -927,10 +928,10 @@ __device__ __forceinline__ void backup(const Params &p, WG &w, const int2 *path,
 }
 
 // _ready_for_next_gumbel_phase (mcts.py:166-181), tables precomputed on the host.
-__device__ __forceinline__ bool halving_ready(const Params &p, WG &w)
+__device__ __forceinline__ bool halving_ready(const Params &p, WG &w, int sim_count)
 {
     const int thr = w.next_thr;
-    if (w.sim_count < thr) return false;
+    if (sim_count < thr) return false;
     const int ph = w.phase + 1;
     if (ph > p.n_phases) { wg_set(w.phase, p.n_phases + 1); return false; }   // current_num_top_actions < 1
     __syncwarp();
