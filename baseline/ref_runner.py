@@ -6,11 +6,13 @@ imported and called; the only additions are (a) the config overrides the benchma
 imported (game.py binds its defaults at import), and (b) the fixed evaluator E0 behind the reference's own
 queue protocol (tests/golden/e0_py.E0Queue, the same object that produced the golden vectors).
 
-Three measurements:
+Measurements:
   tree_only()  -- P processes, each running reference `search(game)` with E0 in-process: the reference's tree
                   code with a free evaluator, the counterpart of the GPU engine's E0 numbers;
   topology()   -- the reference's production topology (main.py:91-104): `universal_worker` x W processes
                   + one `inference_server_worker` running GomokuNetEZ on the GPU, mp.Queue IPC per simulation;
+  inprocess_net() -- BASELINE.md section 4.1 (E1): ONE reference process playing games with the reference's
+                  GomokuNetEZ on the GPU answering its queue protocol synchronously in-process (no IPC);
   per()        -- reference InMemoryReplayBuffer.sample + update_priorities on one core.
 """
 from __future__ import annotations
@@ -224,6 +226,88 @@ def topology(seconds=60.0, n_workers=None, N=15, S=400, K=16, mode="AlphaZero"):
         os.chdir(cwd)
         import shutil
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# one reference process, network on the GPU answered in-process
+# ---------------------------------------------------------------------------------------------------------
+class _InProcessNet:
+    """The evaluator protocol of mcts.py:66-82 answered synchronously by a model in this process (the role
+    webui.py:107-141 plays for the UI): put() runs the network, get() hands the result back."""
+
+    def __init__(self, model, device):
+        self.model, self.device, self.pending, self.calls = model, device, None, 0
+
+    def put(self, request):
+        import torch
+        _worker, kind, payload = request
+        self.calls += 1
+        with torch.no_grad():
+            if kind == "initial":
+                p, v, h = self.model.initial_inference(torch.from_numpy(payload)[None].to(self.device))
+                self.pending = (p[0].cpu().numpy(), v[0, 0].cpu().numpy(), h.cpu().numpy())
+            else:
+                hidden, actions = payload
+                out = self.model.recurrent_inference(torch.from_numpy(hidden).to(self.device),
+                                                     torch.from_numpy(actions).long().to(self.device))
+                self.pending = tuple(t.cpu().numpy() for t in out)
+
+    def get(self, timeout=None):
+        import queue
+        if self.pending is None:
+            raise queue.Empty
+        out, self.pending = self.pending, None
+        return out
+
+    get_nowait = get
+
+
+def _inprocess_entry(N, S, K, mode, seconds, out_q):
+    try:
+        cfg = _configure(N, 5, S, K, mode)
+        import torch
+        import game as ref_game
+        import mcts as ref_mcts
+        from network import GomokuNetEZ
+        dev = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        cfg.DEVICE = dev
+        torch.manual_seed(0)
+        q = _InProcessNet(GomokuNetEZ(cfg).to(dev).eval(), dev)
+        eng = (ref_mcts.AlphaZeroMCTS if mode == "AlphaZero" else ref_mcts.MuZeroMCTS)(0, q, q)
+        np.random.seed(0)
+        gm = ref_game.GomokuGame(board_size=N, n_in_row=5)
+        eng.search(gm)                                        # warm-up: CUDA context, cuDNN plans
+        moves = games = 0
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            _, _, action = eng.search(gm)
+            assert action >= 0
+            gm.do_move(action); moves += 1
+            if gm.get_game_ended() is not None:
+                gm.reset(); games += 1
+        dt = time.perf_counter() - t0
+        out_q.put({"seconds": dt, "moves": moves, "games_finished": games, "moves_per_sec": moves / dt, "sims_per_sec": moves * S / dt,
+                   "evaluator_calls": q.calls, "device": str(dev),
+                   "what": "ONE reference process: %sMCTS.search + GomokuGame loop, %dx%d / %d sims, reference GomokuNetEZ (fp32, "
+                           "random init) on the %s answering the queue protocol in-process (no IPC)" % (mode, N, N, S, dev.type)})
+    except Exception as ex:
+        out_q.put({"error": repr(ex)})
+
+
+def inprocess_net(seconds=10.0, N=9, S=100, K=16, mode="AlphaZero"):
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    p = ctx.Process(target=_inprocess_entry, args=(N, S, K, mode, seconds, out_q), daemon=True)
+    p.start()
+    try:
+        res = out_q.get(timeout=seconds + 600)
+    finally:
+        p.join(timeout=30)
+        if p.is_alive():
+            p.terminate()
+    if "error" in res:
+        raise RuntimeError("reference in-process run failed: " + res["error"])
+    return res
 
 
 def per(capacity=1_000_000, batch=360, rounds=200, seed=0):

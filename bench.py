@@ -217,6 +217,23 @@ def run_reference(args):
                                                              N=N, S=S, K=K_TOP)
         except Exception as ex:
             line["reference_topology"] = {"error": repr(ex)[:300]}
+        # config 1 with the reference's network answering in-process, and the
+        # MuZero-mode counterparts (tree only with E0 on every host thread; the production topology for half the time)
+        extras = {
+            "config1_net": lambda: ref_runner.inprocess_net(seconds=8.0, N=9, S=100, K=K_TOP, mode="AlphaZero"),
+            "config1_net_muzero": lambda: ref_runner.inprocess_net(seconds=8.0, N=9, S=100, K=K_TOP, mode="MuZero"),
+            "muzero_tree_only": lambda: dict(ref_runner.tree_only(threads, 3, warmup=1, N=N, S=S, K=K_TOP, mode="MuZero", e0_seed=E0_SEED,
+                                                                  logit_div=LOGIT_DIV),
+                                             what="unmodified reference MuZeroMCTS.search, 15x15 / 400 sims, E0 behind its queue protocol "
+                                                  "in-process, one process per host thread"),
+            "reference_topology_muzero": lambda: ref_runner.topology(seconds=args.ref_topology_seconds / 2, n_workers=max(1, threads - 2),
+                                                                     N=N, S=S, K=K_TOP, mode="MuZero"),
+        }
+        for name, fn in extras.items():
+            try:
+                line[name] = fn()
+            except Exception as ex:
+                line[name] = {"error": repr(ex)[:300]}
     print(json.dumps(line))
 
 
@@ -323,14 +340,41 @@ def net_leg(eng, dev, peaks, dtype_name="bf16"):
     net_ms = n0.elapsed_time(n1) / 10
     tf = 1.064e9 * G / (net_ms * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    peak_sus = float(peaks.get("bf16_tflops_sustained", peak_tf))
+    selfplay = None
+    if dtype_name == "bf16":
+        # production self-play with the network (universal_worker + inference server, workers.py:129-241, 314-373):
+        # lock-step moves of all G games -- search, decision, trajectory record, do_move, end check, restart --
+        # finished games packed on the device into the replay ring + PER tree
+        from datou_gomoku_muzero_b200.replay_buffer import DeviceReplayBuffer
+        from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+        from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
+        sp = SelfPlayEngine(eng, ns, noise_seed=4244)
+        traj = TrajectoryStore(eng)
+        buf = DeviceReplayBuffer(1 << 16, N, device=dev)
+        n_moves = 2
+        eng.selfplay_e0(G * 40, E0_SEED, LOGIT_DIV, 4244, traj, True)      # untimed: ~40 E0-driven moves per game, so the timed
+        torch.cuda.synchronize()                                           # moves start from mid-game boards, not 4096 empty ones
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(); sp.play(moves_per_game=n_moves, traj=traj, sink=buf.add_packed, chunk=n_moves); s1.record(); torch.cuda.synchronize()
+        sp_ms = s0.elapsed_time(s1)
+        selfplay = {"moves_per_sec": G * n_moves / (sp_ms * 1e-3), "sims_per_sec": G * n_moves * S / (sp_ms * 1e-3),
+                    "moves": G * n_moves, "api": "SelfPlayEngine(engine, NetworkSearch).play(traj=, sink=DeviceReplayBuffer.add_packed)",
+                    "what": "%d lock-step moves of %d games (each ~40 moves into its game): search (%d graph replays), decision, "
+                            "trajectory record, do_move, end check, pack of finished games into the replay ring" % (n_moves, G, S - 1)}
+        del traj, buf
     return {"evaluator": "GomokuNetEZ 8x128 %s (random init, BN folded, cuDNN fused conv+bias+relu); one CUDA graph per simulation "
                          "step {select -> network -> expand/backup}" % dtype_name,
             "accum_dtype": eng.accum_dtype,
             "sims_per_sec": G * S / (ms * 1e-3), "moves_per_sec": G / (ms * 1e-3), "ms_per_search": ms,
             "net_forward_ms": net_ms, "tree_kernels_ms_per_sim_step": tree_ms,
             "step_minus_standalone_forward_ms": ms / S - net_ms,
+            **({"selfplay": selfplay} if selfplay else {}),
             "tensor": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                       "flop_per_eval": 1.064e9, "note": "algorithmic conv FLOPs (SURVEY 8d) / measured cuBLAS bf16 burst peak "
+                       "peak_sustained": peak_sus, "frac_sustained": tf / peak_sus,
+                       "flop_per_eval": 1.064e9, "note": "algorithmic conv FLOPs (SURVEY 8d) / measured cuBLAS bf16 peak: `peak` = burst (a "
+                                                         "kernel timed alone), `peak_sustained` = back-to-back GEMMs for 4 s -- the search is "
+                                                         "400 forwards back to back, so the sustained figure is the one it runs against "
                                                          "(also for the tf32 leg: there is no measured tf32 peak)"}}
 
 
@@ -386,12 +430,27 @@ def muzero_leg(dev, peaks, G):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     tf = (1.141e9 * steps + 1.064e9) * G / (ms * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    peak_sus = float(peaks.get("bf16_tflops_sustained", peak_tf))
+    # the same MuZero-mode search with the fixed evaluator, fused in the persistent kernel (E0's recurrent half on the
+    # parent's hidden hash): the counterpart of the reference's MuZero tree-only run (`--impl reference`: muzero_tree_only)
+    eng.set_roots(*staggered_positions(G, 0))
+    eng.search_e0(gum, E0_SEED, LOGIT_DIV)
+    z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    z0.record()
+    for _ in range(3):
+        eng.search_e0(gum, E0_SEED, LOGIT_DIV)
+    z1.record(); torch.cuda.synchronize()
+    e0_ms = z0.elapsed_time(z1) / 3
     return {"workload": "MuZero-mode 15x15, 400 sims/move, %d games, GomokuNetEZ 8x128 bf16 dynamics in the tree "
                         "(BASELINE configs[2])" % G,
             "sims_per_sec": G * S / (ms * 1e-3), "moves_per_sec": G / (ms * 1e-3), "ms_per_search": ms,
             "recurrent_evals_per_search": steps, "distinct_evals_per_sec": G * (steps + 1) / (ms * 1e-3),
             "hidden_pool_gb": mz.pool.numel() * mz.pool.element_size() / 1e9,
-            "tensor": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf},
+            "e0_fused": {"sims_per_sec": G * S / (e0_ms * 1e-3), "ms_per_search": e0_ms,
+                         "what": "same searches with the fixed evaluator E0 inside the persistent kernel (k_play_e0<NC, MZ>)"},
+            "tensor": {"bound": "tensor", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                       "peak_sustained": peak_sus, "frac_sustained": tf / peak_sus},
             "hidden_gather": {"bound": "hbm", "ms": gather_ms, "achieved": gather_bytes / gather_ms / 1e6, "peak": peak,
                               "unit": "GB/s", "frac": gather_bytes / gather_ms / 1e6 / peak, "bytes": gather_bytes},
             "hidden_scatter": {"bound": "hbm", "ms": scatter_ms, "achieved": scatter_bytes / scatter_ms / 1e6, "peak": peak,
@@ -811,7 +870,7 @@ def main():
     ap.add_argument("--no-selfplay-e2e", action="store_true", help="skip the device-side self-play -> replay -> batch leg")
     ap.add_argument("--no-config5", action="store_true", help="skip the PER and re-analysis legs (BASELINE configs[4])")
     ap.add_argument("--reanalysis-positions", type=int, default=1_000_000)
-    ap.add_argument("--ref-topology-seconds", type=float, default=40.0,
+    ap.add_argument("--ref-topology-seconds", type=float, default=60.0,
                     help="--impl reference at N = 1: seconds of the reference's universal_worker + inference_server topology (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

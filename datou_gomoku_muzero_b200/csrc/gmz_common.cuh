@@ -215,24 +215,27 @@ __device__ __forceinline__ u64 shfl_u64(u64 v, int src) { return __shfl_sync(GMZ
 // ---------------------------------------------------------------------------------------------
 // E0, the fixed deterministic evaluator (device twin of tests/golden/e0_py.py):
 //   h0 = mix64(seed ^ GOLD)
-//   h  = mix64( XOR_w [ mix64((own_w ^ h0) + (2w+1) GOLD) ^ mix64((opp_w ^ h0) + (2w+2) GOLD) ] + (last+1) CV )
-//   x_a = 32-bit hash of (lo32(h) ^ hi32(h)) + (a+1) * 0x9E3779B1   (two multiplies, high bits used)
+//   h  = mix64( XOR_w [ ((own_w ^ h0) + (2w+1) GOLD) K1 ^ rot32(((opp_w ^ h0) + (2w+2) GOLD) K2) ] + (last+1) CV )
+//   y = (lo32(h) ^ hi32(h)) + (a+1) * 0x9E3779B1;  x_a = (y ^ (y >> 16)) * 0x7FEB352D   (one multiply, high bits used)
 //   quantised (logit_div > 0): logit = ((x_a >> 26) - 32) / logit_div,  value = ((h >> 40) % 33 - 16) / 16,
 //                              reward = (((h >> 16) & 0xFFFFFF) % 5 - 2) / 16
 //   dense (logit_div = 0):     logit = ((x_a >> 8) - 2^23) 2^-21,  value = ((h >> 40) - 2^23) 2^-23,
 //                              reward = (((h >> 16) & 0xFFFFFF) - 2^23) 2^-25
 //   MuZero mode: h_child = mix64(h_parent + (a+1) CA)
-// The per-word terms are XOR-combined, so lane w hashes word w and a REDUX finishes the board hash: two
-// dependent mix64 per evaluation instead of 2*NW + 2.
+// The per-word terms are XOR-combined, so lane w hashes word w and a REDUX finishes the board hash; a word term is
+// one odd-constant multiply (a bijection of the word), the single mix64 after the REDUX gives the avalanche.
 #define E0_GOLD 0x9E3779B97F4A7C15ULL
 #define E0_CV 0xD1B54A32D192ED03ULL
 #define E0_CA 0x8CB92BA72F3D8DD7ULL
 #define E0_GOLD32 0x9E3779B1u
 
+#define E0_K1 0xBF58476D1CE4E5B9ULL
+#define E0_K2 0x94D049BB133111EBULL
+
 __host__ __device__ __forceinline__ u64 mix64(u64 z)
 {
-    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
-    z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+    z ^= z >> 30; z *= E0_K1;
+    z ^= z >> 27; z *= E0_K2;
     z ^= z >> 31;
     return z;
 }
@@ -263,15 +266,16 @@ __device__ __forceinline__ u64 warp_xor_u64(u64 v)
 __device__ __forceinline__ u64 e0_hash_planes(u64 h0, u64 own_w, u64 opp_w, int nw, int last, int lane)
 {
     u64 t = 0;
-    if (lane < nw)
-        t = mix64((own_w ^ h0) + (u64)(2 * lane + 1) * E0_GOLD) ^ mix64((opp_w ^ h0) + (u64)(2 * lane + 2) * E0_GOLD);
+    if (lane < nw) {
+        const u64 b = ((opp_w ^ h0) + (u64)(2 * lane + 2) * E0_GOLD) * E0_K2;
+        t = (((own_w ^ h0) + (u64)(2 * lane + 1) * E0_GOLD) * E0_K1) ^ ((b << 32) | (b >> 32));
+    }
     return mix64(warp_xor_u64(t) + (u64)(long long)(last + 1) * E0_CV);
 }
 __device__ __forceinline__ unsigned e0_seed32(u64 h) { return (unsigned)h ^ (unsigned)(h >> 32); }
 __device__ __forceinline__ unsigned e0_action_hash(unsigned x)      // x = seed32 + (a + 1) * E0_GOLD32
 {
     x ^= x >> 16; x *= 0x7FEB352Du;
-    x ^= x >> 15; x *= 0x846CA68Bu;
     return x;
 }
 __device__ __forceinline__ float e0_logit_of(unsigned x, const E0Spec &e)

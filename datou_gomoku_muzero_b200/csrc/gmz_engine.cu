@@ -659,7 +659,7 @@ extern "C" int gmz_search_e0(gmz_engine *e, const double *gumbel, uint64_t seed,
 {
     LIVE(e, "gmz_search_e0");
     if (!gumbel) return fail("gmz_search_e0: null argument");
-    if (logit_div < 0) return fail("gmz_search_e0: logit_div must be >= 0 (0 = dense logits)");
+    if (logit_div < 0 || (logit_div & (logit_div - 1))) return fail("gmz_search_e0: logit_div must be 0 (dense logits) or a power of two");
     PlayArgs a; memset(&a, 0, sizeof(a));
     a.e0 = e0_spec((u64)seed, logit_div);
     a.total_tickets = e->p.G; a.do_step = 0; a.gumbel_in = gumbel;
@@ -680,7 +680,7 @@ extern "C" int gmz_selfplay_e0(gmz_engine *e, const gmz_traj *traj, uint64_t eva
 {
     LIVE(e, "gmz_selfplay_e0");
     if (traj && check_traj(e, traj)) return 1;
-    if (logit_div < 0) return fail("gmz_selfplay_e0: logit_div must be >= 0 (0 = dense logits)");
+    if (logit_div < 0 || (logit_div & (logit_div - 1))) return fail("gmz_selfplay_e0: logit_div must be 0 (dense logits) or a power of two");
     if (total_moves <= 0) return 0;
     PlayArgs a; memset(&a, 0, sizeof(a));
     a.e0 = e0_spec((u64)eval_seed, logit_div); a.noise_seed = noise_seed;

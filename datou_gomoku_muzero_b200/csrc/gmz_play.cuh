@@ -330,19 +330,11 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                 {   // evaluate + leaf.expand fused: logits go straight into the new node's row
                     float lg[4 * NC];
                     const unsigned xb = e0_seed32(h) + (unsigned)(4 * lane + 1) * E0_GOLD32;   // seed + (a + 1) * G for this lane's first action
-                    if (a.e0.lmul != 0.0f) {                                 // power-of-two divisor / dense: one multiply
 #pragma unroll
-                        for (int i = 0; i < 4 * NC; ++i) {
-                            const int off = 128 * (i >> 2) + (i & 3);
-                            const unsigned x = e0_action_hash(xb + (unsigned)off * E0_GOLD32);
-                            lg[i] = __fmul_rn((float)((int)(x >> a.e0.lshift) - a.e0.lbias), a.e0.lmul);   // (padding past A: never read, the valid mask covers it)
-                        }
-                    } else {
-#pragma unroll 1
-                        for (int i = 0; i < 4 * NC; ++i) {
-                            const int ac = 128 * (i >> 2) + 4 * lane + (i & 3);
-                            lg[i] = ac < p.A ? e0_logit(h, ac, a.e0) : 0.0f;
-                        }
+                    for (int i = 0; i < 4 * NC; ++i) {                       // (power-of-two divisor / dense: one exact multiply -- the entry points reject other divisors)
+                        const int off = 128 * (i >> 2) + (i & 3);
+                        const unsigned x = e0_action_hash(xb + (unsigned)off * E0_GOLD32);
+                        lg[i] = __fmul_rn((float)((int)(x >> a.e0.lshift) - a.e0.lbias), a.e0.lmul);   // (padding past A: never read, the valid mask covers it)
                     }
                     node_write_row<NC>(p, w, nn, lg, lane);
                     node_init_hdr<NC>(p, w, nn, lg, lane);

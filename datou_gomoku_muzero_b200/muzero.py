@@ -189,7 +189,8 @@ class TorchE0:
     tests/golden/e0_py.py; logit_div = 0 selects the dense (unquantised) heads."""
 
     GOLD, CV, CA = 0x9E3779B97F4A7C15, 0xD1B54A32D192ED03, 0x8CB92BA72F3D8DD7
-    GOLD32, M1, M2 = 0x9E3779B1, 0x7FEB352D, 0x846CA68B
+    K1, K2 = 0xBF58476D1CE4E5B9, 0x94D049BB133111EB
+    GOLD32, M1 = 0x9E3779B1, 0x7FEB352D
 
     def __init__(self, board_size, seed=0, logit_div=16, device="cuda"):
         self.N, self.A = board_size, board_size * board_size
@@ -211,9 +212,9 @@ class TorchE0:
 
     def mix(self, z):
         z = z ^ self._shr(z, 30)
-        z = z * self._s(0xBF58476D1CE4E5B9)
+        z = z * self._s(self.K1)
         z = z ^ self._shr(z, 27)
-        z = z * self._s(0x94D049BB133111EB)
+        z = z * self._s(self.K2)
         return z ^ self._shr(z, 31)
 
     def heads(self, h, with_reward=False):
@@ -222,8 +223,6 @@ class TorchE0:
         x = (s[:, None] + self.a1[None, :]) & m32
         x = x ^ (x >> 16)
         x = (x * self.M1) & m32
-        x = x ^ (x >> 15)
-        x = (x * self.M2) & m32
         vk = self._shr(h, 40) & 0xFFFFFF
         rk = self._shr(h, 16) & 0xFFFFFF
         if self.div > 0:
@@ -250,8 +249,9 @@ class TorchE0:
         last = torch.where(has_last, planes[:, 2].float().argmax(dim=1), torch.full((B,), -1, device=obs.device))
         acc = torch.zeros((B,), dtype=torch.int64, device=obs.device)
         for w in range(nw):
-            acc = acc ^ self.mix((own[:, w] ^ self.h0) + self._s((2 * w + 1) * self.GOLD))
-            acc = acc ^ self.mix((opp[:, w] ^ self.h0) + self._s((2 * w + 2) * self.GOLD))
+            acc = acc ^ (((own[:, w] ^ self.h0) + self._s((2 * w + 1) * self.GOLD)) * self._s(self.K1))
+            b = ((opp[:, w] ^ self.h0) + self._s((2 * w + 2) * self.GOLD)) * self._s(self.K2)
+            acc = acc ^ ((b << 32) | self._shr(b, 32))
         h = self.mix(acc + (last + 1) * self._s(self.CV))
         lg, v = self.heads(h)
         return lg, v, h

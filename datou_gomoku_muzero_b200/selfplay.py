@@ -11,8 +11,10 @@ from .engine import SearchEngine
 
 
 class SelfPlayEngine:
-    """evaluator: "e0" (fixed deterministic evaluator, fused persistent-kernel search), a callable
-    `f(obs f32 [G,3,N,N]) -> (logits f32 [G,A], values f32/f64 [G])` run on the device (stepwise path), or --
+    """evaluator: "e0" (fixed deterministic evaluator, fused persistent-kernel search); a `GomokuNetEZ` module or a
+    `network.NetworkSearch` (the production evaluator of universal_worker, workers.py:129-241: one CUDA graph per
+    simulation step, select -> network -> expand/backup, bf16 NHWC observations written by the select); any callable
+    `f(obs f32 [G,3,N,N]) -> (logits f32 [G,A], values f32/f64 [G])` run on the device (eager stepwise path); or --
     for an engine in MuZero mode -- a pair `(initial_fn, recurrent_fn)` / a `muzero.MuZeroDeviceSearch`
     (learned dynamics in the tree, hidden states in the device pool; MuZeroMCTS.search, mcts.py:288-362)."""
 
@@ -26,8 +28,18 @@ class SelfPlayEngine:
         self.moves_played = 0
         self.games_finished = 0
         self.done_mask = torch.zeros(G, dtype=torch.uint8, device=engine.device)
-        self.mz = None
-        if evaluator != "e0" and engine.mode == "MuZero":
+        self.mz = self.ns = None
+        if not isinstance(evaluator, str) and engine.mode == "AlphaZero":
+            from .network import NetworkSearch
+            if isinstance(evaluator, NetworkSearch):
+                if evaluator.e is not engine:
+                    raise ValueError("the NetworkSearch drives a different engine")
+                self.ns = evaluator
+            elif isinstance(evaluator, torch.nn.Module):
+                self.ns = NetworkSearch(engine, evaluator)
+        elif isinstance(evaluator, str) and evaluator != "e0":
+            raise ValueError(f"unknown evaluator {evaluator!r}")
+        if not isinstance(evaluator, str) and engine.mode == "MuZero":
             from .muzero import MuZeroDeviceSearch
             if isinstance(evaluator, MuZeroDeviceSearch):
                 self.mz = evaluator
@@ -35,6 +47,7 @@ class SelfPlayEngine:
                 self.mz = MuZeroDeviceSearch(engine, evaluator[0], evaluator[1])
             else:
                 raise ValueError("a MuZero-mode engine needs evaluator='e0', (initial_fn, recurrent_fn) or a MuZeroDeviceSearch")
+        self._e0 = isinstance(evaluator, str)
         engine.reset_games()
 
     def search(self, gumbel=None):
@@ -44,8 +57,10 @@ class SelfPlayEngine:
             e.fill_gumbel(self.gumbel, self.noise_seed, self.noise_counter)
             self.noise_counter += self.gumbel.numel()
             gumbel = self.gumbel
-        if self.evaluator == "e0":
+        if self._e0:
             e.search_e0(gumbel, self.seed, self.logit_div)
+        elif self.ns is not None:
+            self.ns.search(gumbel)
         elif self.mz is not None:
             self.mz.search(gumbel)
         else:
@@ -69,20 +84,27 @@ class SelfPlayEngine:
         return winner
 
     def play(self, moves_per_game=1, traj=None, restart=True, sink=None, chunk=None):
-        """Persistent-kernel self-play (fixed evaluator only): G * moves_per_game moves, games advancing
-        independently.  Without `sink` it is ONE launch and the caller harvests finished games from `traj`
+        """Self-play of G * moves_per_game moves.  Fixed evaluator: the persistent kernel, games advancing
+        independently; any other evaluator: `moves_per_game` step() calls (all games move in lock-step, one
+        network batch of G per simulation).  Without `sink` the caller harvests finished games from `traj`
         (games that finish when no trajectory slot is free park until slots are released).  With `sink` -- a
         callable taking a trajectory.PackedGames, e.g. `DeviceReplayBuffer.add_packed` -- the run is cut into
-        launches of `chunk` moves per game (default: what the store's spare slots absorb, at most 48) and after
+        pieces of `chunk` moves per game (default: what the store's spare slots absorb, at most 48) and after
         each one the finished games are packed on the device, handed to the sink and their slots recycled, so a
         run of any length never parks a game."""
-        if self.evaluator != "e0":
-            raise NotImplementedError("the persistent self-play kernel runs the fixed evaluator E0")
         e = self.e
         total = int(moves_per_game)
+
+        def advance(n):
+            if self._e0:
+                e.selfplay_e0(e.G * n, self.seed, self.logit_div, self.noise_seed, traj, restart)
+                self.moves_played += e.G * n
+            else:
+                for _ in range(n):
+                    self.step(restart, traj)
+
         if sink is None or traj is None:
-            e.selfplay_e0(e.G * total, self.seed, self.logit_div, self.noise_seed, traj, restart)
-            self.moves_played += e.G * total
+            advance(total)
             return
         if chunk is None:          # a game ends about every A/3 moves at the earliest in practice; spare slots absorb the finishes
             spare = max(1, traj.n_slots - e.G)
@@ -90,13 +112,12 @@ class SelfPlayEngine:
         done = 0
         while done < total:
             n = min(int(chunk), total - done)
-            e.selfplay_e0(e.G * n, self.seed, self.logit_div, self.noise_seed, traj, restart)
+            advance(n)
             done += n
             packed = traj.pack_finished(recycle=True)
             if packed is not None:
                 sink(packed)
                 self.games_finished += len(packed)
-        self.moves_played += e.G * total
 
     def count_finished(self, winner):
         n = int((winner != 2).sum().item())

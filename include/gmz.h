@@ -129,7 +129,9 @@ int gmz_finalize(gmz_engine *e, double *policy, double *value, int32_t *action, 
  * logits f32 [B,A], values f64 [B] (the device twin of tests/golden/e0_py.py).
  * logit_div > 0: quantised logits (k-32)/logit_div, k in 0..63, values k/16; logit_div = 0: DENSE
  * logits (24 random mantissa bits in [-4, 4)) and values in [-1, 1) -- what a network's outputs look
- * like to the search.  Every value / reward E0 produces is exactly representable in float32. */
+ * like to the search.  Every value / reward E0 produces is exactly representable in float32.
+ * The fused kernels (gmz_search_e0, gmz_selfplay_e0) take logit_div = 0 or a power of two (the logit is then
+ * one exact multiply); gmz_e0_eval_obs takes any logit_div >= 0. */
 int gmz_e0_eval_obs(const float *obs, int batch, int board_size, uint64_t seed, int logit_div,
                     float *logits, double *values, gmz_stream stream);
 /* Whole search (root evaluation + S-1 simulations) in ONE persistent kernel

@@ -53,13 +53,17 @@ typedef struct {
 #define E0_CV 0xD1B54A32D192ED03ULL
 #define E0_CA 0x8CB92BA72F3D8DD7ULL
 
+#define E0_K1 0xBF58476D1CE4E5B9ULL
+#define E0_K2 0x94D049BB133111EBULL
+
 static inline uint64_t mix64(uint64_t z)
 {
-    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
-    z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+    z ^= z >> 30; z *= E0_K1;
+    z ^= z >> 27; z *= E0_K2;
     z ^= z >> 31;
     return z;
 }
+static inline uint64_t rot32(uint64_t z) { return (z << 32) | (z >> 32); }
 
 /* hash of the observation planes game.py:12-17 builds: own / opp / last move.  The per-word terms
  * are combined with XOR, so the words can be hashed in any order (in parallel on the GPU). */
@@ -74,18 +78,17 @@ static uint64_t e0_hash_obs(const orc_config *c, const int8_t *board, int player
     const uint64_t h0 = mix64(c->eval_seed ^ E0_GOLD);
     uint64_t acc = 0;
     for (int w = 0; w < nw; ++w) {
-        acc ^= mix64((own[w] ^ h0) + (uint64_t)(2 * w + 1) * E0_GOLD);
-        acc ^= mix64((opp[w] ^ h0) + (uint64_t)(2 * w + 2) * E0_GOLD);
+        acc ^= ((own[w] ^ h0) + (uint64_t)(2 * w + 1) * E0_GOLD) * E0_K1;            /* one odd multiply per plane word; */
+        acc ^= rot32(((opp[w] ^ h0) + (uint64_t)(2 * w + 2) * E0_GOLD) * E0_K2);     /* the final mix64 avalanches       */
     }
     return mix64(acc + (uint64_t)(int64_t)(last_move + 1) * E0_CV);
 }
 
-/* per-action 32-bit hash (two multiplies; only the high bits are used) */
+/* per-action 32-bit hash (one multiply; only the high bits are used) */
 static inline uint32_t e0_action_hash(uint32_t s, int a)
 {
     uint32_t x = s + (uint32_t)(a + 1) * 0x9E3779B1u;
     x ^= x >> 16; x *= 0x7FEB352Du;
-    x ^= x >> 15; x *= 0x846CA68Bu;
     return x;
 }
 

@@ -4,11 +4,14 @@ reference's inference-queue protocol (mcts.py:73-85, tests/test_mcts_logic.py:26
 Used (a) by make_golden.py to drive the imported reference and (b) by CPU tests to check
 that the C oracle's and the CUDA engine's E0 produce the same integers.
 
-Definition (round 2; cheap on a GPU: the board hash is order-free over the words, the per-action
-hash is 32-bit):
+Definition (round 2, third version; cheap on a GPU: the board hash is order-free over the words with ONE
+odd-constant multiply per plane word -- a bijection of the word, so two positions differing in one word never
+collide before the final mix, and the final mix64 gives the avalanche -- and the per-action hash is 32-bit with
+one multiply, its top bits being what the heads use):
     h0 = mix64(seed ^ GOLD)
-    h  = mix64( XOR_w [ mix64((own_w ^ h0) + (2w+1) GOLD) ^ mix64((opp_w ^ h0) + (2w+2) GOLD) ]  +  (last+1) CV )
-    s  = lo32(h) ^ hi32(h);   x_a = lowbias32-style mix of  s + (a+1) * 0x9E3779B1   (two multiplies)
+    h  = mix64( XOR_w [ ((own_w ^ h0) + (2w+1) GOLD) K1  ^  rot32(((opp_w ^ h0) + (2w+2) GOLD) K2) ]  +  (last+1) CV )
+         K1, K2 = mix64's two multipliers, rot32 = swap of the 32-bit halves
+    s  = lo32(h) ^ hi32(h);   y = s + (a+1) * 0x9E3779B1;   x_a = (y ^ (y >> 16)) * 0x7FEB352D   (mod 2^32)
     logit_div > 0 (quantised):  logit_a = ((x_a >> 26) - 32) / logit_div       value = (((h >> 40) % 33) - 16) / 16
                                 reward  = ((((h >> 16) & 0xFFFFFF) % 5) - 2) / 16
     logit_div = 0 (dense):      logit_a = ((x_a >> 8) - 2^23) * 2^-21  in [-4, 4)   -- 24 random mantissa bits
@@ -30,17 +33,22 @@ M64 = (1 << 64) - 1
 GOLD = 0x9E3779B97F4A7C15
 CV = 0xD1B54A32D192ED03
 CA = 0x8CB92BA72F3D8DD7
-GOLD32, M1_32, M2_32 = 0x9E3779B1, 0x7FEB352D, 0x846CA68B
+K1, K2 = 0xBF58476D1CE4E5B9, 0x94D049BB133111EB
+GOLD32, M1_32 = 0x9E3779B1, 0x7FEB352D
 
 
 def mix64(z: int) -> int:
     z &= M64
     z ^= z >> 30
-    z = (z * 0xBF58476D1CE4E5B9) & M64
+    z = (z * K1) & M64
     z ^= z >> 27
-    z = (z * 0x94D049BB133111EB) & M64
+    z = (z * K2) & M64
     z ^= z >> 31
     return z
+
+
+def rot32(z: int) -> int:
+    return ((z << 32) | (z >> 32)) & M64
 
 
 def _words(plane_bits: np.ndarray, nw: int):
@@ -59,8 +67,8 @@ def hash_obs(obs: np.ndarray, seed: int) -> int:
     h0 = mix64((seed & M64) ^ GOLD)
     acc = 0
     for w in range(nw):
-        acc ^= mix64((own[w] ^ h0) + (2 * w + 1) * GOLD)
-        acc ^= mix64((opp[w] ^ h0) + (2 * w + 2) * GOLD)
+        acc ^= (((own[w] ^ h0) + (2 * w + 1) * GOLD) * K1) & M64
+        acc ^= rot32((((opp[w] ^ h0) + (2 * w + 2) * GOLD) * K2) & M64)
     return mix64(acc + (last + 1) * CV)
 
 
@@ -71,8 +79,6 @@ def action_hash(h: int, A: int) -> np.ndarray:
         x = s + np.arange(1, A + 1, dtype=np.uint32) * np.uint32(GOLD32)
         x ^= x >> np.uint32(16)
         x *= np.uint32(M1_32)
-        x ^= x >> np.uint32(15)
-        x *= np.uint32(M2_32)
     return x
 
 

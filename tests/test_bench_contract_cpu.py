@@ -52,3 +52,17 @@ def test_reference_install_is_unmodified():
     from baseline import install_reference, ref_runner
     if ref_runner.available():
         assert install_reference.verify()
+
+
+def test_reference_in_process_network_runner():
+    """one reference process with the reference's own network answering its queue
+    protocol in-process -- a few moves at a tiny size, in both search modes (on the CPU here, on the B200 in the bench)."""
+    sys.path.insert(0, ROOT)
+    import pytest
+    from baseline import ref_runner
+    if not ref_runner.available():
+        pytest.skip("baseline/_ref not installed")
+    for mode in ("AlphaZero", "MuZero"):
+        r = ref_runner.inprocess_net(seconds=1.0, N=6, S=16, K=4, mode=mode)
+        assert r["moves"] >= 1 and r["sims_per_sec"] > 0 and r["evaluator_calls"] >= r["moves"] * (16 if mode == "AlphaZero" else 2)
+        assert mode in r["what"]

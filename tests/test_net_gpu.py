@@ -212,3 +212,66 @@ def test_bf16_network_against_fp32_network_at_8x128():
     assert rep["bf16"]["max_abs_dpolicy"] < 0.02 and rep["bf16"]["max_abs_dvalue"] < 0.05, rep
     assert rep["tf32"]["max_abs_dpolicy"] <= rep["bf16"]["max_abs_dpolicy"] + 1e-3, rep
     assert rep["bf16"]["move_agreement"] > 0.5 and rep["bf16"]["mean_visit_l1"] < 0.35, rep
+
+
+def test_selfplay_with_the_network_play_equals_stepping():
+    """SelfPlayEngine with a GomokuNetEZ evaluator (the production path of universal_worker, workers.py:129-241):
+    play(sink=...) -- lock-step network searches cut into chunks, finished games packed on the device and handed
+    to the sink -- produces exactly the games a plain loop of step() calls does, every game is a legal finished
+    Gomoku game, and the trajectories land in a DeviceReplayBuffer ready to be sampled."""
+    import torch
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.game import GomokuGame
+    from datou_gomoku_muzero_b200.network import NetworkSearch
+    from datou_gomoku_muzero_b200.replay_buffer import DeviceReplayBuffer
+    from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+    from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
+    N, S, G, moves = 6, 20, 16, 30
+    net = _net(3, n=N, blocks=1, ch=16)
+
+    def run(chunked):
+        e = SearchEngine(G, board_size=N, num_simulations=S, n_in_row=4, accum_dtype="float32")
+        sp = SelfPlayEngine(e, net if chunked else NetworkSearch(e, net), noise_seed=77)
+        assert sp.ns is not None
+        traj = TrajectoryStore(e, extra_slots=8 * G)
+        got = []
+        if chunked:
+            sp.play(moves_per_game=moves, traj=traj, sink=got.append, chunk=7)
+        else:
+            for _ in range(moves):
+                sp.step(traj=traj)
+            got.append(traj.pack_finished(recycle=True))
+        assert sp.moves_played == G * moves
+        games = {}
+        for pk in got:
+            for i in range(len(pk)):
+                games.setdefault(int(pk.table[i][1]), []).append(pk.game(i).copy())
+        return games, got, e
+
+    ga, packs, e = run(True)
+    gb, _, _ = run(False)
+    assert sum(len(v) for v in ga.values()) >= G // 2 and set(ga) == set(gb)
+    for g in ga:
+        assert len(ga[g]) == len(gb[g])
+        for a, b in zip(ga[g], gb[g]):          # field by field (numpy does not copy a structured dtype's padding; slot ids depend on recycling)
+            assert len(a) == len(b)
+            for f in a.dtype.names:
+                if f not in ("slot", "game_seq"):
+                    assert np.array_equal(a[f], b[f]), (g, f)
+    # every recorded game replays to a finished game on the host GomokuGame with the recorded winner
+    pk = packs[0]
+    for i in range(len(pk)):
+        r, gm = pk.game(i), GomokuGame(N, 4)
+        for t in range(len(r)):
+            assert np.array_equal(r["board"][t].reshape(N, N), gm.board) and gm.get_game_ended() is None
+            assert abs(float(r["policy"][t].sum()) - 1.0) < 1e-12 and r["policy"][t][int(r["action"][t])] > 0
+            gm.do_move(int(r["action"][t]))
+        assert gm.get_game_ended() is not None and int(gm.get_game_ended()) == int(pk.table[i][3])
+    buf = DeviceReplayBuffer(4096, N)
+    for p in packs:
+        buf.add_packed(p)
+    assert len(buf) == sum(p.n_moves for p in packs)
+    batch, idx, w = buf.sample(32)
+    assert batch is not None and len(idx) == 32
+    with pytest.raises(ValueError):
+        SelfPlayEngine(e, "e1")

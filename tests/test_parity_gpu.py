@@ -304,7 +304,7 @@ def test_deep_paths_match_oracle(mode):
     import torch
     from datou_gomoku_muzero_b200.engine import SearchEngine
     from oracle import oracle
-    N, S, G, seed, div = 9, 300, 12, 3, 2
+    N, S, G, seed, div = 9, 300, 12, 12, 2
     A = N * N
     rs = np.random.RandomState(4)
     boards = np.zeros((G, A), np.int8); players = np.ones(G, np.int8)
