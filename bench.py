@@ -330,7 +330,9 @@ def net_leg(eng, dev, peaks, dtype_name="bf16"):
     eng.set_roots(*staggered_positions(G, 0))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clk = ClockSampler(dev.index or 0); clk.start()
     e0.record(); ns.search(gum); eng.finalize(want_visits=False); e1.record(); torch.cuda.synchronize()
+    clk.stop_flag = True; clk.join(timeout=2)
     ms = e0.elapsed_time(e1)
     n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0.record()
@@ -367,6 +369,7 @@ def net_leg(eng, dev, peaks, dtype_name="bf16"):
                          "step {select -> network -> expand/backup}" % dtype_name,
             "accum_dtype": eng.accum_dtype,
             "sims_per_sec": G * S / (ms * 1e-3), "moves_per_sec": G / (ms * 1e-3), "ms_per_search": ms,
+            "clocks": clk.summary(),      # tensor-bound legs run into the board's power cap: the SM clock during the search says how far
             "net_forward_ms": net_ms, "tree_kernels_ms_per_sim_step": tree_ms,
             "step_minus_standalone_forward_ms": ms / S - net_ms,
             **({"selfplay": selfplay} if selfplay else {}),
@@ -389,7 +392,7 @@ def muzero_leg(dev, peaks, G):
     from datou_gomoku_muzero_b200.muzero import FoldedRecurrentInference, MuZeroDeviceSearch, evals_per_search
     from datou_gomoku_muzero_b200.network import FoldedInitialInference, GomokuNetEZ
     torch.manual_seed(0)
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = os.environ.get("GMZ_CUDNN_BENCHMARK", "1") != "0"
     cfg = Config(BOARD_SIZE=N, ACTION_SPACE_SIZE=A, NUM_RES_BLOCKS=8, NUM_FILTERS=128, HEAD_HIDDEN_DIM=64)
     net = GomokuNetEZ(cfg).to(dev).eval()
     fi, fr = FoldedInitialInference(net, torch.bfloat16), FoldedRecurrentInference(net, torch.bfloat16)
@@ -407,8 +410,10 @@ def muzero_leg(dev, peaks, G):
     mz.search(gum, max_steps=evals); eng.finalize(want_visits=False)          # warm-up: cuDNN plans + graph capture
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clk = ClockSampler(dev.index or 0); clk.start()
     e0.record(); steps = mz.search(gum, max_steps=evals); eng.finalize(want_visits=False); e1.record()
     torch.cuda.synchronize()
+    clk.stop_flag = True; clk.join(timeout=2)
     ms = e0.elapsed_time(e1)
     # the pool kernels on their own: bytes moved per launch / time, against the measured HBM peak
     parent, action, child, _ = eng._mz_out[:4]
@@ -446,6 +451,7 @@ def muzero_leg(dev, peaks, G):
                         "(BASELINE configs[2])" % G,
             "sims_per_sec": G * S / (ms * 1e-3), "moves_per_sec": G / (ms * 1e-3), "ms_per_search": ms,
             "recurrent_evals_per_search": steps, "distinct_evals_per_sec": G * (steps + 1) / (ms * 1e-3),
+            "clocks": clk.summary(),      # (this leg has measured 435 ms at 1965 MHz and 615-630 ms under sw_power_cap at ~1350 MHz)
             "hidden_pool_gb": mz.pool.numel() * mz.pool.element_size() / 1e9,
             "e0_fused": {"sims_per_sec": G * S / (e0_ms * 1e-3), "ms_per_search": e0_ms,
                          "what": "same searches with the fixed evaluator E0 inside the persistent kernel (k_play_e0<NC, MZ>)"},
@@ -564,7 +570,8 @@ def selfplay_e2e_leg(dev, rank, world, G, steps):
             batch, idx, w = buf.sample(360, rot_k=state["batches"] % 4, flip=bool(state["batches"] & 1))
             buf.update_priorities(idx, batch[4][:, 0] - 0.5)     # stand-in TD errors (device)
             state["batches"] += 1
-    sp.play(moves_per_game=8, traj=traj, sink=sink)              # warm-up
+    sp.play(moves_per_game=steps, traj=traj, sink=sink)          # warm-up of the timed length: the caching allocator then holds
+                                                                 # blocks of the sizes the timed chunk packs into (steady state)
     m0, f0 = eng.play_counters()
     if world > 1:
         dist.barrier()
