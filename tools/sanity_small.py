@@ -26,6 +26,15 @@ for N, S, G in ((6, 24, 10), (15, 40, 9), (19, 20, 5)):
     samples = store.ingest(fin)
     if samples:
         store.batch(samples[:7])
+    # packed records -> device replay ring + PER tree -> batch (float32 accumulation, dense logits)
+    e32 = SearchEngine(G, board_size=N, num_simulations=S, accum_dtype="float32")
+    sp32 = SelfPlayEngine(e32, "e0", seed=5, logit_div=0, noise_seed=6)
+    t32 = TrajectoryStore(e32, extra_slots=8)
+    ring = rb.DeviceReplayBuffer(64, N)
+    sp32.play(moves_per_game=A, traj=t32, sink=ring.add_packed, chunk=7)
+    if len(ring) >= 4:
+        (obs, act, rew, pi, val), idx, w = ring.sample(4, rot_k=1, flip=True)
+        ring.update_priorities(idx, val[:, 0] - 0.5)
     b, pl, lm, mc = eng.get_roots()
     classify_boards(b, pl, N)
     mz = SearchEngine(G, board_size=N, num_simulations=S, mode="MuZero")
@@ -33,6 +42,7 @@ for N, S, G in ((6, 24, 10), (15, 40, 9), (19, 20, 5)):
     from datou_gomoku_muzero_b200.muzero import MuZeroDeviceSearch, TorchE0
     e0 = TorchE0(N, seed=4)
     MuZeroDeviceSearch(mz, e0.initial, e0.recurrent).search(gum); mz.finalize()
+    mz.search_e0(gum, 4, 0); mz.finalize()                      # fused MuZero-mode kernel, dense heads
 config.ENABLE_PER = True
 buf = rb.InMemoryReplayBuffer(37)
 for i in range(50):
