@@ -14,6 +14,15 @@ if which == "muzero":
         r = bench.muzero_leg(dev, peaks, 4096)
         print("muzero", i, r["ms_per_search"], r["sims_per_sec"], r["tensor"]["frac"], r["e0_fused"]["sims_per_sec"], flush=True)
         torch.cuda.empty_cache()
+elif which == "net":
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    torch.backends.cudnn.benchmark = os.environ.get("GMZ_CUDNN_BENCHMARK", "0") != "0"
+    for name in sys.argv[2:] or ["bf16"]:
+        eng = SearchEngine(4096, board_size=bench.N, n_in_row=bench.N_IN_ROW, num_simulations=bench.S, num_top_actions=bench.K_TOP,
+                           device=dev, accum_dtype="float32")
+        r = bench.net_leg(eng, dev, peaks, name)
+        print("net", name, "benchmark", torch.backends.cudnn.benchmark, r["sims_per_sec"], r["net_forward_ms"], r["clocks"], r["tensor"]["frac_sustained"], flush=True)
+        del eng
 elif which == "selfplay":
     from datou_gomoku_muzero_b200.engine import SearchEngine
     from datou_gomoku_muzero_b200.replay_buffer import DeviceReplayBuffer
