@@ -68,12 +68,16 @@ def bench_config(games):
             "l2": "GPU arm: node pools (4 GB per GPU) exceed the 126 MB L2, no explicit flush; CPU arm: n/a"}
 
 
+PLAY_KERNEL_SOURCES = ("gmz_common.cuh", "gmz_tree.cuh", "gmz_play.cuh", "gmz_play_inst.cu", "gmz_internal.h")
+
+
 def kernel_source_sha():
-    """Hash of the CUDA sources: stamps `roofline.traffic` (an ncu measurement) with the kernel it was taken on."""
+    """Hash of the sources the play kernel is compiled from: stamps `roofline.traffic` (an ncu measurement) with the
+    kernel it was taken on."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "datou_gomoku_muzero_b200", "csrc")
-    for f in sorted(os.listdir(d)):
+    for f in PLAY_KERNEL_SOURCES:
         h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
 

@@ -145,6 +145,22 @@ def test_e0_kernel_matches_python():
             assert np.array_equal(lg[b], l2) and v[b] == v2, (N, b)
 
 
+def test_fused_kernels_reject_divisors_that_are_not_powers_of_two():
+    """gmz_e0_eval_obs takes any logit_div >= 0 (checked above with 3); the fused kernels compute a logit as one exact
+    multiply and say so instead of computing something else (include/gmz.h)."""
+    import torch
+    from datou_gomoku_muzero_b200._lib import GmzError
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    eng = SearchEngine(2, board_size=6, num_simulations=8)
+    gum = torch.zeros((2, 36), dtype=torch.float64, device="cuda")
+    for bad in (3, 12, -1):
+        with pytest.raises(GmzError, match="power of two"):
+            eng.search_e0(gum, 1, bad)
+        with pytest.raises(GmzError, match="power of two"):
+            eng.selfplay_e0(2, 1, bad)
+    eng.search_e0(gum, 1, 8); eng.search_e0(gum, 1, 0)
+
+
 @pytest.mark.parametrize("div,accum", [(16, "float64"), (0, "float64"), (0, "float32"), (16, "float32")])
 @pytest.mark.parametrize("N,S,G", [(9, 100, 64), (15, 400, 96), (19, 64, 16), (6, 50, 64)])
 def test_random_positions_match_oracle(N, S, G, div, accum):
