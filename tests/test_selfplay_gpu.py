@@ -294,3 +294,11 @@ def test_muzero_stepwise_selfplay_matches_persistent_kernel():
         assert np.array_equal(a["values"], b["values"]) and np.array_equal(a["policies"], b["policies"]), g
     with pytest.raises(ValueError):
         SelfPlayEngine(e2, lambda obs: None)
+    # play() drives the same stepwise loop for a learned-dynamics evaluator (lock-step moves, sink per chunk)
+    got, before = [], sp2.moves_played
+    sp2.play(moves_per_game=5, traj=t2, sink=got.append, chunk=2)
+    assert sp2.moves_played == before + 5 * G
+    for pk in got:
+        for i in range(len(pk)):
+            r = pk.game(i)
+            assert len(r) == int(pk.table[i][2]) and np.allclose(r["policy"].sum(axis=1), 1.0, atol=1e-12)
