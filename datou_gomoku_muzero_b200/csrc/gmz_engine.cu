@@ -204,10 +204,10 @@ k_select(const __grid_constant__ Params p, T *leaf_obs, int32_t *out_a, int32_t 
     int lp, la;
     const int depth = descend<NC, MZ, F32>(p, w, path, ds, s_sel[threadIdx.x >> 5], blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5), lane,
                                       lp, la);
-    if (!MZ && leaf_obs) { // the replayed position; colour = the player to move at the leaf; last move = la
-        u64 P, M;
-        const int colour = replay_path(p, w, path, ds, depth, la, lane, P, M);
-        obs_emit<NC, T>(leaf_obs + (size_t)g * 3 * p.A, p.A, colour > 0 ? P : M, colour > 0 ? M : P, la, lane);
+    if (!MZ && leaf_obs) { // the replayed position as the player to move at the leaf sees it; last move = la
+        u64 own, opp;
+        replay_path(p, w, path, ds, depth, la, lane, own, opp);
+        obs_emit<NC, T>(leaf_obs + (size_t)g * 3 * p.A, p.A, own, opp, la, lane);
     }
     if (lane < min(depth, 32)) path[lane] = lane == 0 ? make_int2(0, 0) : make_int2(ds.path[lane].node, ds.path[lane].mir);   // for k_expand_backup
     if (lane == 0) {

@@ -324,13 +324,12 @@ k_play_e0(const __grid_constant__ Params p, const __grid_constant__ PlayArgs a)
                 PathReg pr;
                 path_load<MZ>(p, w, ds, depth, pr, lane);
                 prefetch_parent_rows<NC>(p, w, lp, lane);
-                u64 P = 0, M = 0;
-                int colour = 0;
-                if (!MZ) colour = replay_path(p, w, path, ds, depth, la, lane, P, M);
+                u64 own = 0, opp = 0;
+                if (!MZ) replay_path(p, w, path, ds, depth, la, lane, own, opp);
                 // AlphaZero mode: evaluate the replayed board (mcts.py:251-253).  MuZero mode: the learned
                 // dynamics, here E0's recurrent half on the parent's hidden state (mcts.py:336-343).
                 const u64 h = MZ ? e0_child_hidden(p.nH[w.nbase + (size_t)lp], la)
-                                 : e0_hash_planes(a.e0.h0, colour > 0 ? P : M, colour > 0 ? M : P, p.NW, la, lane);
+                                 : e0_hash_planes(a.e0.h0, own, opp, p.NW, la, lane);
                 const int reps = MZ ? w.n_surv : 1;            // MuZero: len(selected) identical selections -> that many backups
                 const int nn = w.num_nodes;
                 {   // evaluate + leaf.expand fused: logits go straight into the new node's row

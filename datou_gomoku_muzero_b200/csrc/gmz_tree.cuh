@@ -777,8 +777,10 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, int2 *path,
     const double rden = rng ? rcp_newton(F32 ? mm_denom<true>(p, w.mm_min, w.mm_max) : (w.mm_max - w.mm_min) + p.delta) : 0.0, mn = rng ? w.mm_min : 0.0;
     while (node >= 0) {
         const int mir = (parent << 5) | slot;
-        if (depth < 32) {
-            if (lane == 0) { PathEntry e; e.node = node; e.mir = mir; e.n = cn; e.act = a; e.W = cW; e.R = cR; ds.path[depth] = e; }
+        if (depth < 32) {          // (every lane stores the same entry: cheaper than electing one)
+            PathEntry &e = ds.path[depth];
+            e.node = node; e.mir = mir; e.n = cn; e.act = a; e.W = cW;
+            if (MZ) e.R = cR;
         } else if (lane == 0) path[depth] = make_int2(node, mir | (a << 20));
         int c;
         select_interior<NC, MZ, F32>(p, w, nbase, node, lane, sc, warp_slot, mn, rden, a, c, slot, cn, cW, cR);
@@ -791,19 +793,29 @@ __device__ __forceinline__ int descend(const Params &p, const WG &w, int2 *path,
 
 // The position at the leaf (AlphaZero mode, mcts.py:236-248): the root bitboards with the path's moves replayed on
 // them, AFTER the descent -- nothing of it is live across the selects, and the actions come out of shared memory
-// as independent loads.  Lane w ends up with word w of the +1 / -1 stones; returns the player to move at the leaf.
-__device__ __forceinline__ int replay_path(const Params &p, const WG &w, const int2 *path, const DescSmem &ds, int depth, int leaf_action,
-                                           int lane, u64 &P, u64 &M)
+// as independent loads.  The boards are kept RELATIVE to the player about to move (`mine`, `theirs`): a move sets the
+// mover's bit and clears the other's (GomokuGame.do_move overwrites, game.py:20-23), then the roles swap -- two plies per
+// iteration make the swap a renaming.  Lane w ends up with word w of the planes the evaluator sees at the leaf:
+// own = the stones of the player to move there, opp = the other's (game.py:12-17).
+__device__ __forceinline__ void bb_place(u64 &mover, u64 &other, int a, int lane)
 {
-    P = lane < GMZ_WORDS ? w.rP[lane] : 0ull;
-    M = lane < GMZ_WORDS ? w.rM[lane] : 0ull;
-    int colour = w.to_move;
-    for (int d = 1; d < depth; ++d) {
-        const int a = d < 32 ? ds.path[d].act : (path[d].y >> 20);
-        bb_do_move(P, M, colour, a, lane); colour = -colour;
+    const u64 b = lane == (a >> 6) ? 1ull << (a & 63) : 0ull;
+    mover |= b; other &= ~b;
+}
+__device__ __forceinline__ void replay_path(const Params &p, const WG &w, const int2 *path, const DescSmem &ds, int depth, int leaf_action,
+                                            int lane, u64 &own, u64 &opp)
+{
+    const u64 rP = lane < GMZ_WORDS ? w.rP[lane] : 0ull, rM = lane < GMZ_WORDS ? w.rM[lane] : 0ull;
+    u64 mine = w.to_move > 0 ? rP : rM, theirs = w.to_move > 0 ? rM : rP;
+    // moves 1 .. depth-1 are the path's, move `depth` is the leaf action
+    auto move_at = [&](int d) { return d < depth ? (d < 32 ? ds.path[d].act : (path[d].y >> 20)) : leaf_action; };
+    int d = 1;
+    for (; d < depth; d += 2) {
+        bb_place(mine, theirs, move_at(d), lane);
+        bb_place(theirs, mine, move_at(d + 1), lane);
     }
-    bb_do_move(P, M, colour, leaf_action, lane);
-    return -colour;
+    if (d == depth) { bb_place(mine, theirs, leaf_action, lane); own = theirs; opp = mine; }     // odd number of plies: the roles end swapped
+    else { own = mine; opp = theirs; }
 }
 
 // The descent's path into registers for the backup: lane d <- position d.  The root (lane 0) and the root child
