@@ -89,7 +89,8 @@ class SelfPlayEngine:
         network batch of G per simulation).  Without `sink` the caller harvests finished games from `traj`
         (games that finish when no trajectory slot is free park until slots are released).  With `sink` -- a
         callable taking a trajectory.PackedGames, e.g. `DeviceReplayBuffer.add_packed` -- the run is cut into
-        pieces of `chunk` moves per game (default: what the store's spare slots absorb, at most 48) and after
+        pieces of `chunk` moves per game (default: what the store's spare slots absorb, at most 48; 1 for a network
+        evaluator) and after
         each one the finished games are packed on the device, handed to the sink and their slots recycled, so a
         run of any length never parks a game."""
         e = self.e
@@ -106,6 +107,8 @@ class SelfPlayEngine:
         if sink is None or traj is None:
             advance(total)
             return
+        if chunk is None and not self._e0:
+            chunk = 1              # lock-step games finish in bursts and a move costs S network batches: pack after every move
         if chunk is None:          # a game ends about every A/3 moves at the earliest in practice; spare slots absorb the finishes
             spare = max(1, traj.n_slots - e.G)
             chunk = int(max(4, min(48, spare * (e.A // 3) // max(1, e.G))))
