@@ -60,6 +60,30 @@ def reanalyse(game_records, batch_search, board_size=None, gumbel_fn=None):
     return out
 
 
+def writeback_windows(new_policies, new_value_targets, unroll_steps=None):
+    """The write-back format of a re-analysed game (db_manager.py:189-203, `finish_reanalysis_for_game`): for every move
+    t the window of U + 1 policies / value targets starting at t, zero-padded past the end of the game -- what replaces
+    `policy_history` / `value_history` of the stored TrainingSlice of move t.  Returns (policy windows float64
+    [T, U+1, A], value windows float32 [T, U+1])."""
+    U = int(config.NUM_UNROLL_STEPS if unroll_steps is None else unroll_steps)
+    pol = np.asarray(new_policies, dtype=np.float64)
+    T, A = pol.shape
+    val = np.asarray(new_value_targets, dtype=np.float64)
+    win = np.lib.stride_tricks.sliding_window_view
+    pw = win(np.concatenate([pol, np.zeros((U, A), np.float64)]), U + 1, axis=0)           # [T, A, U+1]
+    vw = win(np.concatenate([val, np.zeros(U, np.float64)]), U + 1)                         # [T, U+1]
+    return np.ascontiguousarray(np.moveaxis(pw, -1, 1)), vw.astype(np.float32)
+
+
+def apply_writeback(slices, new_policies, new_value_targets, unroll_steps=None):
+    """`original_slice._replace(policy_history=..., value_history=...)` for every stored slice of the game
+    (db_manager.py:209-214); `slices` in move order."""
+    pw, vw = writeback_windows(new_policies, new_value_targets, unroll_steps)
+    if len(slices) != len(pw):
+        raise ValueError("one stored slice per move expected")
+    return [s._replace(policy_history=pw[t], value_history=vw[t]) for t, s in enumerate(slices)]
+
+
 def reanalyse_positions(engines, boards, players, last_moves, move_counts, evaluator="e0", eval_seed=0, logit_div=16,
                         noise_seed=0, gumbel=None, want_policies=True, cls=None):
     """Re-search `n` stored positions (host arrays: boards int8 [n, A], players [n], last_moves [n], move_counts [n])

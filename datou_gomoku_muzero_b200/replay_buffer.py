@@ -164,6 +164,7 @@ class DeviceReplayBuffer:
                           data_loader_worker stacks (workers.py:430-433); rot_k / flip apply the trainer's D4
                           augmentation while gathering (loss.py:37-51)
     update_priorities  = replay_buffer.py:98-103 on device tensors (td_errors float32, as the loss returns them)
+    rewrite_targets    = the re-analysis write-back (db_manager.py:189-214) for records in the ring
     """
 
     def __init__(self, capacity, board_size, device=None, unroll_steps=None):
@@ -217,6 +218,21 @@ class DeviceReplayBuffer:
                                          _ptr(obs), _ptr(act), _ptr(rew), _ptr(pi), _ptr(val), self.sum_tree._stream()),
               "gmz_records_batch")
         return obs, act, rew, pi, val
+
+    def rewrite_targets(self, positions, policies, value_targets):
+        """Re-analysis write-back (db_manager.py:189-214) for records resident in the ring: the policy and the value
+        target of the move stored at each ring position are replaced; every slice that covers the move -- slices are
+        assembled from consecutive records when a batch is built -- then carries the new window.  positions int64 [M],
+        policies float64 [M, A], value_targets float32 [M] (host or device)."""
+        pos = self.sum_tree._dev(positions, torch.int64).reshape(-1)
+        pol = self.sum_tree._dev(policies, torch.float64).reshape(pos.numel(), self.A).contiguous()
+        val = self.sum_tree._dev(value_targets, torch.float32).reshape(pos.numel()).contiguous()
+        if pos.numel() == 0:
+            return
+        if int(pos.min()) < 0 or int(pos.max()) >= self.capacity:
+            raise ValueError("ring position out of range")
+        self.ring[pos, 64:64 + 8 * self.A] = pol.view(torch.uint8).reshape(pos.numel(), 8 * self.A)      # gmz_move_record: policy f64[A]
+        self.ring[pos, 36:40] = val.view(torch.uint8).reshape(pos.numel(), 4)                             # header: value_target f32
 
     def update_priorities(self, tree_indices, td_errors):
         if not config.ENABLE_PER:

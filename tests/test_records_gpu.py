@@ -152,3 +152,41 @@ def test_long_selfplay_run_through_a_sink_never_parks():
     assert moves == G * 150 and eng.tickets_unserved == 0 and eng.tickets_idle == 0
     assert sum(g for g, _ in got) == nfin and nfin > 3 * G and len(got) > 10
     assert len(buf) == sum(m for _, m in got) <= moves
+
+
+def test_reanalysis_writeback_into_the_device_ring():
+    """DeviceReplayBuffer.rewrite_targets = the re-analysis write-back (db_manager.py:189-214) for records resident on
+    the device: after it, the batches built from the ring carry exactly the windows `writeback_windows` produces for the
+    new policies / value targets, and nothing else of the records changes."""
+    import torch
+    from datou_gomoku_muzero_b200.config import config
+    from datou_gomoku_muzero_b200.engine import SearchEngine
+    from datou_gomoku_muzero_b200.reanalysis import writeback_windows
+    from datou_gomoku_muzero_b200.replay_buffer import DeviceReplayBuffer
+    from datou_gomoku_muzero_b200.selfplay import SelfPlayEngine
+    from datou_gomoku_muzero_b200.trajectory import TrajectoryStore
+    N, S, G = 6, 12, 16
+    A, U = N * N, int(config.NUM_UNROLL_STEPS)
+    eng = SearchEngine(G, board_size=N, num_simulations=S)
+    sp = SelfPlayEngine(eng, "e0", seed=4, noise_seed=5)
+    traj = TrajectoryStore(eng, extra_slots=32)
+    buf = DeviceReplayBuffer(4096, N)
+    packs = []
+    sp.play(moves_per_game=40, traj=traj, sink=lambda pg: (packs.append(pg), buf.add_packed(pg)))
+    pg = packs[0]
+    assert len(pg) >= 1
+    T = int(pg.offsets[1] - pg.offsets[0])                       # first game of the first pack sits at ring positions 0 .. T-1
+    before = buf.ring[:T + 3].clone()
+    rs = np.random.RandomState(9)
+    new_pol = rs.dirichlet(np.ones(A), size=T)
+    new_val = rs.uniform(-1, 1, T).astype(np.float32)
+    buf.rewrite_targets(np.arange(T), new_pol, new_val)
+    obs, act, rew, pi, val = buf.batch(torch.arange(T, device="cuda"))
+    pw, vw = writeback_windows(new_pol, new_val.tolist(), unroll_steps=U)
+    assert np.array_equal(pi.cpu().numpy(), pw) and np.array_equal(val.cpu().numpy(), vw)
+    after = buf.ring[:T + 3]
+    changed = (after != before).any(dim=0).nonzero().flatten().cpu().numpy()
+    assert set(changed) <= set(range(36, 40)) | set(range(64, 64 + 8 * A))      # only value_target and policy bytes
+    assert torch.equal(after[T:], before[T:])                                   # the next game's records are untouched
+    with pytest.raises(ValueError):
+        buf.rewrite_targets([buf.capacity], new_pol[:1], new_val[:1])
