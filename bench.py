@@ -71,14 +71,21 @@ def bench_config(games):
 PLAY_KERNEL_SOURCES = ("gmz_common.cuh", "gmz_tree.cuh", "gmz_play.cuh", "gmz_play_inst.cu", "gmz_internal.h")
 
 
-def kernel_source_sha():
-    """Hash of the sources the play kernel is compiled from: stamps `roofline.traffic` (an ncu measurement) with the
-    kernel it was taken on."""
+def _strip_comments(text):
+    import re
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    return "\n".join(l.rstrip() for l in text.split("\n") if l.strip())
+
+
+def kernel_source_sha(read=None):
+    """Hash of the sources the play kernel is compiled from, comments and blank lines removed: stamps `roofline.traffic`
+    (an ncu measurement) with the kernel it was taken on.  `read(name) -> str` overrides where the sources come from."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "datou_gomoku_muzero_b200", "csrc")
     for f in PLAY_KERNEL_SOURCES:
-        h.update(open(os.path.join(d, f), "rb").read())
+        h.update(_strip_comments(read(f) if read else open(os.path.join(d, f)).read()).encode())
     return h.hexdigest()[:16]
 
 

@@ -66,3 +66,17 @@ def test_reference_in_process_network_runner():
         r = ref_runner.inprocess_net(seconds=1.0, N=6, S=16, K=4, mode=mode)
         assert r["moves"] >= 1 and r["sims_per_sec"] > 0 and r["evaluator_calls"] >= r["moves"] * (16 if mode == "AlphaZero" else 2)
         assert mode in r["what"]
+
+
+def test_traffic_stamp_is_current_and_ignores_comments():
+    """`roofline.traffic` is an ncu measurement: profiles/traffic.json names the play-kernel sources it was taken on
+    (comments and blank lines do not count) and must match the sources in the tree."""
+    sys.path.insert(0, ROOT)
+    import bench
+    tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert tj["kernel_source_sha"] == bench.kernel_source_sha()
+    src = {f: open(os.path.join(ROOT, "datou_gomoku_muzero_b200", "csrc", f)).read() for f in bench.PLAY_KERNEL_SOURCES}
+    commented = dict(src, **{"gmz_play.cuh": "// a remark\n\n" + src["gmz_play.cuh"] + "\n/* another\n one */\n"})
+    changed = dict(src, **{"gmz_play.cuh": src["gmz_play.cuh"].replace("GMZ_PLAY_MIN_CTAS 28", "GMZ_PLAY_MIN_CTAS 27")})
+    assert bench.kernel_source_sha(commented.__getitem__) == bench.kernel_source_sha()
+    assert bench.kernel_source_sha(changed.__getitem__) != bench.kernel_source_sha()
