@@ -56,7 +56,7 @@ def _random_position(N, n_moves, rs, game_mod, n_in_row):
 
 def _search_cases(N):
     A = N * N
-    base = dict(S={6: 50, 9: 100, 15: 400}[N], K=16)
+    base = dict(S={6: 50, 9: 100, 15: 400, 19: 200}[N], K=16)      # 19x19 = the largest board the engine takes
     cases = []
     for n_moves in [0, 1, 2, 7, A // 3, A // 2, A - 20, A - 9, A - 3, A - 1]:
         cases.append(dict(base, n_moves=n_moves))
@@ -71,10 +71,10 @@ def _search_cases(N):
     cases.append(dict(base, n_moves=5, discount=1.0, delta=0.01))
     cases.append(dict(base, n_moves=5, kind=1, const_value=0.5))       # MockModel
     cases.append(dict(base, n_moves=5, kind=1, const_value=1.5, const_reward=0.25))  # exercises the clip
-    if N == 15:
+    if N >= 15:
         cases = cases[:10] + cases[10:16:2] + cases[-6:]
     # dense (unquantised) logits / values: logit_div = 0 -- what a real network's outputs look like
-    for n_moves in ([0, 5, A // 3, A - 9] if N != 15 else [0, 9, A // 2]):
+    for n_moves in ([0, 5, A // 3, A - 9] if N < 15 else [0, 9, A // 2]):
         cases.append(dict(base, n_moves=n_moves, logit_div=0))
     # the production dtype: the evaluator returns np.float32 scalars like the reference's inference server
     # (workers.py:355,368) -> float32 value_sum / Q / MinMaxStats under NumPy >= 2
@@ -83,7 +83,7 @@ def _search_cases(N):
            dict(base, n_moves=A - 5, logit_div=0), dict(base, n_moves=3, logit_div=0, K=8),
            dict(base, n_moves=7, logit_div=0, S=33), dict(base, n_moves=5, logit_div=0, discount=1.0, delta=0.01),
            dict(base, n_moves=5, kind=1, const_value=0.5), dict(base, n_moves=5, kind=1, const_value=1.5, const_reward=0.25)]
-    if N == 15:
+    if N >= 15:
         f32 = f32[:2] + f32[3:7] + f32[-2:]
     cases += [dict(c, vdtype=1) for c in f32]
     return cases
@@ -452,7 +452,7 @@ def _sub(*args):
 if __name__ == "__main__":
     cmd = sys.argv[1] if len(sys.argv) > 1 else "all"
     if cmd == "all":
-        for N in (6, 9, 15):
+        for N in (6, 9, 15, 19):
             _sub("search_az", N); _sub("search_mz", N)
         _sub("selfplay", 6, 36, 11, "az"); _sub("selfplay", 9, 100, 12, "az"); _sub("selfplay", 6, 50, 13, "mz")
         _sub("selfplay", 9, 64, 14, "az", 0, 1); _sub("selfplay", 6, 50, 15, "mz", 0, 1)

@@ -6,7 +6,7 @@ from _golden_util import load_search_cases
 def test_evals_per_search_matches_reference_request_counts():
     from datou_gomoku_muzero_b200.muzero import evals_per_search
     n = 0
-    for N in (6, 9, 15):
+    for N in (6, 9, 15, 19):
         for c in load_search_cases("mz", N):
             n_valid = int((c["board"] == 0).sum())
             assert evals_per_search(c["S"], c["K"], min(c["K"], n_valid)) == c["n_recurrent"], (N, c["idx"])
@@ -21,7 +21,7 @@ def test_torch_e0_matches_python_e0():
     import e0_py
     from datou_gomoku_muzero_b200.muzero import TorchE0
     rs = np.random.RandomState(2)
-    for N in (6, 9, 15):
+    for N in (6, 9, 15, 19):
         A = N * N
         B = 12
         obs = np.zeros((B, 3, N, N), np.float32)
@@ -32,7 +32,7 @@ def test_torch_e0_matches_python_e0():
                 a = rs.randint(A); obs[b, 2, a // N, a % N] = 1
         if N == 15:
             obs[0, 0].reshape(-1)[63] = 1; obs[0, 1].reshape(-1)[63] = 0      # exercise the sign bit of a word
-        seed, div = int(rs.randint(1 << 30)), [0, 4, 16][[6, 9, 15].index(N)]
+        seed, div = int(rs.randint(1 << 30)), [0, 4, 16, 2][[6, 9, 15, 19].index(N)]
         e0 = TorchE0(N, seed=seed, logit_div=div, device="cpu")
         lg, v, h = e0.initial(torch.from_numpy(obs))
         acts = torch.from_numpy(rs.randint(0, A, size=B))

@@ -20,7 +20,7 @@ def _cfg(c):
 
 
 @pytest.mark.parametrize("mode", ["az", "mz"])
-@pytest.mark.parametrize("N", [6, 9, 15])
+@pytest.mark.parametrize("N", [6, 9, 15, 19])
 def test_search_matches_reference(mode, N):
     cases = load_search_cases(mode, N)
     assert len(cases) >= 19
@@ -46,7 +46,7 @@ def test_search_matches_reference(mode, N):
 def test_e0_python_and_c_agree():
     import e0_py
     rs = np.random.RandomState(0)
-    for N in (6, 9, 15):
+    for N in (6, 9, 15, 19):
         A = N * N
         for trial in range(20):
             board = rs.randint(-1, 2, size=A).astype(np.int8)

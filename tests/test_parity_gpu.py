@@ -35,7 +35,7 @@ def _check(c, pol, val, act, vis, ta, td, tag):
     np.testing.assert_allclose(pol, c["policy"], rtol=RTOL, atol=1e-12, err_msg=tag)
 
 
-@pytest.mark.parametrize("N", [6, 9, 15])
+@pytest.mark.parametrize("N", [6, 9, 15, 19])
 def test_fused_search_matches_reference_goldens(N):
     for c in [c for c in load_search_cases("az", N) if c["kind"] == 0]:
         eng = _engine(c, G=3)
@@ -47,10 +47,10 @@ def test_fused_search_matches_reference_goldens(N):
             _check(c, pol[g], val[g], act[g], vis[g], ta[g], td[g], f"fused az N={N} case {c['idx']} game {g}")
 
 
-@pytest.mark.parametrize("N", [6, 9, 15])
+@pytest.mark.parametrize("N", [6, 9, 15, 19])
 def test_stepwise_search_matches_reference_goldens(N):
     cases = [c for c in load_search_cases("az", N) if c["kind"] == 0]
-    if N == 15:
+    if N >= 15:
         cases = cases[::3]
     for c in cases:
         eng = _engine(c, G=2)
@@ -62,7 +62,7 @@ def test_stepwise_search_matches_reference_goldens(N):
                    None if td is None else td[g].cpu().numpy(), f"stepwise az N={N} case {c['idx']} game {g}")
 
 
-@pytest.mark.parametrize("N", [6, 9, 15])
+@pytest.mark.parametrize("N", [6, 9, 15, 19])
 def test_constant_evaluator_goldens(N):
     """MockModel-style evaluator (tests/test_mcts_logic.py:60-80): logits 0, value const (incl. > 1 -> clip)."""
     import torch
@@ -79,7 +79,7 @@ def test_constant_evaluator_goldens(N):
         _check(c, pol[0], val[0], act[0], vis[0], None, None, f"const az N={N} case {c['idx']}")
 
 
-@pytest.mark.parametrize("N", [6, 9, 15])
+@pytest.mark.parametrize("N", [6, 9, 15, 19])
 def test_muzero_search_matches_reference_goldens(N):
     """MuZero mode through gmz_select_mz / gmz_expand_backup with the E0 recurrent evaluator run
     on the host (hidden state = 64-bit hash per node slot)."""
