@@ -13,3 +13,7 @@ rm -f gpurun_out/soak_final.jsonl
 (timeout 400 python tools/soak_parity.py --batches 4 --divs 2,0 --accum float64 --sims 1600 --games 1024 | tail -1 >> gpurun_out/soak_final.jsonl) 2>> gpurun_out/soak_final.err
 (timeout 400 python tools/soak_parity.py --batches 4 --divs 0,16 --accum float32 --board 19 --top 32 --sims 200 --games 2048 | tail -1 >> gpurun_out/soak_final.jsonl) 2>> gpurun_out/soak_final.err
 cut -c1-400 gpurun_out/soak_final.jsonl
+# optional (6 min): the production-mode soak, 1 024 000 searches -> last line of profiles/r02_soak_parity.jsonl
+if [ -n "$GMZ_LONG_SOAK" ]; then
+(timeout 1200 python tools/soak_parity.py --batches 250 --divs 0,0,16 --accum float32 | tail -1 >> gpurun_out/soak_final.jsonl) 2>> gpurun_out/soak_final.err
+fi
