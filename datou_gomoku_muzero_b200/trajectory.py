@@ -158,10 +158,10 @@ class TrajectoryStore:
         lens = np.minimum(q[:, 2], self.max_moves).astype(np.int64)
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         stride = int(e.lib.gmz_move_record_bytes(e.N))
-        # allocated in buckets of 8192 records: chunks of similar size then reuse the caching allocator's blocks (a fresh
-        # cudaMalloc of a few hundred MB costs ~100 ms, 300x the pack kernel itself)
+        # allocated in power-of-two buckets (>= 8192 records): chunks of similar size then reuse the caching allocator's
+        # blocks (a fresh cudaMalloc of a few hundred MB costs ~100 ms, 300x the pack kernel itself)
         M = int(off[-1])
-        rec = torch.empty(((M + 8191) // 8192 * 8192, stride), dtype=torch.uint8, device=e.device)[:M]
+        rec = torch.empty((max(8192, 1 << (M - 1).bit_length()), stride), dtype=torch.uint8, device=e.device)[:M]
         off_d = torch.as_tensor(off[:-1].copy(), device=e.device)
         dpow = torch.tensor([config.DISCOUNT ** i for i in range(config.N_STEPS + 1)], dtype=torch.float64, device=e.device)
         check(e.lib.gmz_traj_pack(C.byref(self.c), e.N, self.fin_queue.data_ptr(), n, off_d.data_ptr(), dpow.data_ptr(),
